@@ -1,0 +1,176 @@
+/*
+ * ldpc_b200.h -- C ABI of the B200-native LDPC message-passing engine.
+ *
+ * This is the drop-in boundary.  The reference project
+ * (BananaFalls/LDPC-NeuralNetwork-Decoder) has no FFI layer: its boundary is the Python
+ * class API.  Each entry point below states the reference interface it replaces
+ * (paths relative to /root/reference/ldpc_neural_decoder).  The Python classes in
+ * ldpc-neuralnetwork-decoder_b200/{models,utils} keep the reference signatures and call
+ * these functions through ctypes (see INTEGRATION.md for the binding).
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes; no torch / ATen / pybind types.
+ *  - Every function returns 0 on success or a negative ldpc_status code; the message of
+ *    the last failure on the calling thread is returned by ldpc_last_error().
+ *  - Device pointers are caller-owned (e.g. torch.Tensor.data_ptr()); the library never
+ *    frees or retains them.  `stream` is a cudaStream_t passed as void*; launches are
+ *    asynchronous on that stream unless the function name ends in _host.
+ *  - There is no CPU fallback: without a CUDA device every compute entry point fails
+ *    with LDPC_ERR_CUDA.
+ *  - LLR sign convention is the reference's: bit = 1  <=>  belief < 0
+ *    (models/traditional_decoders.py:99,252).
+ */
+#ifndef LDPC_B200_H
+#define LDPC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LDPC_B200_ABI_VERSION 1
+
+typedef enum ldpc_status {
+    LDPC_OK = 0,
+    LDPC_ERR_INVALID = -1,     /* bad argument                                   */
+    LDPC_ERR_UNSUPPORTED = -2, /* valid request the engine has no kernel for     */
+    LDPC_ERR_CUDA = -3,        /* CUDA runtime error (message has the detail)    */
+    LDPC_ERR_NOMEM = -4
+} ldpc_status;
+
+/* hard-decision output formats */
+#define LDPC_HARD_F32 0    /* float32 0.0/1.0, [B,N]  (what the reference returns)        */
+#define LDPC_HARD_U8 1     /* uint8 0/1, [B,N]                                            */
+#define LDPC_HARD_PACKED 2 /* uint32 words, [B, ceil(N/32)], bit n%32 of word n/32        */
+
+/* stopping rules */
+#define LDPC_STOP_FIXED 0        /* run exactly `iters` iterations                          */
+#define LDPC_STOP_PER_CODEWORD 1 /* freeze a codeword once its syndrome is zero             */
+/* The reference's batch-global rule (stop when EVERY codeword of the batch is valid,
+ * traditional_decoders.py:102-106,255-258) is built by the caller from `valid_mask`.     */
+
+/* kernel selection */
+#define LDPC_PATH_AUTO 0  /* fastest kernel that supports the code                          */
+#define LDPC_PATH_EXACT 1 /* table-driven kernel, reference operation order (any QC code)   */
+#define LDPC_PATH_FAST 2  /* register/shuffle kernel specialised for a shipped 5G table     */
+
+#define LDPC_ALGO_MINSUM 0
+#define LDPC_ALGO_BP 1
+
+typedef struct ldpc_code ldpc_code_t; /* opaque: base-graph shift tables resident on one device */
+
+/* ---- library ---------------------------------------------------------------------- */
+int ldpc_abi_version(void);
+const char* ldpc_last_error(void);
+/* number of CUDA kernels this library has launched in this process (bench `gpu_launches`) */
+uint64_t ldpc_launch_count(void);
+
+/* ---- code tables -------------------------------------------------------------------
+ * Replaces utils/ldpc_utils.py:97-125 (expand_base_matrix: dense H is never built) and the
+ * adjacency scans traditional_decoders.py:26-40,161-175 / message_gnn_decoder.py:382-408.
+ * shifts: [rows*cols] row-major, -1 = zero block, otherwise 0 <= shift < Z.
+ * Lifting convention (ldpc_utils.py:121-123): check i*Z+r  <->  variable j*Z+((r+s) mod Z).
+ * 1 <= Z <= 32.  Tables go to __constant__ memory when they fit a slot, else to global. */
+int ldpc_code_create(const int16_t* shifts, int rows, int cols, int Z, int device, ldpc_code_t** out);
+int ldpc_code_destroy(ldpc_code_t* code);
+/* info[0..7] = rows, cols, Z, base edges, N=cols*Z, M=rows*Z, max row degree, max col degree */
+int ldpc_code_info(const ldpc_code_t* code, int32_t info[8]);
+/* 1 if the specialised (LDPC_PATH_FAST) kernels cover this code/algorithm */
+int ldpc_code_has_fast_path(const ldpc_code_t* code, int algo);
+
+/* ---- classic decoders --------------------------------------------------------------
+ * ldpc_minsum_decode replaces MinSumScaledDecoder.decode (traditional_decoders.py:177-260),
+ * ldpc_bp_decode replaces BeliefPropagationDecoder.decode (traditional_decoders.py:42-109).
+ * Flooding schedule, fp32, no clipping (BP keeps the reference's inf/NaN behaviour).
+ *   llr         [B,N] fp32 row-major, device
+ *   soft_out    [B,N] fp32 posterior beliefs (reference local `var_beliefs`) or NULL
+ *   hard_out    per hard_dtype, or NULL
+ *   syndrome_ok [B] uint8: 1 if the returned hard decision satisfies every check
+ *               (_check_valid_codeword, traditional_decoders.py:111-134,262-284) or NULL
+ *   iters_out   [B] int32 iterations actually run per codeword, or NULL
+ *   valid_mask  [B,mask_words] uint64, bit t of word t/64 = "valid after iteration t+1",
+ *               or NULL (mask_words ignored)                                            */
+int ldpc_minsum_decode(const ldpc_code_t* code, const float* llr, int64_t B, int iters, float alpha,
+                       int stop_mode, int path, float* soft_out, void* hard_out, int hard_dtype,
+                       uint8_t* syndrome_ok, int32_t* iters_out, uint64_t* valid_mask, int mask_words,
+                       void* stream);
+int ldpc_bp_decode(const ldpc_code_t* code, const float* llr, int64_t B, int iters, int stop_mode, int path,
+                   float* soft_out, void* hard_out, int hard_dtype, uint8_t* syndrome_ok, int32_t* iters_out,
+                   uint64_t* valid_mask, int mask_words, void* stream);
+
+/* Host-buffer variant (the `e2e` path of bench.py): llr_host / hard_host are HOST pointers
+ * (pinned memory recommended).  The call chunks the batch, overlaps H2D, decode and D2H on
+ * internal streams and returns when hard_host (and soft_host if given) are complete.     */
+int ldpc_decode_host(const ldpc_code_t* code, int algo, const float* llr_host, int64_t B, int iters, float alpha,
+                     int path, float* soft_host, void* hard_host, int hard_dtype, int64_t chunk);
+
+/* ---- channel + metrics -------------------------------------------------------------
+ * ldpc_awgn_llr replaces AWGNChannel.transmit (utils/channel.py:205-231): BPSK 0->+1,
+ * sigma = 1/sqrt(10^(snr_db/10)), llr = 2*(s+n)/sigma^2, noise from Philox4x32-10 keyed by
+ * (seed) with counter (first_frame + b, n/4): results do not depend on batch split or GPU
+ * count.  bits: [B,N] uint8 or NULL (= all-zero codeword, as every reference sweep uses). */
+int ldpc_awgn_llr(const uint8_t* bits, int64_t B, int64_t N, float snr_db, uint64_t seed, uint64_t first_frame,
+                  float* llr_out, void* stream);
+/* ldpc_count_errors replaces compute_ber_fer (utils/channel.py:156-190) with integer
+ * counters: counters[0]+=bit errors, [1]+=frame errors, [2]+=frames.  tx may be NULL
+ * (all-zero).  hard per hard_dtype.                                                      */
+int ldpc_count_errors(const void* hard, int hard_dtype, const uint8_t* tx, int64_t B, int64_t N,
+                      uint64_t* counters, void* stream);
+/* Fused Monte-Carlo path (SURVEY K4+K1/K2+K5): generate LLRs on chip, decode, count; LLRs
+ * never touch HBM.  counters (device, 4 x uint64) += [bit errors, frame errors, frames,
+ * undetected frame errors (syndrome ok but bits wrong)].                                 */
+int ldpc_sim_fer(const ldpc_code_t* code, int algo, int iters, float alpha, float snr_db, uint64_t seed,
+                 uint64_t first_frame, uint64_t n_frames, uint64_t* counters, void* stream);
+
+/* ---- edge-space layers (models/layers.py) ------------------------------------------
+ * x, out: [B,E] fp32.  idx: [E,K] int64 neighbour lists, -1 padded
+ * (utils/ldpc_utils.py:5-60).                                                            */
+/* CheckLayer.forward, layers.py:14-66.  argmin_out [B,E] int32 (slot of the selected
+ * minimum, -1 if none) is optional and feeds the backward.                               */
+int ldpc_check_layer_fwd(const float* x, const int64_t* idx, int64_t B, int64_t E, int K, float* out,
+                         int32_t* argmin_out, void* stream);
+int ldpc_check_layer_bwd(const float* x, const int64_t* idx, const int32_t* argmin, const float* grad_out,
+                         int64_t B, int64_t E, int K, float* grad_x, void* stream);
+/* VariableLayer.forward, layers.py:78-125: out = llr + sum_k c2v[idx]                    */
+int ldpc_variable_layer_fwd(const float* llr, const float* c2v, const int64_t* idx, int64_t B, int64_t E, int K,
+                            float* out, void* stream);
+/* grad_c2v[b, idx[e,k]] += grad_out[b,e]  (grad_llr = grad_out, done by the caller)      */
+int ldpc_variable_layer_bwd(const int64_t* idx, const float* grad_out, int64_t B, int64_t E, int K,
+                            float* grad_c2v, void* stream);
+/* ResidualLayer.forward, layers.py:143-168: out = w_ch*llr + c2v + sum_{i<L} w_res[i]*prev[i]
+ * prev: array of L device pointers (host array of pointers), each [B,E].                 */
+int ldpc_residual_layer_fwd(const float* llr, const float* c2v, const float* w_ch, const float* w_res,
+                            const float* const* prev, int L, int64_t B, int64_t E, float* out, void* stream);
+/* OutputLayer.forward, layers.py:180-210: soft = sigmoid(final+llr); if gt: per-row max of
+ * BCE(soft, gt) -> max_loss [B], argmax [B] int32 (for the backward).                    */
+int ldpc_output_layer_fwd(const float* final_llr, const float* llr, const float* gt, int64_t B, int64_t E,
+                          float* soft, float* max_loss, int32_t* argmax, void* stream);
+
+/* ---- message-centred GNN (models/message_gnn_decoder.py) ---------------------------
+ * Weights are the reference nn.Module's parameters, flattened by the Python wrapper into
+ * one fp32 buffer in state_dict order per layer (see models/message_gnn_decoder.py in the
+ * package).  The graph is the code's Tanner graph, messages in check-major /
+ * ascending-variable order (message_gnn_decoder.py:397-406); the dense E x E adjacencies
+ * (:423-467) are replaced by per-variable / per-check segment means.                     */
+typedef struct ldpc_gnn ldpc_gnn_t;
+int ldpc_gnn_create(const ldpc_code_t* code, int num_layers, int hidden, int num_types, const int32_t* edge_type /*[base edges]*/,
+                    ldpc_gnn_t** out);
+int ldpc_gnn_destroy(ldpc_gnn_t* g);
+size_t ldpc_gnn_param_count(const ldpc_gnn_t* g);
+size_t ldpc_gnn_workspace_bytes(const ldpc_gnn_t* g, int64_t B, int training);
+/* MessageGNNDecoder.forward (message_gnn_decoder.py:190-317): soft_out = combined LLR
+ * (pre-sigmoid), prob_out = sigmoid(soft_out).  Either may be NULL.                       */
+int ldpc_gnn_forward(const ldpc_gnn_t* g, const float* params, const float* llr, int64_t B, float* soft_out,
+                     float* prob_out, void* workspace, size_t ws_bytes, int training, void* stream);
+/* mean-BCE loss on prob_out vs gt (message_gnn_decoder.py:313-315) and its gradient w.r.t.
+ * every parameter (autograd of the reference module); needs the workspace of a
+ * training=1 forward.  grad_params is accumulated into (+=).                              */
+int ldpc_gnn_backward(const ldpc_gnn_t* g, const float* params, const float* llr, const float* gt, int64_t B,
+                      float* loss_out, float* grad_params, void* workspace, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LDPC_B200_H */

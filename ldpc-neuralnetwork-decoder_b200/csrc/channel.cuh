@@ -1,0 +1,127 @@
+// channel.cuh -- BPSK-AWGN channel on the device (Philox4x32-10 + Box-Muller) and integer
+// error counters.
+//
+// Replaces AWGNChannel.transmit (utils/channel.py:205-231) and compute_ber_fer (:156-190).
+// Reference arithmetic kept: symbols = 1-2*bit; sigma = 1/sqrt(10^(snr_db/10)) in float64,
+// used as an fp32 scalar; received = s + z*sigma; llr = (2*received)/sigma^2, all fp32.
+// The reference draws z with torch.randn on the host; here z comes from a counter-based
+// generator so that a frame's noise depends only on (seed, global frame index, bit index):
+//   key     = (seed_lo, seed_hi)
+//   counter = (frame_lo, frame_hi, blk, 0),   blk = ((n >> 7) << 5) | (n & 31)
+//   the block's four outputs serve bits n with (n >> 5) & 3 = 0..3, i.e. one lane of a warp
+//   gets four consecutive 32-wide columns from a single Philox call.
+//   u = x*2^-32 + 2^-33 (cuRAND's open-interval map), z0 = sqrt(-2 ln u0) cos(2 pi u1),
+//   z1 = sqrt(-2 ln u0) sin(2 pi u1), likewise (z2, z3) from (x2, x3).
+// oracle/ldpc_oracle.c restates the same generator on the CPU.
+#pragma once
+#include "common.cuh"
+
+namespace ldpc {
+
+struct GenParams {
+    int enabled;                 // 0: read LLRs from memory
+    float sigma;                 // fp32(1/sqrt(snr_linear))
+    float var;                   // fp32(sigma_d * sigma_d)
+    unsigned long long seed;
+    unsigned long long first_frame;
+};
+
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t (&out)[4]) {
+    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int round = 0; round < 10; ++round) {
+        const uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+        const uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += W0; k1 += W1;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__device__ __forceinline__ float u01(uint32_t x) { return fmaf(__uint2float_rn(x), 2.3283064365386963e-10f, 1.1641532182693481e-10f); }
+
+// four standard normals for (frame, blk)
+__device__ __forceinline__ void normal4(unsigned long long seed, unsigned long long frame, uint32_t blk, float (&z)[4]) {
+    uint32_t x[4];
+    philox4x32_10((uint32_t)frame, (uint32_t)(frame >> 32), blk, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), x);
+    const float r0 = sqrtf(-2.0f * logf(u01(x[0]))), r1 = sqrtf(-2.0f * logf(u01(x[2])));
+    float s0, c0, s1, c1;
+    sincosf(6.2831853071795865f * u01(x[1]), &s0, &c0);
+    sincosf(6.2831853071795865f * u01(x[3]), &s1, &c1);
+    z[0] = r0 * c0; z[1] = r0 * s0; z[2] = r1 * c1; z[3] = r1 * s1;
+}
+
+__device__ __forceinline__ float llr_from_noise(float z, float symbol, const GenParams& g) {
+    const float received = __fadd_rn(symbol, __fmul_rn(z, g.sigma));
+    return __fdiv_rn(__fmul_rn(2.0f, received), g.var);
+}
+
+// one thread per Philox block: writes up to four LLRs
+__global__ void __launch_bounds__(256) awgn_llr_kernel(const uint8_t* __restrict__ bits, long long B, long long N,
+                                                        GenParams g, float* __restrict__ out) {
+    const long long nblk_per_frame = ((N + 127) >> 7) << 5;
+    const long long total = B * nblk_per_frame;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long b = t / nblk_per_frame;
+        const uint32_t blk = (uint32_t)(t - b * nblk_per_frame);
+        float z[4];
+        normal4(g.seed, g.first_frame + (unsigned long long)b, blk, z);
+#pragma unroll
+        for (int comp = 0; comp < 4; ++comp) {
+            const long long n = ((long long)(blk >> 5) << 7) + ((long long)comp << 5) + (blk & 31);
+            if (n < N) {
+                const float s = bits ? 1.0f - 2.0f * (float)bits[b * N + n] : 1.0f;
+                out[b * N + n] = llr_from_noise(z[comp], s, g);
+            }
+        }
+    }
+}
+
+// bit / frame error counters.  One warp per codeword.
+__global__ void __launch_bounds__(256) count_errors_kernel(const void* __restrict__ hard, int hard_dtype,
+                                                            const uint8_t* __restrict__ tx, long long B, long long N,
+                                                            unsigned long long* __restrict__ counters) {
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    unsigned long long bit_err = 0, frame_err = 0, frames = 0;
+    const long long NW = (N + 31) >> 5;
+    for (long long b = warp0; b < B; b += nwarps) {
+        unsigned e = 0;
+        if (hard_dtype == LDPC_HARD_PACKED) {
+            const unsigned* h = (const unsigned*)hard + b * NW;
+            for (long long w = lane; w < NW; w += 32) {
+                unsigned word = h[w];
+                if (tx) {
+                    unsigned t = 0;
+                    for (int k = 0; k < 32; ++k) {
+                        const long long n = w * 32 + k;
+                        if (n < N && tx[b * N + n]) t |= 1u << k;
+                    }
+                    word ^= t;
+                }
+                e += __popc(word);
+            }
+        } else {
+            for (long long n = lane; n < N; n += 32) {
+                const int hb = hard_dtype == LDPC_HARD_F32 ? (((const float*)hard)[b * N + n] != 0.0f)
+                                                          : (((const uint8_t*)hard)[b * N + n] != 0);
+                const int tb = tx ? (tx[b * N + n] != 0) : 0;
+                e += (hb != tb);
+            }
+        }
+        e = __reduce_add_sync(0xffffffffu, e);
+        bit_err += e;
+        frame_err += e != 0;
+        frames += 1;
+    }
+    if (lane == 0 && frames) {
+        atomicAdd(&counters[0], bit_err);
+        atomicAdd(&counters[1], frame_err);
+        atomicAdd(&counters[2], frames);
+    }
+}
+
+}  // namespace ldpc

@@ -1,0 +1,359 @@
+// decode_exact.cuh -- table-driven flooding decoder, reference operation order.
+//
+// Replaces MinSumScaledDecoder.decode (models/traditional_decoders.py:177-260) and
+// BeliefPropagationDecoder.decode (:42-109) for ANY quasi-cyclic code with Z <= 32
+// (LDPC_PATH_EXACT).  It reproduces the reference's fp32 arithmetic operation for operation:
+//   check update   min-sum: sign product and min over the OTHER edges of the check, then
+//                  alpha*min (fp32), then sign apply                       (:207-232)
+//                  BP: prod of tanh(v/2) over the other edges in ascending variable order,
+//                  2*atanh(prod), unclipped (inf/NaN propagate)             (:72-81)
+//   variable update llr + c2v of the other checks, added in ascending check order (:235-244)
+//   posterior      llr + all c2v in ascending check order; bit = belief < 0   (:247-252)
+// so min-sum results are bit-identical to the reference and BP results differ only through
+// the 1-ulp differences of tanh/atanh (math_ref.cuh).
+//
+// Mapping: one warp owns G = 32/Z codewords; lane = cw_in_warp*Z + r.  All edge messages of
+// the warp's codewords stay in shared memory for every iteration:
+//   msg[e][lane]  message on base edge e, CHECK-aligned (lane r <-> check i*Z+r); holds v2c
+//                 at the start of the check phase and c2v after it
+//   T[j][lane]    posterior of variable j*Z+r', VARIABLE-aligned
+//   L[j][lane]    channel LLR, VARIABLE-aligned
+// A circulant shift is an address rotation inside the codeword's Z-lane window, so all
+// shared-memory accesses of a warp hit 32 distinct banks.  Exclusion sums/products use a
+// running prefix (shared) plus a per-edge suffix chain, which is the reference's order.
+#pragma once
+#include <math_constants.h>
+
+#include "channel.cuh"
+#include "math_ref.cuh"
+#include "tables.cuh"
+
+namespace ldpc {
+
+struct DecodeParams {
+    const uint32_t* gtab;
+    int slot;
+    const float* llr;
+    long long B;
+    int iters;
+    float alpha;
+    int stop_mode;
+    float* soft_out;
+    void* hard_out;
+    int hard_dtype;
+    uint8_t* syndrome_ok;
+    int32_t* iters_out;
+    unsigned long long* valid_mask;
+    int mask_words;
+    int floats_per_warp;
+    long long ngroups;
+    GenParams gen;                   // sim mode: LLRs come from the on-chip channel, not from `llr`
+    unsigned long long* counters;    // sim mode: [bit errors, frame errors, frames, undetected]
+};
+
+// channel LLR of bit n of global frame `frame` (all-zero codeword), see channel.cuh
+__device__ __forceinline__ float gen_llr(const GenParams& g, unsigned long long frame, int n) {
+    float z[4];
+    normal4(g.seed, frame, (uint32_t)(((n >> 7) << 5) | (n & 31)), z);
+    const int comp = (n >> 5) & 3;
+    const float zz = comp == 0 ? z[0] : comp == 1 ? z[1] : comp == 2 ? z[2] : z[3];
+    return llr_from_noise(zz, 1.0f, g);
+}
+
+// per-lane partial counters -> one atomicAdd per warp and counter
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+__device__ __forceinline__ void flush_counters(unsigned long long* counters, unsigned long long bits,
+                                               unsigned long long fe, unsigned long long frames,
+                                               unsigned long long und) {
+    bits = warp_sum_u64(bits); fe = warp_sum_u64(fe); frames = warp_sum_u64(frames); und = warp_sum_u64(und);
+    if ((threadIdx.x & 31) == 0 && frames) {
+        atomicAdd(&counters[0], bits);
+        atomicAdd(&counters[1], fe);
+        atomicAdd(&counters[2], frames);
+        atomicAdd(&counters[3], und);
+    }
+}
+
+template <bool kConst>
+__device__ __forceinline__ bool syndrome_bad(const Tab<kConst>& tab, const float* T, int rows, int Z, int base, int r) {
+    const int off_rowptr = tab[7], off_redge = tab[9];
+    unsigned bad = 0;
+    for (int i = 0; i < rows; ++i) {
+        const int e0 = tab[off_rowptr + i], e1 = tab[off_rowptr + i + 1];
+        unsigned par = 0;
+        for (int e = e0; e < e1; ++e) {
+            const uint32_t w = tab[off_redge + e];
+            int rr = r + (int)((w >> 16) & 0xff);
+            rr -= rr >= Z ? Z : 0;
+            par ^= (T[(w & 0xffff) * 32 + base + rr] < 0.0f) ? 1u : 0u;
+        }
+        bad |= par;
+    }
+    return bad != 0;
+}
+
+template <int kAlgo, int kMaxDc, int kMaxDv, bool kConst>
+__global__ void __launch_bounds__(256) decode_exact_kernel(const DecodeParams p) {
+    extern __shared__ float smem[];
+    const Tab<kConst> tab{p.gtab, p.slot};
+    const int rows = tab[0], cols = tab[1], Z = tab[2], E = tab[3], G = tab[4];
+    const int off_rowptr = tab[7], off_colptr = tab[8], off_redge = tab[9], off_cedge = tab[10];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+    float* msg = smem + (size_t)warp * p.floats_per_warp;
+    float* T = msg + E * 32;
+    float* L = T + cols * 32;
+    const bool active = lane < G * Z;
+    const int cwi = active ? lane / Z : 0;
+    const int r = active ? lane - cwi * Z : 0;
+    const int base = cwi * Z;
+    const int N = cols * Z;
+    const unsigned gmask = (Z == 32) ? 0xffffffffu : (((1u << Z) - 1u) << base);
+    const bool track = p.stop_mode != LDPC_STOP_FIXED || p.valid_mask != nullptr;
+    unsigned long long acc_bits = 0, acc_fe = 0, acc_frames = 0, acc_und = 0;
+
+    for (long long grp = (long long)blockIdx.x * W + warp; grp < p.ngroups; grp += (long long)gridDim.x * W) {
+        const long long cw = grp * G + cwi;
+        const bool live = active && cw < p.B;
+        if (p.gen.enabled) {
+            for (int j = 0; j < cols; ++j)
+                L[j * 32 + lane] = live ? gen_llr(p.gen, p.gen.first_frame + (unsigned long long)cw, j * Z + r) : 0.0f;
+        } else {
+            const float* llr = p.llr + cw * N + r;
+            for (int j = 0; j < cols; ++j) L[j * 32 + lane] = live ? __ldg(llr + j * Z) : 0.0f;
+        }
+        __syncwarp();
+        // v2c := llr on every edge (traditional_decoders.py:64-67,199-202)
+        for (int e = 0; e < E; ++e) {
+            const uint32_t w = tab[off_redge + e];
+            int rr = r + (int)((w >> 16) & 0xff);
+            rr -= rr >= Z ? Z : 0;
+            msg[e * 32 + lane] = L[(w & 0xffff) * 32 + base + rr];
+        }
+        for (int j = 0; j < cols; ++j) T[j * 32 + lane] = L[j * 32 + lane];
+        __syncwarp();
+
+        bool done = !live;
+        int my_iters = p.iters;
+        unsigned long long vm = 0;
+        for (int it = 0; it < p.iters; ++it) {
+            // ---------------- check-node update ----------------
+            for (int i = 0; i < rows; ++i) {
+                const int e0 = tab[off_rowptr + i];
+                const int d = (int)tab[off_rowptr + i + 1] - e0;
+                float v[kMaxDc];
+#pragma unroll
+                for (int k = 0; k < kMaxDc; ++k) v[k] = (k < d) ? msg[(e0 + k) * 32 + lane] : 0.0f;
+                if constexpr (kAlgo == LDPC_ALGO_MINSUM) {
+                    float m1 = CUDART_INF_F, m2 = CUDART_INF_F;
+                    uint32_t sg = 0;
+#pragma unroll
+                    for (int k = 0; k < kMaxDc; ++k)
+                        if (k < d) {
+                            const float a = fabsf(v[k]);
+                            m2 = fminf(m2, fmaxf(m1, a));
+                            m1 = fminf(m1, a);
+                            sg ^= f2u(v[k]);
+                        }
+                    const float s1 = __fmul_rn(p.alpha, m1), s2 = __fmul_rn(p.alpha, m2);
+#pragma unroll
+                    for (int k = 0; k < kMaxDc; ++k)
+                        if (k < d) {
+                            const float mag = (fabsf(v[k]) == m1) ? s2 : s1;
+                            v[k] = u2f(f2u(mag) ^ ((sg ^ f2u(v[k])) & 0x80000000u));
+                        }
+                } else {
+                    float t[kMaxDc];
+#pragma unroll
+                    for (int k = 0; k < kMaxDc; ++k) t[k] = (k < d) ? tanh_ref(v[k] * 0.5f) : 1.0f;
+                    float pre = 1.0f;
+#pragma unroll
+                    for (int k = 0; k < kMaxDc; ++k)
+                        if (k < d) {
+                            float pr = pre;
+#pragma unroll
+                            for (int k2 = k + 1; k2 < kMaxDc; ++k2)
+                                if (k2 < d) pr = __fmul_rn(pr, t[k2]);
+                            v[k] = 2.0f * atanh_ref(pr);
+                            pre = __fmul_rn(pre, t[k]);
+                        }
+                }
+                if (!done) {
+#pragma unroll
+                    for (int k = 0; k < kMaxDc; ++k)
+                        if (k < d) msg[(e0 + k) * 32 + lane] = v[k];
+                }
+            }
+            __syncwarp();
+            // ---------------- variable-node update + posterior ----------------
+            for (int j = 0; j < cols; ++j) {
+                const int k0 = tab[off_colptr + j];
+                const int d = (int)tab[off_colptr + j + 1] - k0;
+                float c[kMaxDv];
+                int addr[kMaxDv];
+#pragma unroll
+                for (int k = 0; k < kMaxDv; ++k) {
+                    if (k < d) {
+                        const uint32_t w = tab[off_cedge + k0 + k];
+                        int rr = r - (int)((w >> 16) & 0xff);
+                        rr += rr < 0 ? Z : 0;
+                        addr[k] = (w & 0xffff) * 32 + base + rr;
+                        c[k] = msg[addr[k]];
+                    } else {
+                        addr[k] = 0;
+                        c[k] = 0.0f;
+                    }
+                }
+                float pre = L[j * 32 + lane];
+#pragma unroll
+                for (int k = 0; k < kMaxDv; ++k)
+                    if (k < d) {
+                        float s = pre;
+#pragma unroll
+                        for (int k2 = k + 1; k2 < kMaxDv; ++k2)
+                            if (k2 < d) s = __fadd_rn(s, c[k2]);
+                        pre = __fadd_rn(pre, c[k]);
+                        c[k] = s;
+                    }
+                if (!done) {
+#pragma unroll
+                    for (int k = 0; k < kMaxDv; ++k)
+                        if (k < d) msg[addr[k]] = c[k];
+                    T[j * 32 + lane] = pre;
+                }
+            }
+            __syncwarp();
+            if (track) {
+                const bool bad = syndrome_bad(tab, T, rows, Z, base, r);
+                const unsigned m = __ballot_sync(0xffffffffu, bad && active);
+                const bool ok = (m & gmask) == 0;
+                if (ok) vm |= 1ull << (it & 63);
+                if (p.valid_mask && live && r == 0 && ((it & 63) == 63 || it == p.iters - 1)) {
+                    if ((it >> 6) < p.mask_words) p.valid_mask[cw * p.mask_words + (it >> 6)] = vm;
+                }
+                if ((it & 63) == 63) vm = 0;
+                if (p.stop_mode == LDPC_STOP_PER_CODEWORD) {
+                    if (ok && !done) {
+                        done = true;
+                        my_iters = it + 1;
+                        // the frozen codeword stays valid: mark the remaining iterations of this word
+                        if (p.valid_mask && live && r == 0) {
+                            for (int t2 = it; t2 < p.iters; ++t2)
+                                if ((t2 >> 6) < p.mask_words)
+                                    atomicOr(&p.valid_mask[cw * p.mask_words + (t2 >> 6)], 1ull << (t2 & 63));
+                        }
+                    }
+                    if (__all_sync(0xffffffffu, done)) break;
+                }
+            }
+        }
+
+        // ---------------- outputs ----------------
+        if (p.soft_out && live) {
+            float* o = p.soft_out + cw * N + r;
+            for (int j = 0; j < cols; ++j) o[j * Z] = T[j * 32 + lane];
+        }
+        if (p.iters_out && live && r == 0) p.iters_out[cw] = my_iters;
+        if (p.syndrome_ok || p.counters) {
+            const bool bad = syndrome_bad(tab, T, rows, Z, base, r);
+            const unsigned m = __ballot_sync(0xffffffffu, bad && active);
+            const bool ok = (m & gmask) == 0;
+            if (p.syndrome_ok && live && r == 0) p.syndrome_ok[cw] = ok ? 1 : 0;
+            if (p.counters) {
+                // all-zero codeword was sent: every negative posterior is a bit error
+                unsigned e = 0;
+                if (live)
+                    for (int j = 0; j < cols; ++j) e += T[j * 32 + lane] < 0.0f ? 1u : 0u;
+                unsigned tot = 0;   // errors of this lane's codeword
+                for (int l = 0; l < 32; ++l) {
+                    const unsigned el = __shfl_sync(0xffffffffu, e, l);
+                    if (l >= base && l < base + Z) tot += el;
+                }
+                if (live && r == 0) {
+                    acc_bits += tot;
+                    acc_fe += tot != 0;
+                    acc_frames += 1;
+                    acc_und += (tot != 0 && ok);
+                }
+            }
+        }
+        if (p.hard_out) {
+            if (p.hard_dtype == LDPC_HARD_F32) {
+                float* o = (float*)p.hard_out + cw * N + r;
+                if (live)
+                    for (int j = 0; j < cols; ++j) o[j * Z] = T[j * 32 + lane] < 0.0f ? 1.0f : 0.0f;
+            } else if (p.hard_dtype == LDPC_HARD_U8) {
+                uint8_t* o = (uint8_t*)p.hard_out + cw * N + r;
+                if (live)
+                    for (int j = 0; j < cols; ++j) o[j * Z] = T[j * 32 + lane] < 0.0f ? 1 : 0;
+            } else {
+                // packed words: stage in the (now free) message area
+                const int NW = (N + 31) >> 5;
+                unsigned* buf = reinterpret_cast<unsigned*>(msg);
+                __syncwarp();
+                for (int x = lane; x < G * NW; x += 32) buf[x] = 0;
+                __syncwarp();
+                if (active)
+                    for (int j = 0; j < cols; ++j)
+                        if (T[j * 32 + lane] < 0.0f) {
+                            const int n = j * Z + r;
+                            atomicOr(&buf[cwi * NW + (n >> 5)], 1u << (n & 31));
+                        }
+                __syncwarp();
+                for (int x = lane; x < G * NW; x += 32) {
+                    const long long cw2 = grp * G + x / NW;
+                    if (cw2 < p.B) ((unsigned*)p.hard_out)[cw2 * NW + x % NW] = buf[x];
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (p.counters) flush_counters(p.counters, acc_bits, acc_fe, acc_frames, acc_und);
+}
+
+// ---- host launcher ----------------------------------------------------------------------
+template <int kAlgo, int kMaxDc, int kMaxDv, bool kConst>
+inline int launch_exact_inst(const DecodeParams& p, int W, int grid, size_t smem, cudaStream_t st) {
+    auto kern = decode_exact_kernel<kAlgo, kMaxDc, kMaxDv, kConst>;
+    LDPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, W * 32, smem, st>>>(p);
+    LDPC_CHECK_LAUNCH("decode_exact_kernel");
+    return LDPC_OK;
+}
+
+inline int launch_exact(const ldpc_code* c, int algo, DecodeParams p, cudaStream_t st) {
+    if (c->maxdc > 32 || c->maxdv > 32)
+        return fail(LDPC_ERR_UNSUPPORTED, "exact path: node degree above 32 (row %d, col %d)", c->maxdc, c->maxdv);
+    const size_t per_warp = (size_t)(c->E + 2 * c->cols) * 32 * sizeof(float);
+    int W = (int)(kMaxSmemPerBlock / per_warp);
+    if (W < 1)
+        return fail(LDPC_ERR_UNSUPPORTED, "exact path: %zu bytes of messages per warp exceed shared memory", per_warp);
+    if (W > 8) W = 8;
+    const long long ngroups = (p.B + c->G - 1) / c->G;
+    if ((long long)W > ngroups) W = (int)ngroups;
+    int per_sm = (int)(kMaxSmemPerBlock / (per_warp * W));
+    per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
+    long long blocks = (ngroups + W - 1) / W;
+    if (blocks > (long long)kNumSMs * per_sm) blocks = (long long)kNumSMs * per_sm;
+    p.floats_per_warp = (int)(per_warp / sizeof(float));
+    p.ngroups = ngroups;
+    p.gtab = c->d_tab;
+    p.slot = c->slot < 0 ? 0 : c->slot;
+    const bool small = c->maxdc <= 10 && c->maxdv <= 24;
+    const bool cst = c->slot >= 0;
+    const size_t smem = per_warp * W;
+#define LDPC_EXACT_CASE(A, DC, DV, CST) return launch_exact_inst<A, DC, DV, CST>(p, W, (int)blocks, smem, st)
+    if (algo == LDPC_ALGO_MINSUM) {
+        if (small) { if (cst) LDPC_EXACT_CASE(LDPC_ALGO_MINSUM, 10, 24, true); else LDPC_EXACT_CASE(LDPC_ALGO_MINSUM, 10, 24, false); }
+        else       { if (cst) LDPC_EXACT_CASE(LDPC_ALGO_MINSUM, 32, 32, true); else LDPC_EXACT_CASE(LDPC_ALGO_MINSUM, 32, 32, false); }
+    } else {
+        if (small) { if (cst) LDPC_EXACT_CASE(LDPC_ALGO_BP, 10, 24, true); else LDPC_EXACT_CASE(LDPC_ALGO_BP, 10, 24, false); }
+        else       { if (cst) LDPC_EXACT_CASE(LDPC_ALGO_BP, 32, 32, true); else LDPC_EXACT_CASE(LDPC_ALGO_BP, 32, 32, false); }
+    }
+#undef LDPC_EXACT_CASE
+}
+
+}  // namespace ldpc

@@ -1,0 +1,371 @@
+// ldpc_b200.cu -- the C ABI of include/ldpc_b200.h.  Host-side argument checking, table
+// upload and kernel dispatch only; the kernels live in the .cuh files next to this one.
+// Built for sm_100a only (see __graft_entry__.build / Makefile); there is no CPU fallback.
+#include "common.cuh"
+#include "tables.cuh"
+#include "decode_exact.cuh"
+#include "decode_fast.cuh"
+#include "channel.cuh"
+#include "layers.cuh"
+#include "gnn.cuh"
+
+#include <cstring>
+#include <new>
+
+using namespace ldpc;
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+int check_decode_args(const ldpc_code_t* code, const float* llr, int64_t B, int iters, int stop_mode, int path,
+                      int hard_dtype, const uint64_t* valid_mask, int mask_words) {
+    if (!code) return fail(LDPC_ERR_INVALID, "decode: null code handle");
+    if (!llr) return fail(LDPC_ERR_INVALID, "decode: null llr pointer");
+    if (B < 0) return fail(LDPC_ERR_INVALID, "decode: negative batch %lld", (long long)B);
+    if (iters < 1) return fail(LDPC_ERR_INVALID, "decode: iters=%d, need >= 1", iters);
+    if (stop_mode != LDPC_STOP_FIXED && stop_mode != LDPC_STOP_PER_CODEWORD)
+        return fail(LDPC_ERR_INVALID, "decode: unknown stop_mode %d", stop_mode);
+    if (path < LDPC_PATH_AUTO || path > LDPC_PATH_FAST) return fail(LDPC_ERR_INVALID, "decode: unknown path %d", path);
+    if (hard_dtype < LDPC_HARD_F32 || hard_dtype > LDPC_HARD_PACKED)
+        return fail(LDPC_ERR_INVALID, "decode: unknown hard_dtype %d", hard_dtype);
+    if (valid_mask && mask_words < (iters + 63) / 64)
+        return fail(LDPC_ERR_INVALID, "decode: mask_words=%d too small for %d iterations", mask_words, iters);
+    return LDPC_OK;
+}
+
+int decode_common(const ldpc_code_t* code, int algo, const float* llr, int64_t B, int iters, float alpha, int stop_mode,
+                  int path, float* soft_out, void* hard_out, int hard_dtype, uint8_t* syndrome_ok, int32_t* iters_out,
+                  uint64_t* valid_mask, int mask_words, void* stream) {
+    int rc = check_decode_args(code, llr, B, iters, stop_mode, path, hard_dtype, valid_mask, mask_words);
+    if (rc) return rc;
+    if (B == 0) return LDPC_OK;
+    DeviceGuard g(code->device);
+    if (!g.ok) return fail(LDPC_ERR_CUDA, "decode: cannot select device %d", code->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (valid_mask) LDPC_CUDA(cudaMemsetAsync(valid_mask, 0, sizeof(uint64_t) * (size_t)B * mask_words, st));
+    DecodeParams p{};
+    p.llr = llr; p.B = B; p.iters = iters; p.alpha = alpha; p.stop_mode = stop_mode;
+    p.soft_out = soft_out; p.hard_out = hard_out; p.hard_dtype = hard_dtype; p.syndrome_ok = syndrome_ok;
+    p.iters_out = iters_out; p.valid_mask = (unsigned long long*)valid_mask; p.mask_words = mask_words;
+    const bool fast_ok = fast_path_supports(code, algo, stop_mode, valid_mask != nullptr);
+    if (path == LDPC_PATH_FAST && !fast_ok)
+        return fail(LDPC_ERR_UNSUPPORTED, "decode: no specialised kernel for this code/algorithm/stop mode");
+    if (path != LDPC_PATH_EXACT && fast_ok) return launch_fast(code, algo, p, st);
+    return launch_exact(code, algo, p, st);
+}
+
+}  // namespace
+
+extern "C" {
+
+int ldpc_abi_version(void) { return LDPC_B200_ABI_VERSION; }
+const char* ldpc_last_error(void) { return err_buf(); }
+uint64_t ldpc_launch_count(void) { return launch_counter().load(); }
+
+int ldpc_code_create(const int16_t* shifts, int rows, int cols, int Z, int device, ldpc_code_t** out) {
+    if (!out) return fail(LDPC_ERR_INVALID, "code_create: null out pointer");
+    *out = nullptr;
+    if (device < 0 || device >= kMaxDevices) return fail(LDPC_ERR_INVALID, "code_create: device %d out of range", device);
+    ldpc_code* c = new (std::nothrow) ldpc_code();
+    if (!c) return fail(LDPC_ERR_NOMEM, "code_create: out of host memory");
+    int rc = build_table(shifts, rows, cols, Z, c);
+    if (rc) { delete c; return rc; }
+    c->device = device;
+    DeviceGuard g(device);
+    if (!g.ok) { delete c; return fail(LDPC_ERR_CUDA, "code_create: cannot select CUDA device %d (no GPU?)", device); }
+    cudaError_t e = cudaMalloc(&c->d_tab, sizeof(uint32_t) * c->tab_words);
+    if (e != cudaSuccess) { delete c; return fail(LDPC_ERR_CUDA, "code_create: cudaMalloc: %s", cudaGetErrorString(e)); }
+    e = cudaMemcpy(c->d_tab, c->h_tab.data(), sizeof(uint32_t) * c->tab_words, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(c->d_tab); delete c; return fail(LDPC_ERR_CUDA, "code_create: upload: %s", cudaGetErrorString(e)); }
+    if (c->tab_words <= kSlotWords) {
+        std::lock_guard<std::mutex> lk(slot_mutex());
+        for (int s = 0; s < kNumSlots; ++s)
+            if (!slot_used()[device][s]) {
+                e = cudaMemcpyToSymbol(c_tab, c->h_tab.data(), sizeof(uint32_t) * c->tab_words,
+                                       sizeof(uint32_t) * (size_t)s * kSlotWords, cudaMemcpyHostToDevice);
+                if (e == cudaSuccess) { slot_used()[device][s] = true; c->slot = s; }
+                break;
+            }
+    }
+    c->fast_kind = detect_fast_kind(c);
+    *out = c;
+    return LDPC_OK;
+}
+
+int ldpc_code_destroy(ldpc_code_t* code) {
+    if (!code) return LDPC_OK;
+    {
+        DeviceGuard g(code->device);
+        if (code->d_tab) cudaFree(code->d_tab);
+    }
+    if (code->slot >= 0) {
+        std::lock_guard<std::mutex> lk(slot_mutex());
+        slot_used()[code->device][code->slot] = false;
+    }
+    delete code;
+    return LDPC_OK;
+}
+
+int ldpc_code_info(const ldpc_code_t* c, int32_t info[8]) {
+    if (!c || !info) return fail(LDPC_ERR_INVALID, "code_info: null argument");
+    info[0] = c->rows; info[1] = c->cols; info[2] = c->Z; info[3] = c->E;
+    info[4] = c->N; info[5] = c->M; info[6] = c->maxdc; info[7] = c->maxdv;
+    return LDPC_OK;
+}
+
+int ldpc_code_has_fast_path(const ldpc_code_t* code, int algo) {
+    if (!code) return 0;
+    return fast_path_supports(code, algo, LDPC_STOP_FIXED, false) ? 1 : 0;
+}
+
+int ldpc_minsum_decode(const ldpc_code_t* code, const float* llr, int64_t B, int iters, float alpha, int stop_mode,
+                       int path, float* soft_out, void* hard_out, int hard_dtype, uint8_t* syndrome_ok,
+                       int32_t* iters_out, uint64_t* valid_mask, int mask_words, void* stream) {
+    return decode_common(code, LDPC_ALGO_MINSUM, llr, B, iters, alpha, stop_mode, path, soft_out, hard_out, hard_dtype,
+                         syndrome_ok, iters_out, valid_mask, mask_words, stream);
+}
+
+int ldpc_bp_decode(const ldpc_code_t* code, const float* llr, int64_t B, int iters, int stop_mode, int path,
+                   float* soft_out, void* hard_out, int hard_dtype, uint8_t* syndrome_ok, int32_t* iters_out,
+                   uint64_t* valid_mask, int mask_words, void* stream) {
+    return decode_common(code, LDPC_ALGO_BP, llr, B, iters, 1.0f, stop_mode, path, soft_out, hard_out, hard_dtype,
+                         syndrome_ok, iters_out, valid_mask, mask_words, stream);
+}
+
+int ldpc_decode_host(const ldpc_code_t* code, int algo, const float* llr_host, int64_t B, int iters, float alpha,
+                     int path, float* soft_host, void* hard_host, int hard_dtype, int64_t chunk) {
+    if (!code) return fail(LDPC_ERR_INVALID, "decode_host: null code handle");
+    if (!llr_host || !hard_host) return fail(LDPC_ERR_INVALID, "decode_host: null host buffer");
+    if (algo != LDPC_ALGO_MINSUM && algo != LDPC_ALGO_BP) return fail(LDPC_ERR_INVALID, "decode_host: unknown algo %d", algo);
+    if (hard_dtype < LDPC_HARD_F32 || hard_dtype > LDPC_HARD_PACKED) return fail(LDPC_ERR_INVALID, "decode_host: unknown hard_dtype");
+    if (B <= 0) return B == 0 ? LDPC_OK : fail(LDPC_ERR_INVALID, "decode_host: negative batch");
+    DeviceGuard g(code->device);
+    if (!g.ok) return fail(LDPC_ERR_CUDA, "decode_host: cannot select device %d", code->device);
+    const int N = code->N;
+    if (chunk <= 0) chunk = 1 << 16;
+    if (chunk > B) chunk = B;
+    const size_t hard_row = hard_dtype == LDPC_HARD_F32 ? sizeof(float) * N
+                          : hard_dtype == LDPC_HARD_U8 ? (size_t)N : sizeof(uint32_t) * ((N + 31) / 32);
+    constexpr int kStages = 3;
+    cudaStream_t st[kStages] = {};
+    float* d_llr[kStages] = {};
+    float* d_soft[kStages] = {};
+    char* d_hard[kStages] = {};
+    int rc = LDPC_OK;
+    auto cleanup = [&]() {
+        for (int s = 0; s < kStages; ++s) {
+            if (st[s]) { cudaStreamSynchronize(st[s]); cudaStreamDestroy(st[s]); }
+            cudaFree(d_llr[s]); cudaFree(d_soft[s]); cudaFree(d_hard[s]);
+        }
+    };
+#define HOST_TRY(expr)                                                                                     \
+    do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup();                                      \
+         return fail(LDPC_ERR_CUDA, "decode_host: %s: %s", #expr, cudaGetErrorString(_e)); } } while (0)
+    for (int s = 0; s < kStages; ++s) {
+        HOST_TRY(cudaStreamCreateWithFlags(&st[s], cudaStreamNonBlocking));
+        HOST_TRY(cudaMalloc(&d_llr[s], sizeof(float) * (size_t)chunk * N));
+        HOST_TRY(cudaMalloc(&d_hard[s], hard_row * (size_t)chunk));
+        if (soft_host) HOST_TRY(cudaMalloc(&d_soft[s], sizeof(float) * (size_t)chunk * N));
+    }
+    int64_t done = 0;
+    for (int it = 0; done < B; ++it, done += chunk) {
+        const int s = it % kStages;
+        const int64_t b = (B - done) < chunk ? (B - done) : chunk;
+        // same-stream ordering makes reuse of stage s safe: its previous D2H precedes this H2D
+        HOST_TRY(cudaMemcpyAsync(d_llr[s], llr_host + (size_t)done * N, sizeof(float) * (size_t)b * N, cudaMemcpyHostToDevice, st[s]));
+        rc = decode_common(code, algo, d_llr[s], b, iters, alpha, LDPC_STOP_FIXED, path, d_soft[s], d_hard[s], hard_dtype,
+                           nullptr, nullptr, nullptr, 0, st[s]);
+        if (rc) { cleanup(); return rc; }
+        HOST_TRY(cudaMemcpyAsync((char*)hard_host + hard_row * (size_t)done, d_hard[s], hard_row * (size_t)b, cudaMemcpyDeviceToHost, st[s]));
+        if (soft_host)
+            HOST_TRY(cudaMemcpyAsync(soft_host + (size_t)done * N, d_soft[s], sizeof(float) * (size_t)b * N, cudaMemcpyDeviceToHost, st[s]));
+    }
+    for (int s = 0; s < kStages; ++s) HOST_TRY(cudaStreamSynchronize(st[s]));
+#undef HOST_TRY
+    cleanup();
+    return LDPC_OK;
+}
+
+
+// ---- channel + metrics ------------------------------------------------------------------
+static int make_gen(float snr_db, uint64_t seed, uint64_t first_frame, GenParams* g) {
+    // utils/channel.py:219-222: snr_linear = 10**(snr_db/10); noise_std = 1/np.sqrt(snr_linear), float64
+    const double snr_linear = pow(10.0, (double)snr_db / 10.0);
+    const double sigma = 1.0 / sqrt(snr_linear);
+    g->enabled = 1;
+    g->sigma = (float)sigma;
+    g->var = (float)(sigma * sigma);
+    g->seed = seed;
+    g->first_frame = first_frame;
+    return LDPC_OK;
+}
+
+int ldpc_awgn_llr(const uint8_t* bits, int64_t B, int64_t N, float snr_db, uint64_t seed, uint64_t first_frame,
+                  float* llr_out, void* stream) {
+    if (!llr_out) return fail(LDPC_ERR_INVALID, "awgn_llr: null output");
+    if (B < 0 || N <= 0) return fail(LDPC_ERR_INVALID, "awgn_llr: bad shape [%lld,%lld]", (long long)B, (long long)N);
+    if (B == 0) return LDPC_OK;
+    GenParams g;
+    make_gen(snr_db, seed, first_frame, &g);
+    const long long blocks_needed = (B * ((((long long)N + 127) >> 7) << 5) + 255) / 256;
+    const int grid = (int)(blocks_needed < kNumSMs * 8 ? blocks_needed : kNumSMs * 8);
+    awgn_llr_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(bits, B, N, g, llr_out);
+    LDPC_CHECK_LAUNCH("awgn_llr_kernel");
+    return LDPC_OK;
+}
+
+int ldpc_count_errors(const void* hard, int hard_dtype, const uint8_t* tx, int64_t B, int64_t N, uint64_t* counters,
+                      void* stream) {
+    if (!hard || !counters) return fail(LDPC_ERR_INVALID, "count_errors: null argument");
+    if (hard_dtype < LDPC_HARD_F32 || hard_dtype > LDPC_HARD_PACKED) return fail(LDPC_ERR_INVALID, "count_errors: unknown hard_dtype");
+    if (B < 0 || N <= 0) return fail(LDPC_ERR_INVALID, "count_errors: bad shape");
+    if (B == 0) return LDPC_OK;
+    const long long blocks_needed = (B + 7) / 8;
+    const int grid = (int)(blocks_needed < kNumSMs * 8 ? blocks_needed : kNumSMs * 8);
+    count_errors_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(hard, hard_dtype, tx, B, N, (unsigned long long*)counters);
+    LDPC_CHECK_LAUNCH("count_errors_kernel");
+    return LDPC_OK;
+}
+
+int ldpc_sim_fer(const ldpc_code_t* code, int algo, int iters, float alpha, float snr_db, uint64_t seed,
+                 uint64_t first_frame, uint64_t n_frames, uint64_t* counters, void* stream) {
+    if (!code || !counters) return fail(LDPC_ERR_INVALID, "sim_fer: null argument");
+    if (algo != LDPC_ALGO_MINSUM && algo != LDPC_ALGO_BP) return fail(LDPC_ERR_INVALID, "sim_fer: unknown algo %d", algo);
+    if (iters < 1) return fail(LDPC_ERR_INVALID, "sim_fer: iters=%d", iters);
+    if (n_frames == 0) return LDPC_OK;
+    if (n_frames > (1ull << 40)) return fail(LDPC_ERR_INVALID, "sim_fer: more than 2^40 frames in one call");
+    DeviceGuard g(code->device);
+    if (!g.ok) return fail(LDPC_ERR_CUDA, "sim_fer: cannot select device %d", code->device);
+    DecodeParams p{};
+    p.B = (long long)n_frames; p.iters = iters; p.alpha = alpha; p.stop_mode = LDPC_STOP_FIXED;
+    p.counters = (unsigned long long*)counters;
+    make_gen(snr_db, seed, first_frame, &p.gen);
+    if (fast_path_supports(code, algo, LDPC_STOP_FIXED, false)) return launch_fast(code, algo, p, (cudaStream_t)stream);
+    return launch_exact(code, algo, p, (cudaStream_t)stream);
+}
+
+// ---- edge-space layers ---------------------------------------------------------------------
+#define LDPC_LAYER_DISPATCH(KERNEL, ...)                                                            \
+    do {                                                                                            \
+        const int rows = layer_rows_per_cta(E);                                                     \
+        const int grid = layer_grid(rows ? (B + rows - 1) / rows : B, 1);                           \
+        const size_t smem = (size_t)rows * E * sizeof(float);                                       \
+        switch (rows) {                                                                             \
+            case 0: KERNEL<1, false><<<grid, kLayerThreads, 0, st>>>(__VA_ARGS__); break;           \
+            case 1: LDPC_CUDA(cudaFuncSetAttribute(KERNEL<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+                    KERNEL<1, true><<<grid, kLayerThreads, smem, st>>>(__VA_ARGS__); break;         \
+            case 2: case 3: { const size_t sm2 = (size_t)2 * E * sizeof(float);                     \
+                    LDPC_CUDA(cudaFuncSetAttribute(KERNEL<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2)); \
+                    KERNEL<2, true><<<layer_grid((B + 1) / 2, 1), kLayerThreads, sm2, st>>>(__VA_ARGS__); break; } \
+            case 4: case 5: case 6: case 7: { const size_t sm4 = (size_t)4 * E * sizeof(float);     \
+                    LDPC_CUDA(cudaFuncSetAttribute(KERNEL<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4)); \
+                    KERNEL<4, true><<<layer_grid((B + 3) / 4, 1), kLayerThreads, sm4, st>>>(__VA_ARGS__); break; } \
+            default: LDPC_CUDA(cudaFuncSetAttribute(KERNEL<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+                    KERNEL<8, true><<<grid, kLayerThreads, smem, st>>>(__VA_ARGS__); break;         \
+        }                                                                                           \
+    } while (0)
+
+int ldpc_check_layer_fwd(const float* x, const int64_t* idx, int64_t B, int64_t E, int K, float* out,
+                         int32_t* argmin_out, void* stream) {
+    if (!x || !idx || !out) return fail(LDPC_ERR_INVALID, "check_layer_fwd: null argument");
+    if (B < 0 || E <= 0 || K <= 0) return fail(LDPC_ERR_INVALID, "check_layer_fwd: bad shape");
+    if (B == 0) return LDPC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    LDPC_LAYER_DISPATCH(check_layer_fwd_kernel, x, (const long long*)idx, (long long)B, (long long)E, K, out, argmin_out);
+    LDPC_CHECK_LAUNCH("check_layer_fwd_kernel");
+    return LDPC_OK;
+}
+
+int ldpc_check_layer_bwd(const float* x, const int64_t* idx, const int32_t* argmin, const float* grad_out, int64_t B,
+                         int64_t E, int K, float* grad_x, void* stream) {
+    if (!x || !idx || !argmin || !grad_out || !grad_x) return fail(LDPC_ERR_INVALID, "check_layer_bwd: null argument");
+    if (B < 0 || E <= 0 || K <= 0) return fail(LDPC_ERR_INVALID, "check_layer_bwd: bad shape");
+    if (B == 0) return LDPC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    LDPC_CUDA(cudaMemsetAsync(grad_x, 0, sizeof(float) * (size_t)B * E, st));
+    check_layer_bwd_kernel<<<layer_grid(B * E, kLayerThreads), kLayerThreads, 0, st>>>(
+        x, (const long long*)idx, argmin, grad_out, (long long)B, (long long)E, K, grad_x);
+    LDPC_CHECK_LAUNCH("check_layer_bwd_kernel");
+    return LDPC_OK;
+}
+
+int ldpc_variable_layer_fwd(const float* llr, const float* c2v, const int64_t* idx, int64_t B, int64_t E, int K,
+                            float* out, void* stream) {
+    if (!llr || !c2v || !idx || !out) return fail(LDPC_ERR_INVALID, "variable_layer_fwd: null argument");
+    if (B < 0 || E <= 0 || K <= 0) return fail(LDPC_ERR_INVALID, "variable_layer_fwd: bad shape");
+    if (B == 0) return LDPC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    LDPC_LAYER_DISPATCH(variable_layer_fwd_kernel, llr, c2v, (const long long*)idx, (long long)B, (long long)E, K, out);
+    LDPC_CHECK_LAUNCH("variable_layer_fwd_kernel");
+    return LDPC_OK;
+}
+
+int ldpc_variable_layer_bwd(const int64_t* idx, const float* grad_out, int64_t B, int64_t E, int K, float* grad_c2v,
+                            void* stream) {
+    if (!idx || !grad_out || !grad_c2v) return fail(LDPC_ERR_INVALID, "variable_layer_bwd: null argument");
+    if (B < 0 || E <= 0 || K <= 0) return fail(LDPC_ERR_INVALID, "variable_layer_bwd: bad shape");
+    if (B == 0) return LDPC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    LDPC_CUDA(cudaMemsetAsync(grad_c2v, 0, sizeof(float) * (size_t)B * E, st));
+    variable_layer_bwd_kernel<<<layer_grid(B * E, kLayerThreads), kLayerThreads, 0, st>>>(
+        (const long long*)idx, grad_out, (long long)B, (long long)E, K, grad_c2v);
+    LDPC_CHECK_LAUNCH("variable_layer_bwd_kernel");
+    return LDPC_OK;
+}
+
+int ldpc_residual_layer_fwd(const float* llr, const float* c2v, const float* w_ch, const float* w_res,
+                            const float* const* prev, int L, int64_t B, int64_t E, float* out, void* stream) {
+    if (!llr || !c2v || !w_ch || !out || (L > 0 && (!prev || !w_res))) return fail(LDPC_ERR_INVALID, "residual_layer_fwd: null argument");
+    if (L < 0 || L > kMaxResidual) return fail(LDPC_ERR_UNSUPPORTED, "residual_layer_fwd: depth %d outside 0..%d", L, kMaxResidual);
+    if (B < 0 || E <= 0) return fail(LDPC_ERR_INVALID, "residual_layer_fwd: bad shape");
+    if (B == 0) return LDPC_OK;
+    ResidualPtrs rp{};
+    for (int i = 0; i < L; ++i) {
+        if (!prev[i]) return fail(LDPC_ERR_INVALID, "residual_layer_fwd: prev[%d] is null", i);
+        rp.prev[i] = prev[i];
+    }
+    residual_layer_fwd_kernel<<<layer_grid(B * E, kLayerThreads), kLayerThreads, 0, (cudaStream_t)stream>>>(
+        llr, c2v, w_ch, w_res, rp, L, (long long)B, (long long)E, out);
+    LDPC_CHECK_LAUNCH("residual_layer_fwd_kernel");
+    return LDPC_OK;
+}
+
+int ldpc_output_layer_fwd(const float* final_llr, const float* llr, const float* gt, int64_t B, int64_t E, float* soft,
+                          float* max_loss, int32_t* argmax, void* stream) {
+    if (!final_llr || !llr || !soft) return fail(LDPC_ERR_INVALID, "output_layer_fwd: null argument");
+    if (gt && !max_loss) return fail(LDPC_ERR_INVALID, "output_layer_fwd: ground truth given without max_loss buffer");
+    if (B < 0 || E <= 0) return fail(LDPC_ERR_INVALID, "output_layer_fwd: bad shape");
+    if (B == 0) return LDPC_OK;
+    output_layer_fwd_kernel<<<layer_grid(B, kLayerThreads / 32), kLayerThreads, 0, (cudaStream_t)stream>>>(
+        final_llr, llr, gt, (long long)B, (long long)E, soft, max_loss, argmax);
+    LDPC_CHECK_LAUNCH("output_layer_fwd_kernel");
+    return LDPC_OK;
+}
+
+// ---- message-centred GNN -------------------------------------------------------------------
+int ldpc_gnn_create(const ldpc_code_t*, int, int, int, const int32_t*, ldpc_gnn_t** out) {
+    if (out) *out = nullptr;
+    return fail(LDPC_ERR_UNSUPPORTED, "gnn: not built yet");
+}
+int ldpc_gnn_destroy(ldpc_gnn_t* g) { delete g; return LDPC_OK; }
+size_t ldpc_gnn_param_count(const ldpc_gnn_t*) { return 0; }
+size_t ldpc_gnn_workspace_bytes(const ldpc_gnn_t*, int64_t, int) { return 0; }
+int ldpc_gnn_forward(const ldpc_gnn_t*, const float*, const float*, int64_t, float*, float*, void*, size_t, int, void*) {
+    return fail(LDPC_ERR_UNSUPPORTED, "gnn: not built yet");
+}
+int ldpc_gnn_backward(const ldpc_gnn_t*, const float*, const float*, const float*, int64_t, float*, float*, void*, size_t, void*) {
+    return fail(LDPC_ERR_UNSUPPORTED, "gnn: not built yet");
+}
+
+}  // extern "C"

@@ -1,0 +1,183 @@
+"""Edge-space layers, drop-in for the reference's models/layers.py.
+
+  CheckLayer      reference :5-66     unscaled min-sum over listed neighbours
+  VariableLayer   reference :69-125   llr + sum of listed check messages
+  ResidualLayer   reference :128-168  w_ch*llr + c2v + sum_i w_res[i]*prev[i]
+  OutputLayer     reference :171-210  sigmoid(final+llr), per-frame max BCE
+
+Same `nn.Module` interfaces and parameter names (`w_ch`, `w_res`); forward and backward of
+the gather-type layers run in the engine's kernels (csrc/layers.cuh) through
+torch.autograd.Function.  CUDA tensors only.
+"""
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from .. import _native
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("the LDPC engine layers need CUDA tensors (no CPU fallback)")
+
+
+class _CheckFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, idx):
+        _need_cuda(x, idx)
+        x = x.detach().to(torch.float32).contiguous()
+        idx = idx.to(torch.int64).contiguous()
+        B, E = x.shape
+        Em, K = idx.shape
+        if Em != E:
+            raise ValueError("check_index_tensor must have one row per edge")
+        out = torch.empty_like(x)
+        am = torch.empty((B, E), dtype=torch.int32, device=x.device)
+        with torch.cuda.device(x.device):
+            _native.check(_native.lib().ldpc_check_layer_fwd(
+                _native.ptr(x), _native.ptr(idx), B, E, K, _native.ptr(out), _native.ptr(am),
+                _native.stream_ptr(x.device)))
+        ctx.save_for_backward(x, idx, am)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, idx, am = ctx.saved_tensors
+        g = g.to(torch.float32).contiguous()
+        B, E = x.shape
+        gx = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            _native.check(_native.lib().ldpc_check_layer_bwd(
+                _native.ptr(x), _native.ptr(idx), _native.ptr(am), _native.ptr(g), B, E, idx.shape[1],
+                _native.ptr(gx), _native.stream_ptr(x.device)))
+        return gx, None
+
+
+class _VariableFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, llr, c2v, idx):
+        _need_cuda(llr, c2v, idx)
+        llr = llr.detach().to(torch.float32).contiguous()
+        c2v = c2v.detach().to(torch.float32).contiguous()
+        idx = idx.to(torch.int64).contiguous()
+        B, E = c2v.shape
+        out = torch.empty_like(c2v)
+        with torch.cuda.device(c2v.device):
+            _native.check(_native.lib().ldpc_variable_layer_fwd(
+                _native.ptr(llr), _native.ptr(c2v), _native.ptr(idx), B, E, idx.shape[1], _native.ptr(out),
+                _native.stream_ptr(c2v.device)))
+        ctx.save_for_backward(idx)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        g = g.to(torch.float32).contiguous()
+        B, E = g.shape
+        gc = torch.empty_like(g)
+        with torch.cuda.device(g.device):
+            _native.check(_native.lib().ldpc_variable_layer_bwd(
+                _native.ptr(idx), _native.ptr(g), B, E, idx.shape[1], _native.ptr(gc),
+                _native.stream_ptr(g.device)))
+        return g, gc, None
+
+
+class _ResidualFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, llr, c2v, w_ch, w_res, *prev):
+        _need_cuda(llr, c2v, w_ch, w_res, *prev)
+        ts = [t.detach().to(torch.float32).contiguous() for t in (llr, c2v, w_ch, w_res) + tuple(prev)]
+        llr_c, c2v_c, wch_c, wres_c, prev_c = ts[0], ts[1], ts[2], ts[3], ts[4:]
+        B, E = llr_c.shape
+        out = torch.empty_like(llr_c)
+        arr = (C.c_void_p * max(len(prev_c), 1))(*[p.data_ptr() for p in prev_c])
+        with torch.cuda.device(llr_c.device):
+            _native.check(_native.lib().ldpc_residual_layer_fwd(
+                _native.ptr(llr_c), _native.ptr(c2v_c), _native.ptr(wch_c), _native.ptr(wres_c), arr, len(prev_c),
+                B, E, _native.ptr(out), _native.stream_ptr(llr_c.device)))
+        ctx.save_for_backward(llr_c, wch_c, wres_c, *prev_c)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        llr, w_ch, w_res, *prev = ctx.saved_tensors
+        # elementwise products / column sums of the upstream gradient: plain tensor algebra
+        g_llr = g * w_ch.unsqueeze(0)
+        g_wch = (g * llr).sum(dim=0)
+        g_wres = torch.zeros_like(w_res)
+        g_prev = []
+        for i, p in enumerate(prev):
+            g_wres[i] = (g * p).sum()
+            g_prev.append(g * w_res[i])
+        return (g_llr, g, g_wch, g_wres, *g_prev)
+
+
+class _OutputFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, final_llr, llr, gt):
+        _need_cuda(final_llr, llr, gt)
+        f = final_llr.detach().to(torch.float32).contiguous()
+        l = llr.detach().to(torch.float32).contiguous()
+        y = gt.detach().to(torch.float32).contiguous() if gt is not None else None
+        B, E = f.shape
+        soft = torch.empty_like(f)
+        ml = torch.empty(B, dtype=torch.float32, device=f.device) if y is not None else None
+        am = torch.empty(B, dtype=torch.int32, device=f.device) if y is not None else None
+        with torch.cuda.device(f.device):
+            _native.check(_native.lib().ldpc_output_layer_fwd(
+                _native.ptr(f), _native.ptr(l), _native.ptr(y), B, E, _native.ptr(soft), _native.ptr(ml),
+                _native.ptr(am), _native.stream_ptr(f.device)))
+        ctx.has_gt = y is not None
+        if y is not None:
+            ctx.save_for_backward(soft, y, am)
+            ctx.mark_non_differentiable(am)
+            return soft, ml
+        ctx.save_for_backward(soft)
+        return soft, None
+
+    @staticmethod
+    def backward(ctx, g_soft, g_ml):
+        if ctx.has_gt:
+            soft, y, am = ctx.saved_tensors
+        else:
+            (soft,) = ctx.saved_tensors
+        gz = torch.zeros_like(soft)
+        if g_soft is not None:
+            gz = gz + g_soft * soft * (1.0 - soft)
+        if ctx.has_gt and g_ml is not None:
+            # d BCE(sigmoid(z), y)/dz = sigmoid(z) - y at the arg-max bit of each frame
+            rows = torch.arange(soft.shape[0], device=soft.device)
+            cols = am.long()
+            gz[rows, cols] += g_ml * (soft[rows, cols] - y[rows, cols])
+        return gz, gz, None
+
+
+class CheckLayer(nn.Module):
+    def forward(self, input_tensor, check_index_tensor):
+        return _CheckFn.apply(input_tensor, check_index_tensor)
+
+
+class VariableLayer(nn.Module):
+    def forward(self, input_llr, check_messages, var_index_tensor):
+        return _VariableFn.apply(input_llr, check_messages, var_index_tensor)
+
+
+class ResidualLayer(nn.Module):
+    def __init__(self, num_nodes, depth_L=2):
+        super().__init__()
+        self.num_nodes = num_nodes
+        self.depth_L = depth_L
+        self.w_ch = nn.Parameter(torch.ones(num_nodes))
+        self.w_res = nn.Parameter(torch.ones(depth_L))
+
+    def forward(self, input_llr, check_messages, prev_var_messages):
+        prev = list(prev_var_messages)[:self.depth_L]        # reference :164-166 ignores i >= depth_L
+        return _ResidualFn.apply(input_llr, check_messages, self.w_ch, self.w_res, *prev)
+
+
+class OutputLayer(nn.Module):
+    def forward(self, final_llr, input_llr, ground_truth=None):
+        soft, max_loss = _OutputFn.apply(final_llr, input_llr, ground_truth)
+        return soft, max_loss

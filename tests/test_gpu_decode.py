@@ -1,0 +1,235 @@
+"""Parity of the CUDA decoders (through the drop-in classes -> ctypes -> C ABI) with the
+oracle and with the golden vectors of the unmodified reference.  Needs a B200 (-m gpu)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, unpack
+from test_oracle_golden import CLASSIC, fast_order_tolerance_ok
+from oracle import oracle
+import ldpc_b200
+from ldpc_b200 import _native
+from ldpc_b200.models import MinSumScaledDecoder, BeliefPropagationDecoder
+from ldpc_b200.utils import QCCode, expand_base_matrix
+
+pytestmark = pytest.mark.gpu
+
+
+def dev():
+    return torch.device("cuda", 0)
+
+
+def run(dec, llr):
+    soft, hard = dec.forward(torch.from_numpy(np.ascontiguousarray(llr)).to(dev()))
+    torch.cuda.synchronize()
+    return soft.cpu().numpy(), hard.cpu().numpy().astype(np.uint8)
+
+
+# ---- golden vectors of the reference -------------------------------------------------------
+@pytest.mark.parametrize("name", CLASSIC)
+def test_minsum_exact_path_bit_identical_to_reference(name):
+    g = load_golden(name)
+    Z = int(g["Z"])
+    code = QCCode.nr_2_0(Z)
+    dec = MinSumScaledDecoder(code, int(g["iters"]), float(g["alpha"]), early_stopping=False, path="exact")
+    soft, hard = run(dec, g["llr"])
+    assert np.array_equal(hard, unpack(g["ms_bits"], code.N))
+    assert np.array_equal(soft, g["ms_beliefs"])          # the reference's `var_beliefs`, bit for bit
+
+
+@pytest.mark.parametrize("name", CLASSIC)
+def test_minsum_fast_path_against_reference(name):
+    g = load_golden(name)
+    Z = int(g["Z"])
+    code = QCCode.nr_2_0(Z)
+    it, alpha = int(g["iters"]), float(g["alpha"])
+    assert code.has_fast_path(dev())
+    dec = MinSumScaledDecoder(code, it, alpha, early_stopping=False, path="fast")
+    soft, hard = run(dec, g["llr"])
+    assert np.array_equal(hard, unpack(g["ms_bits"], code.N))
+    r = oracle.decode(code.shifts, Z, g["llr"], it, "minsum", alpha, want_mask=True)
+    conv = ((r["valid_mask"][:, (it - 1) >> 6] >> np.uint64((it - 1) & 63)) & np.uint64(1)).astype(bool)
+    assert fast_order_tolerance_ok(soft, g["ms_beliefs"], conv)
+    # and bit-identical to the oracle restated in the kernel's own operation order
+    o = oracle.decode(code.shifts, Z, g["llr"], it, "minsum", alpha, order="fast")
+    assert np.array_equal(soft, o["beliefs"])
+
+
+@pytest.mark.parametrize("name", CLASSIC)
+def test_bp_against_reference_and_oracle(name):
+    g = load_golden(name)
+    Z = int(g["Z"])
+    code = QCCode.nr_2_0(Z)
+    dec = BeliefPropagationDecoder(code, int(g["iters"]), early_stopping=False)
+    soft, hard = run(dec, g["llr"])
+    ref = g["bp_beliefs"]
+    assert np.array_equal(hard, unpack(g["bp_bits"], code.N))
+    assert np.array_equal(np.isnan(ref), np.isnan(soft))
+    assert np.array_equal(np.isposinf(ref), np.isposinf(soft))
+    assert np.array_equal(np.isneginf(ref), np.isneginf(soft))
+    fin = np.isfinite(ref)
+    assert np.all(np.abs(soft[fin] - ref[fin]) <= 2e-4 * np.maximum(np.abs(ref[fin]), 1.0))
+    # same correctly rounded tanh/atanh as the oracle: every bit equal (NaN == NaN)
+    o = oracle.decode(code.shifts, Z, g["llr"], int(g["iters"]), "bp")
+    assert np.array_equal(soft, o["beliefs"], equal_nan=True)
+
+
+def test_reference_early_stopping_rule():
+    g = load_golden("earlystop_z4_b8")
+    code = QCCode.nr_2_0(4)
+    llr = torch.from_numpy(g["llr"]).to(dev())
+    for cls, key, kw in ((MinSumScaledDecoder, "ms", dict(scaling_factor=0.75)), (BeliefPropagationDecoder, "bp", {})):
+        dec = cls(code, max_iterations=int(g["iters"]), early_stopping=True, **kw)
+        bits, iters = dec.decode(llr)
+        assert iters == int(g[key + "_iters"])
+        assert bits.dtype == torch.float32 and bits.shape == llr.shape
+        assert np.array_equal(bits.cpu().numpy().astype(np.uint8), unpack(g[key + "_bits"], code.N))
+        assert bool(dec._check_valid_codeword(bits).all())
+        soft = dec.forward(llr)[0].cpu().numpy()
+        assert np.array_equal(soft, g[key + "_beliefs"])
+
+
+# ---- seeded inputs against the oracle ------------------------------------------------------
+@pytest.mark.parametrize("Z,B,iters,snr_db,alpha", [(32, 97, 10, -2.0, 0.75), (32, 33, 3, -3.0, 0.8), (4, 1001, 5, 2.0, 0.75),
+                                                     (4, 5, 7, -4.0, 0.9), (32, 1, 1, 0.0, 0.75), (16, 40, 6, -1.0, 0.75)])
+def test_minsum_paths_vs_oracle(Z, B, iters, snr_db, alpha):
+    code = QCCode.nr_2_0(Z)
+    llr = oracle.awgn_llr(None, B, code.N, snr_db, seed=Z * 1000 + B)
+    o = oracle.decode(code.shifts, Z, llr, iters, "minsum", alpha)
+    soft, hard = run(MinSumScaledDecoder(code, iters, alpha, early_stopping=False, path="exact"), llr)
+    assert np.array_equal(soft, o["beliefs"]) and np.array_equal(hard, o["hard"])
+    if code.has_fast_path(dev()):
+        of = oracle.decode(code.shifts, Z, llr, iters, "minsum", alpha, order="fast")
+        soft, hard = run(MinSumScaledDecoder(code, iters, alpha, early_stopping=False, path="fast"), llr)
+        assert np.array_equal(soft, of["beliefs"]) and np.array_equal(hard, of["hard"])
+    else:
+        assert Z == 16
+
+
+def test_exact_zeros_ties_and_negative_zero():
+    """sign(0)=0 (reference :217), ties between equal magnitudes, -0.0 < 0 is False."""
+    code = QCCode.nr_2_0(32)
+    rng = np.random.default_rng(3)
+    llr = rng.choice(np.array([-2.0, -1.0, -0.0, 0.0, 1.0, 1.0, 2.0, 3.0], dtype=np.float32), size=(24, code.N))
+    llr[0] = 0.0
+    llr[1] = -0.0
+    llr[2] = 1.5
+    for path, order in (("exact", "reference"), ("fast", "fast")):
+        o = oracle.decode(code.shifts, 32, llr, 6, "minsum", 0.75, order=order)
+        soft, hard = run(MinSumScaledDecoder(code, 6, 0.75, early_stopping=False, path=path), llr)
+        assert np.array_equal(soft, o["beliefs"]), path
+        assert np.array_equal(hard, o["hard"]), path
+        assert not hard[0].any() and not hard[1].any()
+
+
+def test_bp_inf_nan_semantics():
+    """Saturated tanh -> atanh(1)=inf, inf-inf=NaN, NaN<0 False -> bit 0."""
+    code = QCCode.nr_2_0(32)
+    llr = oracle.awgn_llr(None, 32, code.N, 4.0, seed=5)          # high SNR: |llr| ~ 5..30, saturates
+    llr[0, :64] = -llr[0, :64]
+    o = oracle.decode(code.shifts, 32, llr, 10, "bp")
+    soft, hard = run(BeliefPropagationDecoder(code, 10, early_stopping=False), llr)
+    assert np.isinf(soft).any()
+    assert np.array_equal(soft, o["beliefs"], equal_nan=True) and np.array_equal(hard, o["hard"])
+    assert not hard[np.isnan(soft)].any()
+
+
+def test_non_qc_toy_matrix_and_dense_H_constructor():
+    """Decoder(H) with the notebook's 3x4 H (Z=1 tables) and with a dense BG2 Z=4 H."""
+    H = torch.tensor([[1, 1, 0, 0], [0, 1, 1, 1], [1, 0, 0, 1]], dtype=torch.float32)
+    llr = np.array([[0.0, 0.0, 0.0, 0.0], [-0.3, 0.7, -0.9, 0.2], [2.0, -1.0, 0.5, 0.1]], dtype=np.float32)
+    shifts = QCCode.from_dense(H).shifts
+    for cls, algo in ((MinSumScaledDecoder, "minsum"), (BeliefPropagationDecoder, "bp")):
+        dec = cls(H, max_iterations=4, early_stopping=False)
+        soft, hard = run(dec, llr)
+        o = oracle.decode(shifts, 1, llr, 4, algo, 0.75)
+        assert np.array_equal(soft, o["beliefs"], equal_nan=True) and np.array_equal(hard, o["hard"])
+    code = QCCode.nr_2_0(4)
+    dec = MinSumScaledDecoder(code.dense(), max_iterations=3, early_stopping=False)
+    assert dec.code.Z == 4 and np.array_equal(dec.code.shifts, code.shifts)
+
+
+def test_output_formats_syndrome_and_per_codeword_stop():
+    code = QCCode.nr_2_0(32)
+    B, iters = 70, 12
+    llr = oracle.awgn_llr(None, B, code.N, -1.5, seed=11)
+    llr_t = torch.from_numpy(llr).to(dev())
+    o = oracle.decode(code.shifts, 32, llr, iters, "minsum", 0.75, want_mask=True, stop_when_valid=True)
+    for path, order in (("exact", "reference"), ("fast", "fast")):
+        of = oracle.decode(code.shifts, 32, llr, iters, "minsum", 0.75, order=order, want_mask=True)
+        dec = MinSumScaledDecoder(code, iters, 0.75, early_stopping=False, path=path)
+        for dtype in (_native.HARD_F32, _native.HARD_U8, _native.HARD_PACKED):
+            _, hard, syn, its, _ = dec._launch(llr_t, dev(), iters, hard_dtype=dtype, syndrome=True, iters_out=True)
+            h = hard.cpu().numpy()
+            if dtype == _native.HARD_PACKED:
+                h = np.unpackbits(h.view(np.uint8), axis=1, bitorder="little")[:, :code.N]
+            assert np.array_equal(h.astype(np.uint8), of["hard"]), (path, dtype)
+            last = ((of["valid_mask"][:, 0] >> np.uint64(iters - 1)) & np.uint64(1)).astype(np.uint8)
+            assert np.array_equal(syn.cpu().numpy(), last)
+            assert (its.cpu().numpy() == iters).all()
+    # per-codeword early exit (exact path): iteration counts and frozen outputs as the oracle
+    dec = MinSumScaledDecoder(code, iters, 0.75, early_stopping=True)
+    bits, its, ok = dec.decode_with_iterations(llr_t)
+    assert np.array_equal(its.cpu().numpy(), o["iters"])
+    assert np.array_equal(bits.cpu().numpy().astype(np.uint8), o["hard"])
+    assert np.array_equal(ok.cpu().numpy(), o["iters"] < iters) or ok.cpu().numpy()[o["iters"] == iters].any()
+    # validity mask of the C ABI == oracle's
+    _, _, _, _, mask = MinSumScaledDecoder(code, iters, 0.75, early_stopping=False)._launch(llr_t, dev(), iters, mask=True)
+    ref_mask = oracle.decode(code.shifts, 32, llr, iters, "minsum", 0.75, want_mask=True)["valid_mask"]
+    assert np.array_equal(mask.cpu().numpy().view(np.uint64), ref_mask)
+
+
+def test_empty_ragged_and_cpu_inputs():
+    code = QCCode.nr_2_0(4)
+    dec = MinSumScaledDecoder(code, 3, 0.75, early_stopping=False)
+    bits, it = dec.decode(torch.zeros((0, code.N), device=dev()))
+    assert bits.shape == (0, code.N) and it == 3
+    with pytest.raises(ValueError):
+        dec.decode(torch.zeros((2, code.N + 1), device=dev()))
+    llr = oracle.awgn_llr(None, 13, code.N, 1.0, seed=2)      # 13 is not a multiple of 8 codewords/warp
+    bits_cpu, _ = dec.decode(torch.from_numpy(llr))           # CPU tensor: staged through the GPU
+    assert not bits_cpu.is_cuda
+    o = oracle.decode(code.shifts, 4, llr, 3, "minsum", 0.75, order="fast")
+    assert np.array_equal(bits_cpu.numpy().astype(np.uint8), o["hard"])
+    # float64 / non-contiguous input is converted like the reference's float tensors
+    bits2, _ = dec.decode(torch.from_numpy(llr.astype(np.float64)).to(dev()))
+    assert np.array_equal(bits2.cpu().numpy().astype(np.uint8), o["hard"])
+
+
+def test_host_buffer_entry_point():
+    """ldpc_decode_host (the e2e path of bench.py): pinned host LLRs in, host bits out."""
+    import ctypes as C
+    code = QCCode.nr_2_0(32)
+    B, iters = 3000, 10
+    llr = oracle.awgn_llr(None, B, code.N, -2.0, seed=21)
+    pinned = torch.from_numpy(llr).pin_memory()
+    hard = torch.empty((B, (code.N + 31) // 32), dtype=torch.int32).pin_memory()
+    soft = torch.empty((B, code.N), dtype=torch.float32).pin_memory()
+    _native.check(_native.lib().ldpc_decode_host(code.handle(dev()), _native.ALGO_MINSUM, _native.ptr(pinned), B, iters, 0.75,
+                                                 _native.PATH_AUTO, _native.ptr(soft), _native.ptr(hard),
+                                                 _native.HARD_PACKED, 1024))
+    o = oracle.decode(code.shifts, 32, llr, iters, "minsum", 0.75, order="fast")
+    h = np.unpackbits(hard.numpy().view(np.uint8), axis=1, bitorder="little")[:, :code.N]
+    assert np.array_equal(h, o["hard"]) and np.array_equal(soft.numpy(), o["beliefs"])
+
+
+def test_linearity_at_full_batch_size():
+    """Size-independent property at a bench-sized batch: min-sum is odd-symmetric under a
+    codeword flip -- decoding llr*(1-2c) for a codeword c gives the decisions XOR c -- and
+    the all-zero codeword decodes to zero with a valid syndrome at high SNR."""
+    code = QCCode.nr_2_0(32)
+    B, iters = 1 << 15, 10
+    ch_llr = torch.empty((B, code.N), dtype=torch.float32, device=dev())
+    _native.check(_native.lib().ldpc_awgn_llr(None, B, code.N, 1.0, 99, 0, _native.ptr(ch_llr), _native.stream_ptr(dev())))
+    dec = MinSumScaledDecoder(code, iters, 0.75, early_stopping=False)
+    _, hard, syn, _, _ = dec._launch(ch_llr, dev(), iters, hard_dtype=_native.HARD_U8, syndrome=True)
+    assert int(hard.sum()) == 0 and bool(syn.all())
+    # a non-zero codeword from the decoder itself: decode noise-free +-1 pattern found by flipping
+    base = oracle.awgn_llr(None, 8, code.N, -3.5, seed=77)
+    o = oracle.decode(code.shifts, 32, base, 50, "minsum", 0.75, want_mask=True)
+    valid = [b for b in range(8) if ((o["valid_mask"][b, 0] >> np.uint64(49)) & np.uint64(1)) and o["hard"][b].any()]
+    if valid:
+        c = torch.from_numpy(o["hard"][valid[0]].astype(np.float32)).to(dev())
+        flipped = ch_llr[:4096] * (1.0 - 2.0 * c)
+        _, h2, s2, _, _ = dec._launch(flipped.contiguous(), dev(), iters, hard_dtype=_native.HARD_U8, syndrome=True)
+        assert bool((h2.float() == c).all()) and bool(s2.all())
