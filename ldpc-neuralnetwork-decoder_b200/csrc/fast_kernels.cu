@@ -1,0 +1,44 @@
+// fast_kernels.cu -- translation unit of the fully unrolled specialised kernels
+// (decode_fast_kernel.cuh) and their launcher.  Separate from ldpc_b200.cu so the two compile
+// in parallel (the unrolled kernels dominate build time).
+#include "decode_fast.cuh"
+#include "decode_fast_kernel.cuh"
+
+namespace ldpc {
+
+#ifndef LDPC_FAST_WARPS
+#define LDPC_FAST_WARPS 8
+#endif
+constexpr int kFastWarps = LDPC_FAST_WARPS;
+
+template <class BG>
+inline int launch_fast_inst(DecodeParams p, cudaStream_t st) {
+    constexpr int G = 32 / BG::kZ;
+    constexpr size_t smem = (size_t)kFastWarps * ((BG::kCoreEdges + 3) / 4 + (BG::kCoreCols + 3) / 4) * 32 * sizeof(float4);
+    static_assert(smem <= (size_t)kMaxSmemPerBlock, "fast kernel shared memory");
+    auto kern = minsum_fast_kernel<BG, kFastWarps>;
+    LDPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    p.ngroups = (p.B + G - 1) / G;
+    long long blocks = (p.ngroups + kFastWarps - 1) / kFastWarps;
+    if (blocks > kNumSMs) blocks = kNumSMs;
+    kern<<<(int)blocks, kFastWarps * 32, smem, st>>>(p);
+    LDPC_COUNT_LAUNCH();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        cudaFuncAttributes a{};
+        cudaFuncGetAttributes(&a, kern);
+        return fail(LDPC_ERR_CUDA, "launch of minsum_fast_kernel failed: %s (regs %d, max threads/block %d, static smem %zu, "
+                    "max dynamic smem %d, requested %d threads + %zu B)", cudaGetErrorString(e), a.numRegs,
+                    a.maxThreadsPerBlock, a.sharedSizeBytes, a.maxDynamicSharedSizeBytes, kFastWarps * 32, smem);
+    }
+    return LDPC_OK;
+}
+
+int launch_fast(const ldpc_code* c, int algo, const DecodeParams& p, cudaStream_t st) {
+    (void)algo;
+    if (c->fast_kind == 1) return launch_fast_inst<BG2Z32>(p, st);
+    if (c->fast_kind == 2) return launch_fast_inst<BG2Z4>(p, st);
+    return fail(LDPC_ERR_UNSUPPORTED, "fast path: code is not one of the compiled tables");
+}
+
+}  // namespace ldpc

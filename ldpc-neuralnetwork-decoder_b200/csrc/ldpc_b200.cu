@@ -5,7 +5,7 @@
 #include "tables.cuh"
 #include "decode_exact.cuh"
 #include "decode_fast.cuh"
-#include "channel.cuh"
+#include "channel_kernels.cuh"
 #include "layers.cuh"
 #include "gnn.cuh"
 
@@ -31,8 +31,8 @@ struct DeviceGuard {
 int check_decode_args(const ldpc_code_t* code, const float* llr, int64_t B, int iters, int stop_mode, int path,
                       int hard_dtype, const uint64_t* valid_mask, int mask_words) {
     if (!code) return fail(LDPC_ERR_INVALID, "decode: null code handle");
-    if (!llr) return fail(LDPC_ERR_INVALID, "decode: null llr pointer");
     if (B < 0) return fail(LDPC_ERR_INVALID, "decode: negative batch %lld", (long long)B);
+    if (!llr && B > 0) return fail(LDPC_ERR_INVALID, "decode: null llr pointer");
     if (iters < 1) return fail(LDPC_ERR_INVALID, "decode: iters=%d, need >= 1", iters);
     if (stop_mode != LDPC_STOP_FIXED && stop_mode != LDPC_STOP_PER_CODEWORD)
         return fail(LDPC_ERR_INVALID, "decode: unknown stop_mode %d", stop_mode);
@@ -108,6 +108,10 @@ int ldpc_code_destroy(ldpc_code_t* code) {
     {
         DeviceGuard g(code->device);
         if (code->d_tab) cudaFree(code->d_tab);
+        for (int s = 0; s < HostStage::kStages; ++s) {
+            if (code->stage.st[s]) { cudaStreamSynchronize(code->stage.st[s]); cudaStreamDestroy(code->stage.st[s]); }
+            cudaFree(code->stage.d_llr[s]); cudaFree(code->stage.d_hard[s]); cudaFree(code->stage.d_soft[s]);
+        }
     }
     if (code->slot >= 0) {
         std::lock_guard<std::mutex> lk(slot_mutex());
@@ -146,57 +150,61 @@ int ldpc_bp_decode(const ldpc_code_t* code, const float* llr, int64_t B, int ite
 int ldpc_decode_host(const ldpc_code_t* code, int algo, const float* llr_host, int64_t B, int iters, float alpha,
                      int path, float* soft_host, void* hard_host, int hard_dtype, int64_t chunk) {
     if (!code) return fail(LDPC_ERR_INVALID, "decode_host: null code handle");
+    if (B < 0) return fail(LDPC_ERR_INVALID, "decode_host: negative batch");
+    if (B == 0) return LDPC_OK;
     if (!llr_host || !hard_host) return fail(LDPC_ERR_INVALID, "decode_host: null host buffer");
     if (algo != LDPC_ALGO_MINSUM && algo != LDPC_ALGO_BP) return fail(LDPC_ERR_INVALID, "decode_host: unknown algo %d", algo);
     if (hard_dtype < LDPC_HARD_F32 || hard_dtype > LDPC_HARD_PACKED) return fail(LDPC_ERR_INVALID, "decode_host: unknown hard_dtype");
-    if (B <= 0) return B == 0 ? LDPC_OK : fail(LDPC_ERR_INVALID, "decode_host: negative batch");
     DeviceGuard g(code->device);
     if (!g.ok) return fail(LDPC_ERR_CUDA, "decode_host: cannot select device %d", code->device);
     const int N = code->N;
-    if (chunk <= 0) chunk = 1 << 16;
+    if (chunk <= 0) chunk = 1 << 15;
     if (chunk > B) chunk = B;
     const size_t hard_row = hard_dtype == LDPC_HARD_F32 ? sizeof(float) * N
                           : hard_dtype == LDPC_HARD_U8 ? (size_t)N : sizeof(uint32_t) * ((N + 31) / 32);
-    constexpr int kStages = 3;
-    cudaStream_t st[kStages] = {};
-    float* d_llr[kStages] = {};
-    float* d_soft[kStages] = {};
-    char* d_hard[kStages] = {};
-    int rc = LDPC_OK;
-    auto cleanup = [&]() {
-        for (int s = 0; s < kStages; ++s) {
-            if (st[s]) { cudaStreamSynchronize(st[s]); cudaStreamDestroy(st[s]); }
-            cudaFree(d_llr[s]); cudaFree(d_soft[s]); cudaFree(d_hard[s]);
+    // staging buffers and streams live in the handle and are reused by later calls
+    HostStage& hs = code->stage;
+    std::lock_guard<std::mutex> lk(hs.mu);
+    const size_t need_llr = sizeof(float) * (size_t)chunk * N, need_hard = hard_row * (size_t)chunk;
+    const size_t need_soft = soft_host ? need_llr : 0;
+    for (int s = 0; s < HostStage::kStages; ++s) {
+        if (!hs.st[s]) LDPC_CUDA(cudaStreamCreateWithFlags(&hs.st[s], cudaStreamNonBlocking));
+        if (hs.cap_llr[s] < need_llr) {
+            LDPC_CUDA(cudaStreamSynchronize(hs.st[s]));
+            cudaFree(hs.d_llr[s]); hs.d_llr[s] = nullptr; hs.cap_llr[s] = 0;
+            LDPC_CUDA(cudaMalloc(&hs.d_llr[s], need_llr)); hs.cap_llr[s] = need_llr;
         }
-    };
-#define HOST_TRY(expr)                                                                                     \
-    do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup();                                      \
-         return fail(LDPC_ERR_CUDA, "decode_host: %s: %s", #expr, cudaGetErrorString(_e)); } } while (0)
-    for (int s = 0; s < kStages; ++s) {
-        HOST_TRY(cudaStreamCreateWithFlags(&st[s], cudaStreamNonBlocking));
-        HOST_TRY(cudaMalloc(&d_llr[s], sizeof(float) * (size_t)chunk * N));
-        HOST_TRY(cudaMalloc(&d_hard[s], hard_row * (size_t)chunk));
-        if (soft_host) HOST_TRY(cudaMalloc(&d_soft[s], sizeof(float) * (size_t)chunk * N));
+        if (hs.cap_hard[s] < need_hard) {
+            LDPC_CUDA(cudaStreamSynchronize(hs.st[s]));
+            cudaFree(hs.d_hard[s]); hs.d_hard[s] = nullptr; hs.cap_hard[s] = 0;
+            LDPC_CUDA(cudaMalloc(&hs.d_hard[s], need_hard)); hs.cap_hard[s] = need_hard;
+        }
+        if (hs.cap_soft[s] < need_soft) {
+            LDPC_CUDA(cudaStreamSynchronize(hs.st[s]));
+            cudaFree(hs.d_soft[s]); hs.d_soft[s] = nullptr; hs.cap_soft[s] = 0;
+            LDPC_CUDA(cudaMalloc(&hs.d_soft[s], need_soft)); hs.cap_soft[s] = need_soft;
+        }
     }
     int64_t done = 0;
     for (int it = 0; done < B; ++it, done += chunk) {
-        const int s = it % kStages;
+        const int s = it % HostStage::kStages;
         const int64_t b = (B - done) < chunk ? (B - done) : chunk;
         // same-stream ordering makes reuse of stage s safe: its previous D2H precedes this H2D
-        HOST_TRY(cudaMemcpyAsync(d_llr[s], llr_host + (size_t)done * N, sizeof(float) * (size_t)b * N, cudaMemcpyHostToDevice, st[s]));
-        rc = decode_common(code, algo, d_llr[s], b, iters, alpha, LDPC_STOP_FIXED, path, d_soft[s], d_hard[s], hard_dtype,
-                           nullptr, nullptr, nullptr, 0, st[s]);
-        if (rc) { cleanup(); return rc; }
-        HOST_TRY(cudaMemcpyAsync((char*)hard_host + hard_row * (size_t)done, d_hard[s], hard_row * (size_t)b, cudaMemcpyDeviceToHost, st[s]));
+        LDPC_CUDA(cudaMemcpyAsync(hs.d_llr[s], llr_host + (size_t)done * N, sizeof(float) * (size_t)b * N,
+                                  cudaMemcpyHostToDevice, hs.st[s]));
+        int rc = decode_common(code, algo, (const float*)hs.d_llr[s], b, iters, alpha, LDPC_STOP_FIXED, path,
+                               soft_host ? (float*)hs.d_soft[s] : nullptr, hs.d_hard[s], hard_dtype, nullptr, nullptr,
+                               nullptr, 0, hs.st[s]);
+        if (rc) return rc;
+        LDPC_CUDA(cudaMemcpyAsync((char*)hard_host + hard_row * (size_t)done, hs.d_hard[s], hard_row * (size_t)b,
+                                  cudaMemcpyDeviceToHost, hs.st[s]));
         if (soft_host)
-            HOST_TRY(cudaMemcpyAsync(soft_host + (size_t)done * N, d_soft[s], sizeof(float) * (size_t)b * N, cudaMemcpyDeviceToHost, st[s]));
+            LDPC_CUDA(cudaMemcpyAsync(soft_host + (size_t)done * N, hs.d_soft[s], sizeof(float) * (size_t)b * N,
+                                      cudaMemcpyDeviceToHost, hs.st[s]));
     }
-    for (int s = 0; s < kStages; ++s) HOST_TRY(cudaStreamSynchronize(st[s]));
-#undef HOST_TRY
-    cleanup();
+    for (int s = 0; s < HostStage::kStages; ++s) LDPC_CUDA(cudaStreamSynchronize(hs.st[s]));
     return LDPC_OK;
 }
-
 
 // ---- channel + metrics ------------------------------------------------------------------
 static int make_gen(float snr_db, uint64_t seed, uint64_t first_frame, GenParams* g) {

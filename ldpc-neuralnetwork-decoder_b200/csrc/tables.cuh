@@ -41,6 +41,18 @@ struct Tab {
 
 }  // namespace ldpc
 
+// Device staging buffers + streams of ldpc_decode_host, owned by the handle and reused
+// across calls (H2D / decode / D2H of consecutive chunks overlap on three streams).
+struct HostStage {
+    static constexpr int kStages = 3;
+    std::mutex mu;
+    cudaStream_t st[kStages] = {};
+    void* d_llr[kStages] = {};
+    void* d_soft[kStages] = {};
+    char* d_hard[kStages] = {};
+    size_t cap_llr[kStages] = {}, cap_soft[kStages] = {}, cap_hard[kStages] = {};
+};
+
 struct ldpc_code {
     int device = 0;
     int rows = 0, cols = 0, Z = 0, E = 0, N = 0, M = 0, G = 0, maxdc = 0, maxdv = 0;
@@ -50,6 +62,7 @@ struct ldpc_code {
     int fast_kind = 0;             // 0 none, 1 = 5G BG2 set 0 at Z=32 (the NR_2_0_32 table)
     std::vector<uint32_t> h_tab;
     std::vector<int16_t> shifts;   // rows*cols
+    mutable HostStage stage;
 };
 
 namespace ldpc {

@@ -147,10 +147,12 @@ class _OutputFn(torch.autograd.Function):
         if g_soft is not None:
             gz = gz + g_soft * soft * (1.0 - soft)
         if ctx.has_gt and g_ml is not None:
-            # d BCE(sigmoid(z), y)/dz = sigmoid(z) - y at the arg-max bit of each frame
+            # chain of torch's own backward formulas at the arg-max bit of each frame:
+            # BCE' = (s - y) / max(s (1 - s), 1e-12), sigmoid' = s (1 - s)  (vanishes when saturated)
             rows = torch.arange(soft.shape[0], device=soft.device)
             cols = am.long()
-            gz[rows, cols] += g_ml * (soft[rows, cols] - y[rows, cols])
+            s, t = soft[rows, cols], y[rows, cols]
+            gz[rows, cols] += g_ml * (s - t) / torch.clamp_min((1.0 - s) * s, 1e-12) * (s * (1.0 - s))
         return gz, gz, None
 
 

@@ -64,6 +64,8 @@ class _FloodingDecoder:
         it_t = torch.empty(B, dtype=torch.int32, device=dev) if iters_out else None
         words = (iters + 63) // 64
         mask_t = torch.empty((B, words), dtype=torch.int64, device=dev) if mask else None
+        if B == 0:
+            return soft_t, hard_t, syn_t, it_t, mask_t
         L = _native.lib()
         h = self.code.handle(dev)
         p = _native.PATHS[path or self.path]
