@@ -30,6 +30,12 @@ K_INFO, N_BITS, BASE_EDGES, Z = 320, 1664, 197, 32
 ITERS, ALPHA, SNR_DB = 10, 0.75, -2.0
 ISSUE_SLOTS_PER_EDGE_ITER = 18          # 14 ALU + 4 MIO lane-ops per edge-iteration
 SM_COUNT = 148
+# Binding resource of the min-sum kernel (ncu: l1tex__data_pipe_lsu_wavefronts_mem_shared is the
+# busiest unit): the shared-memory/shuffle data pipe, 1 wavefront (32 lanes x 4 B) per clock per
+# SM.  Algorithmic wavefronts per codeword-iteration of BG2 (DESIGN.md "Roofline"): 159 core
+# cells x (1 load + 1 store of the resident message) + 145 shifted core cells x 2 rotations +
+# 14 channel-LLR reloads = 622.  Degree-1 columns and unshifted cells need no rotation.
+SMEM_WAVEFRONTS_PER_CW_ITER = 159 * 2 + 145 * 2 + 14
 
 
 def measured_peaks():
@@ -249,10 +255,13 @@ def main():
     if rank == 0:
         peaks, peak_src = measured_peaks()
         kernel_ms = step_ms[len(step_ms) // 2]                    # median launch (decode + tiny count kernel)
-        edge_iters = B * BASE_EDGES * Z * ITERS
-        achieved = edge_iters / (kernel_ms * 1e-3) / 1e9          # G edge-iterations / s, one GPU
         sm_max = float(peaks.get("sm_max_mhz", 1965.0))
-        peak = SM_COUNT * 4 * 32 * sm_max * 1e6 / ISSUE_SLOTS_PER_EDGE_ITER / 1e9
+        wavefronts = B * SMEM_WAVEFRONTS_PER_CW_ITER * ITERS
+        achieved = wavefronts / (kernel_ms * 1e-3) / 1e9          # G wavefronts / s, one GPU
+        peak = SM_COUNT * sm_max * 1e6 / 1e9                      # 1 wavefront / clk / SM
+        edge_iters = B * BASE_EDGES * Z * ITERS
+        issue_ach = edge_iters / (kernel_ms * 1e-3) / 1e9
+        issue_peak = SM_COUNT * 4 * 32 * sm_max * 1e6 / ISSUE_SLOTS_PER_EDGE_ITER / 1e9
         algo_bytes = B * (code.N * 4 + NW * 4)
         hbm_ach = algo_bytes / (kernel_ms * 1e-3) / 1e9
         out = {
@@ -267,12 +276,16 @@ def main():
             "e2e": {"value": e2e_value, "unit": "Gbit/s", "h2d_bytes_per_step": Be * code.N * 4,
                     "d2h_bytes_per_step": Be * NW * 4, "codewords_per_step": Be, "steps": args.e2e_steps,
                     "api": "ldpc_decode_host (pinned host LLRs -> packed hard bits)"},
-            "roofline": {"bound": "issue", "achieved": achieved, "peak": peak, "unit": "Gedge-iter/s",
+            "roofline": {"bound": "smem_pipe", "achieved": achieved, "peak": peak, "unit": "Gwavefront/s",
                          "frac": achieved / peak, "traffic": None,
-                         "model": f"{ISSUE_SLOTS_PER_EDGE_ITER} issue slots per edge-iteration (SURVEY 8d), 148 SMs x 4 "
-                                  f"warp-instr/clk at {sm_max:.0f} MHz ({peak_src} max clock)",
+                         "model": f"{SMEM_WAVEFRONTS_PER_CW_ITER} shared-memory/shuffle wavefronts per codeword-iteration "
+                                  f"(algorithmic, DESIGN.md), 148 SMs x 1 wavefront/clk at {sm_max:.0f} MHz ({peak_src} max clock)",
                          "frac_at_measured_clock": (achieved / (peak * clocks["sm_mhz"] / sm_max)) if clocks and clocks.get("sm_mhz") else None,
                          "kernel_ms": kernel_ms,
+                         "survey_issue_model": {"achieved": issue_ach, "peak": issue_peak, "unit": "Gedge-iter/s",
+                                                "frac": issue_ach / issue_peak,
+                                                "note": "SURVEY 8d estimate of 18 issue slots per edge-iteration; the kernel "
+                                                        "issues 9.4, so this fraction can exceed 1"},
                          "hbm": {"bound": "hbm", "achieved": hbm_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                  "frac": hbm_ach / peaks["hbm_gbs"], "algorithmic_bytes_per_codeword": code.N * 4 + NW * 4,
                                  "peak_source": peak_src}},

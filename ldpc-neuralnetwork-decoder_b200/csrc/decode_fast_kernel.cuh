@@ -107,6 +107,17 @@ __global__ void __launch_bounds__(kWarps * 32, 1) minsum_fast_kernel(const Decod
             static_for<0, BG::kCols>([&](auto jc) {
                 put_llr(jc, live ? __ldg(llr + decltype(jc)::value * Z) : 0.0f);
             });
+            // pull the LLR rows of this warp's NEXT group into L2 while this one is decoded
+            const long long ngrp = grp + (long long)gridDim.x * kWarps;
+            if (ngrp < p.ngroups) {
+                const char* nxt = reinterpret_cast<const char*>(p.llr + ngrp * G * N);
+                const long long bytes = (((ngrp + 1) * G <= p.B) ? (long long)G : (p.B - ngrp * G)) * N * (long long)sizeof(float);
+#pragma unroll
+                for (int q = 0; q < (G * N * 4 + 32 * 128 - 1) / (32 * 128); ++q) {
+                    const long long off = ((long long)q * 32 + lane) * 128;
+                    if (off < bytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + off));
+                }
+            }
         }
         static_for<0, EQ>([&](auto qc) { mq[decltype(qc)::value * 32] = make_float4(0.f, 0.f, 0.f, 0.f); });
 
@@ -181,38 +192,49 @@ __global__ void __launch_bounds__(kWarps * 32, 1) minsum_fast_kernel(const Decod
         iteration(IC<1>{});
 
         // ---- outputs: Tc = posteriors of the core columns, Lx = posteriors of the degree-1 columns ----
-        unsigned long long xneg = 0;
-        unsigned hw[NWR];
-#pragma unroll
-        for (int q = 0; q < NWR; ++q) hw[q] = 0;
-        static_for<0, BG::kCols>([&](auto jc) {
+        // (the output mode is tested once, not per column: each mode is its own unrolled store loop)
+        auto belief_of = [&](auto jc) -> float {
             constexpr int j = decltype(jc)::value, sl = BG::col_slot[j];
-            float belief;
-            if constexpr (BG::col_kind[j] == 0) belief = Tc[sl];
-            else belief = Lx[sl];
-            const bool neg = belief < 0.0f;
-            if constexpr (BG::col_kind[j] != 0) xneg |= neg ? (1ull << sl) : 0ull;
-            if (p.soft_out && live) p.soft_out[cw * N + j * Z + r] = belief;
-            if (p.hard_out) {
-                if (p.hard_dtype == LDPC_HARD_F32) {
-                    if (live) ((float*)p.hard_out)[cw * N + j * Z + r] = neg ? 1.0f : 0.0f;
-                } else if (p.hard_dtype == LDPC_HARD_U8) {
-                    if (live) ((uint8_t*)p.hard_out)[cw * N + j * Z + r] = neg ? 1 : 0;
-                } else {
-                    const unsigned b = __ballot_sync(kFull, neg);
+            if constexpr (BG::col_kind[j] == 0) return Tc[sl];
+            else return Lx[sl];
+        };
+        if (p.soft_out && live) {
+            float* o = p.soft_out + cw * N + r;
+            static_for<0, BG::kCols>([&](auto jc) { o[decltype(jc)::value * Z] = belief_of(jc); });
+        }
+        if (p.hard_out) {
+            if (p.hard_dtype == LDPC_HARD_PACKED) {
+                unsigned hw[NWR];
+#pragma unroll
+                for (int q = 0; q < NWR; ++q) hw[q] = 0;
+                static_for<0, BG::kCols>([&](auto jc) {
+                    constexpr int j = decltype(jc)::value;
+                    const unsigned b = __ballot_sync(kFull, belief_of(jc) < 0.0f);
                     constexpr int wj = (j * Z) >> 5, off = (j * Z) & 31;
                     const unsigned mine = (Z == 32) ? b : ((b >> (cwi * Z)) & ((1u << (Z & 31)) - 1u));
                     if (r == wj % Z) hw[wj / Z] |= mine << off;
+                });
+                if (live) {
+#pragma unroll
+                    for (int q = 0; q < NWR; ++q)
+                        if (q * Z + r < NW) ((unsigned*)p.hard_out)[cw * NW + q * Z + r] = hw[q];
+                }
+            } else if (p.hard_dtype == LDPC_HARD_F32) {
+                if (live) {
+                    float* o = (float*)p.hard_out + cw * N + r;
+                    static_for<0, BG::kCols>([&](auto jc) { o[decltype(jc)::value * Z] = belief_of(jc) < 0.0f ? 1.0f : 0.0f; });
+                }
+            } else {
+                if (live) {
+                    uint8_t* o = (uint8_t*)p.hard_out + cw * N + r;
+                    static_for<0, BG::kCols>([&](auto jc) { o[decltype(jc)::value * Z] = belief_of(jc) < 0.0f ? 1 : 0; });
                 }
             }
-        });
-        if (p.hard_out && p.hard_dtype == LDPC_HARD_PACKED && live) {
-#pragma unroll
-            for (int q = 0; q < NWR; ++q)
-                if (q * Z + r < NW) ((unsigned*)p.hard_out)[cw * NW + q * Z + r] = hw[q];
         }
         if (p.iters_out && live && r == 0) p.iters_out[cw] = p.iters;
         if (p.syndrome_ok || p.counters) {
+            unsigned long long xneg = 0;      // hard decisions of the degree-1 columns
+            static_for<0, NX>([&](auto xc) { xneg |= Lx[decltype(xc)::value] < 0.0f ? (1ull << decltype(xc)::value) : 0ull; });
             unsigned bad = 0;
             static_for<0, BG::kRows>([&](auto ic) {
                 constexpr int i = decltype(ic)::value;
