@@ -362,18 +362,142 @@ int ldpc_output_layer_fwd(const float* final_llr, const float* llr, const float*
 }
 
 // ---- message-centred GNN -------------------------------------------------------------------
-int ldpc_gnn_create(const ldpc_code_t*, int, int, int, const int32_t*, ldpc_gnn_t** out) {
-    if (out) *out = nullptr;
-    return fail(LDPC_ERR_UNSUPPORTED, "gnn: not built yet");
+static size_t gnn_bytes_per_codeword(const ldpc_gnn_t* g) {
+    return (size_t)(2 * (size_t)g->E + g->N + g->M) * kH * sizeof(float);
 }
-int ldpc_gnn_destroy(ldpc_gnn_t* g) { delete g; return LDPC_OK; }
-size_t ldpc_gnn_param_count(const ldpc_gnn_t*) { return 0; }
-size_t ldpc_gnn_workspace_bytes(const ldpc_gnn_t*, int64_t, int) { return 0; }
-int ldpc_gnn_forward(const ldpc_gnn_t*, const float*, const float*, int64_t, float*, float*, void*, size_t, int, void*) {
-    return fail(LDPC_ERR_UNSUPPORTED, "gnn: not built yet");
+
+int ldpc_gnn_create(const ldpc_code_t* code, int num_layers, int hidden, int num_types, const int32_t* edge_type,
+                    ldpc_gnn_t** out) {
+    if (!out) return fail(LDPC_ERR_INVALID, "gnn_create: null out pointer");
+    *out = nullptr;
+    if (!code) return fail(LDPC_ERR_INVALID, "gnn_create: null code handle");
+    if (hidden != kH) return fail(LDPC_ERR_UNSUPPORTED, "gnn_create: hidden_dim %d (kernels are built for %d)", hidden, kH);
+    if (num_layers < 1 || num_layers > 64) return fail(LDPC_ERR_INVALID, "gnn_create: num_layers %d", num_layers);
+    if (num_types < 1) return fail(LDPC_ERR_INVALID, "gnn_create: num_types %d", num_types);
+    const int Z = code->Z, rows = code->rows, cols = code->cols;
+    ldpc_gnn* g = new (std::nothrow) ldpc_gnn();
+    if (!g) return fail(LDPC_ERR_NOMEM, "gnn_create: out of host memory");
+    g->code = code; g->device = code->device; g->layers = num_layers; g->hidden = hidden; g->types = num_types;
+    g->E = code->E * Z; g->N = code->N; g->M = code->M;
+    GnnLayout lay{num_types};
+    g->params = (size_t)lay.total(num_layers);
+    // message list in the reference's order (message_gnn_decoder.py:397-406): check-major, ascending variable
+    std::vector<int> ev(g->E), ec(g->E), et(g->E), cptr(g->M + 1), vptr(g->N + 1, 0), vedge(g->E);
+    const uint32_t* t = code->h_tab.data();
+    const int off_rowptr = t[7], off_redge = t[9];
+    int e = 0;
+    for (int i = 0; i < rows; ++i)
+        for (int r = 0; r < Z; ++r) {
+            cptr[i * Z + r] = e;
+            for (int k = (int)t[off_rowptr + i]; k < (int)t[off_rowptr + i + 1]; ++k) {
+                const int j = t[off_redge + k] & 0xffff, s = (t[off_redge + k] >> 16) & 0xff;
+                ev[e] = j * Z + (r + s) % Z;
+                ec[e] = i * Z + r;
+                int ty = edge_type ? edge_type[k] : 0;
+                ty = ty < 0 ? 0 : (ty >= num_types ? num_types - 1 : ty);      // clamp, as :81
+                et[e] = ty;
+                ++e;
+            }
+        }
+    cptr[g->M] = e;
+    (void)cols;
+    for (int x = 0; x < g->E; ++x) vptr[ev[x] + 1]++;
+    for (int v = 0; v < g->N; ++v) vptr[v + 1] += vptr[v];
+    std::vector<int> fill(g->N, 0);
+    for (int x = 0; x < g->E; ++x) vedge[vptr[ev[x]] + fill[ev[x]]++] = x;
+    DeviceGuard dg(g->device);
+    if (!dg.ok) { delete g; return fail(LDPC_ERR_CUDA, "gnn_create: cannot select device"); }
+    auto up = [&](int** dst, const std::vector<int>& src) -> bool {
+        if (cudaMalloc(dst, sizeof(int) * src.size()) != cudaSuccess) return false;
+        return cudaMemcpy(*dst, src.data(), sizeof(int) * src.size(), cudaMemcpyHostToDevice) == cudaSuccess;
+    };
+    bool ok = up(&g->d_edge_var, ev) && up(&g->d_edge_chk, ec) && up(&g->d_edge_type, et) && up(&g->d_var_ptr, vptr) &&
+              up(&g->d_var_edge, vedge) && up(&g->d_chk_ptr, cptr) &&
+              cudaMalloc(&g->d_packed, sizeof(float) * (size_t)num_layers * kPackedPerLayer) == cudaSuccess &&
+              cudaMalloc(&g->d_emb, sizeof(float) * (size_t)num_layers * num_types * kH) == cudaSuccess;
+    if (!ok) { ldpc_gnn_destroy(g); return fail(LDPC_ERR_CUDA, "gnn_create: device allocation failed: %s", cudaGetErrorString(cudaGetLastError())); }
+    *out = g;
+    return LDPC_OK;
 }
+
+int ldpc_gnn_destroy(ldpc_gnn_t* g) {
+    if (!g) return LDPC_OK;
+    {
+        DeviceGuard dg(g->device);
+        cudaFree(g->d_edge_var); cudaFree(g->d_edge_chk); cudaFree(g->d_edge_type); cudaFree(g->d_var_ptr);
+        cudaFree(g->d_var_edge); cudaFree(g->d_chk_ptr); cudaFree(g->d_packed); cudaFree(g->d_emb);
+    }
+    delete g;
+    return LDPC_OK;
+}
+
+size_t ldpc_gnn_param_count(const ldpc_gnn_t* g) { return g ? g->params : 0; }
+
+size_t ldpc_gnn_workspace_bytes(const ldpc_gnn_t* g, int64_t B, int training) {
+    if (!g || B <= 0) return 0;
+    if (training) return 0;   // training workspace: see ldpc_gnn_backward
+    const int64_t chunk = B < 2048 ? B : 2048;
+    return gnn_bytes_per_codeword(g) * (size_t)chunk;
+}
+
+int ldpc_gnn_forward(const ldpc_gnn_t* g, const float* params, const float* llr, int64_t B, float* soft_out,
+                     float* prob_out, void* workspace, size_t ws_bytes, int training, void* stream) {
+    if (!g || !params) return fail(LDPC_ERR_INVALID, "gnn_forward: null handle or parameters");
+    if (B < 0) return fail(LDPC_ERR_INVALID, "gnn_forward: negative batch");
+    if (B == 0) return LDPC_OK;
+    if (!llr) return fail(LDPC_ERR_INVALID, "gnn_forward: null llr");
+    if (training) return fail(LDPC_ERR_UNSUPPORTED, "gnn_forward: training=1 (saved activations) is not built yet");
+    const size_t per_cw = gnn_bytes_per_codeword(g);
+    if (!workspace || ws_bytes < per_cw)
+        return fail(LDPC_ERR_INVALID, "gnn_forward: workspace of %zu bytes is smaller than one codeword (%zu)", ws_bytes, per_cw);
+    DeviceGuard dg(g->device);
+    if (!dg.ok) return fail(LDPC_ERR_CUDA, "gnn_forward: cannot select device %d", g->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    GnnLayout lay{g->types};
+    gnn_pack_kernel<<<dim3(32, g->layers), 256, 0, st>>>(params, lay, g->layers, g->d_packed, g->d_emb);
+    LDPC_CHECK_LAUNCH("gnn_pack_kernel");
+    const size_t edge_smem = sizeof(float) * kEdgeSmemFloats;
+    LDPC_CUDA(cudaFuncSetAttribute(gnn_edge_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge_smem));
+    LDPC_CUDA(cudaFuncSetAttribute(gnn_edge_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge_smem));
+    const int64_t chunk_max = (int64_t)(ws_bytes / per_cw);
+    const int E = g->E, N = g->N, M = g->M;
+    for (int64_t b0 = 0; b0 < B; b0 += chunk_max) {
+        const int64_t bc = (B - b0) < chunk_max ? (B - b0) : chunk_max;
+        float* xa = (float*)workspace;
+        float* xb = xa + (size_t)bc * E * kH;
+        float* pv = xb + (size_t)bc * E * kH;
+        float* pc = pv + (size_t)bc * N * kH;
+        const float* llr_c = llr + (size_t)b0 * N;
+        gnn_embed_kernel<<<gnn_grid(bc * E * (kH / 4), 256), 256, 0, st>>>(params, lay, llr_c, g->d_edge_var, bc, E, N, xa);
+        LDPC_CHECK_LAUNCH("gnn_embed_kernel");
+        for (int l = 0; l < g->layers; ++l) {
+            const float* pk = g->d_packed + (size_t)l * kPackedPerLayer;
+            const float* em = g->d_emb + (size_t)l * g->types * kH;
+            gnn_node_kernel<<<gnn_grid(bc * N, kGnnThreads), kGnnThreads, 0, st>>>(
+                xa, em, pk, 0, g->d_var_ptr, g->d_var_edge, g->d_edge_type, bc, E, N, pv);
+            LDPC_CHECK_LAUNCH("gnn_node_kernel(var)");
+            gnn_node_kernel<<<gnn_grid(bc * M, kGnnThreads), kGnnThreads, 0, st>>>(
+                xa, em, pk, 1, g->d_chk_ptr, nullptr, g->d_edge_type, bc, E, M, pc);
+            LDPC_CHECK_LAUNCH("gnn_node_kernel(chk)");
+            if (l == 0)
+                gnn_edge_kernel<false><<<gnn_grid(bc * E, kGnnThreads), kGnnThreads, edge_smem, st>>>(
+                    xa, em, pk, g->d_edge_var, g->d_edge_chk, g->d_edge_type, pv, pc, bc, E, N, M, xb);
+            else
+                gnn_edge_kernel<true><<<gnn_grid(bc * E, kGnnThreads), kGnnThreads, edge_smem, st>>>(
+                    xa, em, pk, g->d_edge_var, g->d_edge_chk, g->d_edge_type, pv, pc, bc, E, N, M, xb);
+            LDPC_CHECK_LAUNCH("gnn_edge_kernel");
+            float* tmp = xa; xa = xb; xb = tmp;
+        }
+        gnn_readout_kernel<<<gnn_grid(bc * N, 256), 256, 0, st>>>(
+            xa, params, lay, g->layers - 1, llr_c, g->d_var_ptr, g->d_var_edge, bc, E, N,
+            soft_out ? soft_out + (size_t)b0 * N : nullptr, prob_out ? prob_out + (size_t)b0 * N : nullptr);
+        LDPC_CHECK_LAUNCH("gnn_readout_kernel");
+    }
+    return LDPC_OK;
+}
+
 int ldpc_gnn_backward(const ldpc_gnn_t*, const float*, const float*, const float*, int64_t, float*, float*, void*, size_t, void*) {
-    return fail(LDPC_ERR_UNSUPPORTED, "gnn: not built yet");
+    return fail(LDPC_ERR_UNSUPPORTED, "gnn_backward: not built yet (round 2)");
 }
 
 }  // extern "C"
