@@ -100,6 +100,11 @@ int ldpc_bp_decode(const ldpc_code_t* code, const float* llr, int64_t B, int ite
                    float* soft_out, void* hard_out, int hard_dtype, uint8_t* syndrome_ok, int32_t* iters_out,
                    uint64_t* valid_mask, int mask_words, void* stream);
 
+/* ldpc_syndrome_check replaces _check_valid_codeword (traditional_decoders.py:111-134,262-284):
+ * syndrome_ok[b] = 1 iff every parity check of H is satisfied by hard[b] (per hard_dtype).    */
+int ldpc_syndrome_check(const ldpc_code_t* code, const void* hard, int hard_dtype, int64_t B, uint8_t* syndrome_ok,
+                        void* stream);
+
 /* Host-buffer variant (the `e2e` path of bench.py): llr_host / hard_host are HOST pointers
  * (pinned memory recommended).  The call chunks the batch, overlaps H2D, decode and D2H on
  * internal streams and returns when hard_host (and soft_host if given) are complete.     */

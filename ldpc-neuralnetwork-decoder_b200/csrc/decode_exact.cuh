@@ -266,6 +266,64 @@ __global__ void __launch_bounds__(256) decode_exact_kernel(const DecodeParams p)
     if (p.counters) flush_counters(p.counters, acc_bits, acc_fe, acc_frames, acc_und);
 }
 
+// Syndrome of given hard decisions: one warp per G codewords, bits staged as +-1 in shared
+// memory (same layout / rotation-by-address as the decoder), parity per check row.
+template <bool kConst>
+__global__ void __launch_bounds__(256) syndrome_kernel(const uint32_t* gtab, int slot, const void* __restrict__ hard,
+                                                        int hard_dtype, long long B, long long ngroups,
+                                                        uint8_t* __restrict__ ok_out) {
+    extern __shared__ float smem[];
+    const Tab<kConst> tab{gtab, slot};
+    const int rows = tab[0], cols = tab[1], Z = tab[2], G = tab[4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+    float* T = smem + (size_t)warp * cols * 32;
+    const bool active = lane < G * Z;
+    const int cwi = active ? lane / Z : 0, r = active ? lane - cwi * Z : 0, base = cwi * Z, N = cols * Z;
+    const unsigned gmask = (Z == 32) ? 0xffffffffu : (((1u << Z) - 1u) << base);
+    for (long long grp = (long long)blockIdx.x * W + warp; grp < ngroups; grp += (long long)gridDim.x * W) {
+        const long long cw = grp * G + cwi;
+        const bool live = active && cw < B;
+        for (int j = 0; j < cols; ++j) {
+            const long long n = cw * N + j * Z + r;
+            bool bit = false;
+            if (live) {
+                if (hard_dtype == LDPC_HARD_F32) bit = ((const float*)hard)[n] != 0.0f;
+                else if (hard_dtype == LDPC_HARD_U8) bit = ((const uint8_t*)hard)[n] != 0;
+                else {
+                    const int q = j * Z + r;
+                    bit = (((const unsigned*)hard)[cw * ((N + 31) >> 5) + (q >> 5)] >> (q & 31)) & 1u;
+                }
+            }
+            T[j * 32 + lane] = bit ? -1.0f : 1.0f;
+        }
+        __syncwarp();
+        const bool bad = syndrome_bad(tab, T, rows, Z, base, r);
+        const unsigned m = __ballot_sync(0xffffffffu, bad && active);
+        if (live && r == 0) ok_out[cw] = (m & gmask) == 0 ? 1 : 0;
+        __syncwarp();
+    }
+}
+
+inline int launch_syndrome(const ldpc_code* c, const void* hard, int hard_dtype, long long B, uint8_t* ok, cudaStream_t st) {
+    const size_t per_warp = (size_t)c->cols * 32 * sizeof(float);
+    int W = (int)(kMaxSmemPerBlock / per_warp);
+    if (W < 1) return fail(LDPC_ERR_UNSUPPORTED, "syndrome_check: code too large for shared memory");
+    if (W > 8) W = 8;
+    const long long ngroups = (B + c->G - 1) / c->G;
+    long long blocks = (ngroups + W - 1) / W;
+    if (blocks > (long long)kNumSMs * 4) blocks = (long long)kNumSMs * 4;
+    const size_t smem = per_warp * W;
+    if (c->slot >= 0) {
+        LDPC_CUDA(cudaFuncSetAttribute(syndrome_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        syndrome_kernel<true><<<(int)blocks, W * 32, smem, st>>>(c->d_tab, c->slot, hard, hard_dtype, B, ngroups, ok);
+    } else {
+        LDPC_CUDA(cudaFuncSetAttribute(syndrome_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        syndrome_kernel<false><<<(int)blocks, W * 32, smem, st>>>(c->d_tab, 0, hard, hard_dtype, B, ngroups, ok);
+    }
+    LDPC_CHECK_LAUNCH("syndrome_kernel");
+    return LDPC_OK;
+}
+
 // ---- host launcher ----------------------------------------------------------------------
 template <int kAlgo, int kMaxDc, int kMaxDv, bool kConst>
 inline int launch_exact_inst(const DecodeParams& p, int W, int grid, size_t smem, cudaStream_t st) {

@@ -147,6 +147,18 @@ int ldpc_bp_decode(const ldpc_code_t* code, const float* llr, int64_t B, int ite
                          syndrome_ok, iters_out, valid_mask, mask_words, stream);
 }
 
+int ldpc_syndrome_check(const ldpc_code_t* code, const void* hard, int hard_dtype, int64_t B, uint8_t* syndrome_ok,
+                        void* stream) {
+    if (!code) return fail(LDPC_ERR_INVALID, "syndrome_check: null code handle");
+    if (B < 0) return fail(LDPC_ERR_INVALID, "syndrome_check: negative batch");
+    if (B == 0) return LDPC_OK;
+    if (!hard || !syndrome_ok) return fail(LDPC_ERR_INVALID, "syndrome_check: null buffer");
+    if (hard_dtype < LDPC_HARD_F32 || hard_dtype > LDPC_HARD_PACKED) return fail(LDPC_ERR_INVALID, "syndrome_check: unknown hard_dtype");
+    DeviceGuard g(code->device);
+    if (!g.ok) return fail(LDPC_ERR_CUDA, "syndrome_check: cannot select device %d", code->device);
+    return launch_syndrome(code, hard, hard_dtype, B, syndrome_ok, (cudaStream_t)stream);
+}
+
 int ldpc_decode_host(const ldpc_code_t* code, int algo, const float* llr_host, int64_t B, int iters, float alpha,
                      int path, float* soft_host, void* hard_host, int hard_dtype, int64_t chunk) {
     if (!code) return fail(LDPC_ERR_INVALID, "decode_host: null code handle");

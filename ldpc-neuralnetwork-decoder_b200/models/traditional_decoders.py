@@ -133,14 +133,19 @@ class _FloodingDecoder:
     def _check_valid_codeword(self, decoded_bits):
         """Bool (B,): all parity checks satisfied (reference :111-134 / :262-284)."""
         bits = decoded_bits.detach()
-        llr = (1.0 - 2.0 * bits.to(torch.float32))          # bit 1 -> negative LLR
-        llr_d, dev = self._prepare(llr)
-        chk, var = self.code.edges()
-        v = torch.from_numpy(var).to(dev)
-        c = torch.from_numpy(chk).to(dev)
-        par = torch.zeros((llr_d.shape[0], self.code.M), dtype=torch.int32, device=dev)
-        par.index_add_(1, c, (llr_d[:, v] < 0).to(torch.int32))
-        return ((par & 1) == 0).all(dim=1).to(decoded_bits.device)
+        if bits.dim() != 2 or bits.shape[1] != self.code.N:
+            raise ValueError(f"decoded_bits must have shape (batch, {self.code.N})")
+        dev = bits.device if bits.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        if bits.dtype == torch.uint8:
+            hard, dtype = bits.to(dev).contiguous(), _native.HARD_U8
+        else:
+            hard, dtype = bits.to(device=dev, dtype=torch.float32).contiguous(), _native.HARD_F32
+        ok = torch.empty(bits.shape[0], dtype=torch.uint8, device=dev)
+        if bits.shape[0]:
+            with torch.cuda.device(dev):
+                _native.check(_native.lib().ldpc_syndrome_check(self.code.handle(dev), _native.ptr(hard), dtype,
+                                                                bits.shape[0], _native.ptr(ok), _native.stream_ptr(dev)))
+        return ok.bool().to(decoded_bits.device)
 
 
 class MinSumScaledDecoder(_FloodingDecoder):

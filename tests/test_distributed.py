@@ -1,0 +1,73 @@
+"""Multi-GPU host logic on CPU: frame-range sharding + counter all-reduce with 2 gloo ranks.
+Each rank decodes ITS range of global frame indices (the oracle stands in for the GPU kernel,
+same Philox keying) and the reduced counters must equal a single-rank run over all frames."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+import ldpc_b200
+from ldpc_b200.sim import shard_range, reduce_counters, wilson_interval
+from ldpc_b200.utils import QCCode
+
+FRAMES, SNR_DB, ITERS, SEED = 301, -1.0, 5, 77
+
+
+def local_counters(first, count):
+    from oracle import oracle
+    code = QCCode.nr_2_0(4)
+    llr = oracle.awgn_llr(None, count, code.N, SNR_DB, SEED, first_frame=first)
+    o = oracle.decode(code.shifts, 4, llr, ITERS, "minsum", 0.75, order="fast", want_mask=True)
+    nerr = o["hard"].sum(axis=1)
+    valid = ((o["valid_mask"][:, 0] >> np.uint64(ITERS - 1)) & np.uint64(1)).astype(bool)
+    return torch.tensor([int(nerr.sum()), int((nerr > 0).sum()), count, int(((nerr > 0) & valid).sum())], dtype=torch.int64)
+
+
+def worker(rank, world, port, q):
+    import sys
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    first, count = shard_range(FRAMES, rank, world)
+    c = local_counters(first, count)
+    reduce_counters(c)
+    if rank == 0:
+        q.put(c.tolist())
+    dist.destroy_process_group()
+
+
+def test_shard_range_partitions_exactly():
+    for total in (0, 1, 7, 301, 10 ** 9):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and sum(c for _, c in spans) == total
+            for (f0, c0), (f1, _) in zip(spans, spans[1:]):
+                assert f0 + c0 == f1
+            assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
+    with pytest.raises(ValueError):
+        shard_range(10, 2, 2)
+    lo, hi = wilson_interval(5, 1000)
+    assert lo < 0.005 < hi and wilson_interval(0, 0) == (0.0, 1.0)
+
+
+def test_two_rank_gloo_counters_equal_single_rank():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = local_counters(0, FRAMES).tolist()
+    assert got == want and got[2] == FRAMES

@@ -133,3 +133,20 @@ def test_layers_at_bg2_z32_against_oracle():
     np.testing.assert_allclose(v2c.cpu().numpy(), oracle.variable_layer(llr, ref_c2v, vidx.numpy()), rtol=1e-5, atol=1e-4)
     with pytest.raises(RuntimeError):
         CheckLayer()(torch.from_numpy(x), cidx)
+
+
+def test_sweep_driver_is_independent_of_sharding():
+    """sim.simulate_fer: counters of rank 0 + rank 1 (emulated, world=2) == world=1; frames are
+    keyed by the global frame index, so FER does not depend on the GPU count."""
+    from ldpc_b200.sim import simulate_fer
+    code = QCCode.nr_2_0(32)
+    snrs = [-3.0, -2.0]
+    one = simulate_fer(code, snrs, 6001, iters=6, seed=5, device=DEV, max_frames_per_call=2500)
+    parts = [simulate_fer(code, snrs, 6001, iters=6, seed=5, device=DEV, rank=r, world=2) for r in range(2)]
+    for k, point in enumerate(one):
+        assert point["frames"] == 6001
+        for key in ("bit_errors", "frame_errors", "frames", "undetected"):
+            assert point[key] == parts[0][k][key] + parts[1][k][key]
+        lo, hi = point["fer_ci"]
+        assert lo <= point["fer"] <= hi
+    assert one[0]["fer"] > one[1]["fer"] > 0

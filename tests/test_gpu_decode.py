@@ -245,3 +245,20 @@ def test_linearity_at_full_batch_size():
         flipped = ch_llr[:4096] * (1.0 - 2.0 * c)
         _, h2, s2, _, _ = dec._launch(flipped.contiguous(), dev(), iters, hard_dtype=_native.HARD_U8, syndrome=True)
         assert bool((h2.float() == c).all()) and bool(s2.all())
+
+
+def test_syndrome_check_entry_point():
+    """_check_valid_codeword (reference :262-284) through ldpc_syndrome_check, all bit formats."""
+    code = QCCode.nr_2_0(32)
+    dec = MinSumScaledDecoder(code, 10, 0.75, early_stopping=False)
+    llr = oracle.awgn_llr(None, 50, code.N, -2.5, seed=4)
+    o = oracle.decode(code.shifts, 32, llr, 10, "minsum", 0.75, order="fast", want_mask=True)
+    want = ((o["valid_mask"][:, 0] >> np.uint64(9)) & np.uint64(1)).astype(bool)
+    assert want.any() and not want.all()
+    bits = torch.from_numpy(o["hard"].astype(np.float32)).to(dev())
+    assert np.array_equal(dec._check_valid_codeword(bits).cpu().numpy(), want)
+    assert np.array_equal(dec._check_valid_codeword(bits.to(torch.uint8)).cpu().numpy(), want)
+    assert np.array_equal(dec._check_valid_codeword(bits.cpu()).numpy(), want)
+    toy = MinSumScaledDecoder(torch.tensor([[1, 1, 0, 0], [0, 1, 1, 1], [1, 0, 0, 1]], dtype=torch.float32), 2, early_stopping=False)
+    cw = torch.tensor([[0, 0, 0, 0], [1, 1, 1, 0], [1, 1, 0, 1], [1, 0, 0, 0]], dtype=torch.float32, device=dev())
+    assert toy._check_valid_codeword(cw).tolist() == [True, False, True, False]
