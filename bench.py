@@ -36,6 +36,9 @@ SM_COUNT = 148
 # cells x (1 load + 1 store of the resident message) + 145 shifted core cells x 2 rotations +
 # 14 channel-LLR reloads = 622.  Degree-1 columns and unshifted cells need no rotation.
 SMEM_WAVEFRONTS_PER_CW_ITER = 159 * 2 + 145 * 2 + 14
+# DRAM bytes per codeword of the decode kernel measured by `ncu --set full` (profiles/r1_ncu_minsum_fast.md,
+# capture r1c: dram__bytes_read.sum + dram__bytes_write.sum = 1.8025 GB for 262144 codewords)
+NCU_DRAM_BYTES_PER_CW = 6876.0
 
 
 def measured_peaks():
@@ -128,6 +131,10 @@ def run_reference(args):
            "config": workload_config(args, None), "cpu_baseline": base,
            "e2e": {"value": v, "unit": "Gbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
+
+
+def algo_bytes_fn(B):
+    return B * (N_BITS * 4 + ((N_BITS + 31) // 32) * 4)
 
 
 def workload_config(args, B):
@@ -277,7 +284,9 @@ def main():
                     "d2h_bytes_per_step": Be * NW * 4, "codewords_per_step": Be, "steps": args.e2e_steps,
                     "api": "ldpc_decode_host (pinned host LLRs -> packed hard bits)"},
             "roofline": {"bound": "smem_pipe", "achieved": achieved, "peak": peak, "unit": "Gwavefront/s",
-                         "frac": achieved / peak, "traffic": None,
+                         "frac": achieved / peak,
+                         "traffic": (NCU_DRAM_BYTES_PER_CW * B if args.workload == "minsum" else None),
+                         "traffic_unit": "bytes of DRAM per launch (ncu r1c), algorithmic = %d" % algo_bytes_fn(B),
                          "model": f"{SMEM_WAVEFRONTS_PER_CW_ITER} shared-memory/shuffle wavefronts per codeword-iteration "
                                   f"(algorithmic, DESIGN.md), 148 SMs x 1 wavefront/clk at {sm_max:.0f} MHz ({peak_src} max clock)",
                          "frac_at_measured_clock": (achieved / (peak * clocks["sm_mhz"] / sm_max)) if clocks and clocks.get("sm_mhz") else None,
