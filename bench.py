@@ -92,16 +92,16 @@ def cpu_baseline(workload, seconds=12.0):
     import ldpc_b200
     from ldpc_b200.utils import QCCode
     code = QCCode.nr_2_0(Z)
-    threads = oracle.num_threads()
+    threads = os.cpu_count() or oracle.num_threads()     # torchrun exports OMP_NUM_THREADS=1: ask for all cores explicitly
     probe = 64 * threads
     llr = oracle.awgn_llr(None, probe, code.N, SNR_DB, seed=1)
     t0 = time.perf_counter()
-    oracle.decode(code.shifts, Z, llr, ITERS, workload, ALPHA)
+    oracle.decode(code.shifts, Z, llr, ITERS, workload, ALPHA, threads=threads)
     rate = probe / (time.perf_counter() - t0)
     sample = int(max(probe, min(rate * seconds, 1 << 20)))
     llr = oracle.awgn_llr(None, sample, code.N, SNR_DB, seed=2)
     t0 = time.perf_counter()
-    oracle.decode(code.shifts, Z, llr, ITERS, workload, ALPHA)
+    oracle.decode(code.shifts, Z, llr, ITERS, workload, ALPHA, threads=threads)
     dt = time.perf_counter() - t0
     return {"value": sample * K_INFO / dt / 1e9, "unit": "Gbit/s", "cores": threads, "kind": "port",
             "sample": f"{sample} codewords of the same workload (BG2 Z=32, {ITERS} it, snr_db {SNR_DB}), "
