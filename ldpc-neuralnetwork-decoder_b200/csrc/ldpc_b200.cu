@@ -8,6 +8,7 @@
 #include "channel_kernels.cuh"
 #include "layers.cuh"
 #include "gnn.cuh"
+#include "gnn_bwd.cuh"
 
 #include <cstring>
 #include <new>
@@ -445,9 +446,33 @@ int ldpc_gnn_destroy(ldpc_gnn_t* g) {
 
 size_t ldpc_gnn_param_count(const ldpc_gnn_t* g) { return g ? g->params : 0; }
 
+// Training workspace layout (floats), B codewords, L layers:
+//   X[L+1][B][E][h]  PV[L][B][N][h]  PC[L][B][M][h]  SOFT[B][N]  DSOFT[B][N]
+//   G[B][E][h] DC[B][E][h] HR[B][E][2h] DH[B][E][2h]
+//   DPV,MV,DMV [B][N][h]   DPC,MC,DMC [B][M][h]   PG[L][kPackedPerLayer + types*h]
+struct GnnTrainWs {
+    size_t X, PV, PC, SOFT, DSOFT, G, DC, HR, DH, DPV, MV, DMV, DPC, MC, DMC, PG, total;
+    size_t xs, pvs, pcs, pg_layer;
+};
+static GnnTrainWs gnn_train_layout(const ldpc_gnn_t* g, int64_t B) {
+    GnnTrainWs w{};
+    const size_t L = g->layers, E = g->E, N = g->N, M = g->M, b = (size_t)B;
+    w.xs = b * E * kH; w.pvs = b * N * kH; w.pcs = b * M * kH; w.pg_layer = (size_t)kPackedPerLayer + (size_t)g->types * kH;
+    size_t o = 0;
+    auto take = [&](size_t n) { size_t r = o; o += (n + 3) / 4 * 4; return r; };
+    w.X = take((L + 1) * w.xs); w.PV = take(L * w.pvs); w.PC = take(L * w.pcs);
+    w.SOFT = take(b * N); w.DSOFT = take(b * N);
+    w.G = take(w.xs); w.DC = take(w.xs); w.HR = take(2 * w.xs); w.DH = take(2 * w.xs);
+    w.DPV = take(w.pvs); w.MV = take(w.pvs); w.DMV = take(w.pvs);
+    w.DPC = take(w.pcs); w.MC = take(w.pcs); w.DMC = take(w.pcs);
+    w.PG = take(L * w.pg_layer);
+    w.total = o;
+    return w;
+}
+
 size_t ldpc_gnn_workspace_bytes(const ldpc_gnn_t* g, int64_t B, int training) {
     if (!g || B <= 0) return 0;
-    if (training) return 0;   // training workspace: see ldpc_gnn_backward
+    if (training) return gnn_train_layout(g, B).total * sizeof(float);
     const int64_t chunk = B < 2048 ? B : 2048;
     return gnn_bytes_per_codeword(g) * (size_t)chunk;
 }
@@ -458,10 +483,10 @@ int ldpc_gnn_forward(const ldpc_gnn_t* g, const float* params, const float* llr,
     if (B < 0) return fail(LDPC_ERR_INVALID, "gnn_forward: negative batch");
     if (B == 0) return LDPC_OK;
     if (!llr) return fail(LDPC_ERR_INVALID, "gnn_forward: null llr");
-    if (training) return fail(LDPC_ERR_UNSUPPORTED, "gnn_forward: training=1 (saved activations) is not built yet");
     const size_t per_cw = gnn_bytes_per_codeword(g);
-    if (!workspace || ws_bytes < per_cw)
-        return fail(LDPC_ERR_INVALID, "gnn_forward: workspace of %zu bytes is smaller than one codeword (%zu)", ws_bytes, per_cw);
+    const size_t need = training ? gnn_train_layout(g, B).total * sizeof(float) : per_cw;
+    if (!workspace || ws_bytes < need)
+        return fail(LDPC_ERR_INVALID, "gnn_forward: workspace of %zu bytes, need at least %zu", ws_bytes, need);
     DeviceGuard dg(g->device);
     if (!dg.ok) return fail(LDPC_ERR_CUDA, "gnn_forward: cannot select device %d", g->device);
     cudaStream_t st = (cudaStream_t)stream;
@@ -471,14 +496,16 @@ int ldpc_gnn_forward(const ldpc_gnn_t* g, const float* params, const float* llr,
     const size_t edge_smem = sizeof(float) * kEdgeSmemFloats;
     LDPC_CUDA(cudaFuncSetAttribute(gnn_edge_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge_smem));
     LDPC_CUDA(cudaFuncSetAttribute(gnn_edge_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge_smem));
-    const int64_t chunk_max = (int64_t)(ws_bytes / per_cw);
     const int E = g->E, N = g->N, M = g->M;
+    const GnnTrainWs tw = training ? gnn_train_layout(g, B) : GnnTrainWs{};
+    const int64_t chunk_max = training ? B : (int64_t)(ws_bytes / per_cw);
     for (int64_t b0 = 0; b0 < B; b0 += chunk_max) {
         const int64_t bc = (B - b0) < chunk_max ? (B - b0) : chunk_max;
-        float* xa = (float*)workspace;
-        float* xb = xa + (size_t)bc * E * kH;
-        float* pv = xb + (size_t)bc * E * kH;
-        float* pc = pv + (size_t)bc * N * kH;
+        float* base = (float*)workspace;
+        float* xa = training ? base + tw.X : base;
+        float* xb = training ? xa + tw.xs : xa + (size_t)bc * E * kH;
+        float* pv = training ? base + tw.PV : xb + (size_t)bc * E * kH;
+        float* pc = training ? base + tw.PC : pv + (size_t)bc * N * kH;
         const float* llr_c = llr + (size_t)b0 * N;
         gnn_embed_kernel<<<gnn_grid(bc * E * (kH / 4), 256), 256, 0, st>>>(params, lay, llr_c, g->d_edge_var, bc, E, N, xa);
         LDPC_CHECK_LAUNCH("gnn_embed_kernel");
@@ -498,18 +525,95 @@ int ldpc_gnn_forward(const ldpc_gnn_t* g, const float* params, const float* llr,
                 gnn_edge_kernel<true><<<gnn_grid(bc * E, kGnnThreads), kGnnThreads, edge_smem, st>>>(
                     xa, em, pk, g->d_edge_var, g->d_edge_chk, g->d_edge_type, pv, pc, bc, E, N, M, xb);
             LDPC_CHECK_LAUNCH("gnn_edge_kernel");
-            float* tmp = xa; xa = xb; xb = tmp;
+            if (training) { xa = xb; xb = xa + tw.xs; pv += tw.pvs; pc += tw.pcs; }
+            else { float* tmp = xa; xa = xb; xb = tmp; }
         }
+        float* soft_dst = training ? base + tw.SOFT : (soft_out ? soft_out + (size_t)b0 * N : nullptr);
         gnn_readout_kernel<<<gnn_grid(bc * N, 256), 256, 0, st>>>(
-            xa, params, lay, g->layers - 1, llr_c, g->d_var_ptr, g->d_var_edge, bc, E, N,
-            soft_out ? soft_out + (size_t)b0 * N : nullptr, prob_out ? prob_out + (size_t)b0 * N : nullptr);
+            xa, params, lay, g->layers - 1, llr_c, g->d_var_ptr, g->d_var_edge, bc, E, N, soft_dst,
+            prob_out ? prob_out + (size_t)b0 * N : nullptr);
         LDPC_CHECK_LAUNCH("gnn_readout_kernel");
+        if (training && soft_out)
+            LDPC_CUDA(cudaMemcpyAsync(soft_out, soft_dst, sizeof(float) * (size_t)B * N, cudaMemcpyDeviceToDevice, st));
     }
     return LDPC_OK;
 }
 
-int ldpc_gnn_backward(const ldpc_gnn_t*, const float*, const float*, const float*, int64_t, float*, float*, void*, size_t, void*) {
-    return fail(LDPC_ERR_UNSUPPORTED, "gnn_backward: not built yet (round 2)");
+int ldpc_gnn_backward(const ldpc_gnn_t* g, const float* params, const float* llr, const float* gt, int64_t B,
+                      float* loss_out, float* grad_params, void* workspace, size_t ws_bytes, void* stream) {
+    if (!g || !params || !llr || !gt || !loss_out || !grad_params)
+        return fail(LDPC_ERR_INVALID, "gnn_backward: null argument");
+    if (B <= 0) return fail(LDPC_ERR_INVALID, "gnn_backward: batch must be positive");
+    const GnnTrainWs tw = gnn_train_layout(g, B);
+    if (!workspace || ws_bytes < tw.total * sizeof(float))
+        return fail(LDPC_ERR_INVALID, "gnn_backward: workspace of %zu bytes, need %zu (from a training=1 forward)", ws_bytes,
+                    tw.total * sizeof(float));
+    DeviceGuard dg(g->device);
+    if (!dg.ok) return fail(LDPC_ERR_CUDA, "gnn_backward: cannot select device %d", g->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    GnnLayout lay{g->types};
+    const int E = g->E, N = g->N, M = g->M, L = g->layers;
+    float* base = (float*)workspace;
+    float *G = base + tw.G, *DC = base + tw.DC, *HR = base + tw.HR, *DH = base + tw.DH;
+    float *DPV = base + tw.DPV, *MV = base + tw.MV, *DMV = base + tw.DMV, *DPC = base + tw.DPC, *MC = base + tw.MC, *DMC = base + tw.DMC;
+    float* PG = base + tw.PG;
+    LDPC_CUDA(cudaMemsetAsync(PG, 0, sizeof(float) * (size_t)L * tw.pg_layer, st));
+    LDPC_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), st));
+    // loss and d(loss)/d(soft)
+    gnn_loss_kernel<<<gnn_grid(B * N, 256), 256, 0, st>>>(base + tw.SOFT, gt, (long long)B * N, base + tw.DSOFT, loss_out);
+    LDPC_CHECK_LAUNCH("gnn_loss_kernel");
+    const float* xL = base + tw.X + (size_t)L * tw.xs;
+    gnn_readout_bwd_kernel<<<gnn_grid(B * E, 256), 256, 0, st>>>(xL, params, lay, L - 1, base + tw.DSOFT, g->d_edge_var, B, E, N, G,
+                                                                grad_params);
+    LDPC_CHECK_LAUNCH("gnn_readout_bwd_kernel");
+    const size_t ebwd_smem = sizeof(float) * (2 * kH * kH + kH * 2 * kH + kH * kGnnThreads);
+    LDPC_CUDA(cudaFuncSetAttribute(gnn_edge_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ebwd_smem));
+    const size_t fin_smem = sizeof(float) * (size_t)g->types * kH;
+    const int outer_grid = kNumSMs * 2;
+    for (int l = L - 1; l >= 0; --l) {
+        const float* x = base + tw.X + (size_t)l * tw.xs;
+        const float* pv = base + tw.PV + (size_t)l * tw.pvs;
+        const float* pc = base + tw.PC + (size_t)l * tw.pcs;
+        const float* pk = g->d_packed + (size_t)l * kPackedPerLayer;
+        const float* em = g->d_emb + (size_t)l * g->types * kH;
+        float* pg = PG + (size_t)l * tw.pg_layer;
+        LDPC_CUDA(cudaMemsetAsync(DPV, 0, sizeof(float) * tw.pvs, st));
+        LDPC_CUDA(cudaMemsetAsync(DPC, 0, sizeof(float) * tw.pcs, st));
+        gnn_edge_bwd_kernel<<<gnn_grid(B * E, kGnnThreads), kGnnThreads, ebwd_smem, st>>>(
+            x, em, pk, g->d_edge_var, g->d_edge_chk, g->d_edge_type, pv, pc, G, B, E, N, M, HR, DH, DPV, DPC);
+        LDPC_CHECK_LAUNCH("gnn_edge_bwd_kernel");
+        gnn_dcomb_kernel<<<gnn_grid(B * E, kGnnThreads), kGnnThreads, 0, st>>>(DH, pk, (long long)B * E, DC);
+        LDPC_CHECK_LAUNCH("gnn_dcomb_kernel");
+        // dW2[n][k] += G^T . relu(h);   d(b2) += colsum(G)
+        gnn_outer_kernel<kH, 2 * kH, 0><<<outer_grid, 256, 0, st>>>(G, HR, (long long)B * E, nullptr, nullptr, E, pg + kPkW2, pg + kPkB2);
+        LDPC_CHECK_LAUNCH("gnn_outer_kernel(dW2)");
+        // dW1A[n][k] += dH^T . comb;   d(b1v|b1c) += colsum(dH)
+        gnn_outer_kernel<2 * kH, kH, 2><<<outer_grid, 256, 0, st>>>(DH, x, (long long)B * E, em, g->d_edge_type, E, pg + kPkW1A, pg + kPkB1V);
+        LDPC_CHECK_LAUNCH("gnn_outer_kernel(dW1A)");
+        gnn_node_bwd_kernel<<<gnn_grid(B * N, kGnnThreads), kGnnThreads, 0, st>>>(
+            x, em, pk, 0, g->d_var_ptr, g->d_var_edge, g->d_edge_type, DPV, B, E, N, MV, DMV);
+        LDPC_CHECK_LAUNCH("gnn_node_bwd_kernel(var)");
+        gnn_node_bwd_kernel<<<gnn_grid(B * M, kGnnThreads), kGnnThreads, 0, st>>>(
+            x, em, pk, 1, g->d_chk_ptr, nullptr, g->d_edge_type, DPC, B, E, M, MC, DMC);
+        LDPC_CHECK_LAUNCH("gnn_node_bwd_kernel(chk)");
+        gnn_outer_kernel<kH, kH, 0><<<outer_grid, 256, 0, st>>>(DPV, MV, (long long)B * N, nullptr, nullptr, E, pg + kPkW1BV, nullptr);
+        LDPC_CHECK_LAUNCH("gnn_outer_kernel(dW1Bv)");
+        gnn_outer_kernel<kH, kH, 0><<<outer_grid, 256, 0, st>>>(DPC, MC, (long long)B * M, nullptr, nullptr, E, pg + kPkW1BC, nullptr);
+        LDPC_CHECK_LAUNCH("gnn_outer_kernel(dW1Bc)");
+        if (l > 0)
+            gnn_finish_bwd_kernel<true><<<gnn_grid(B * E * (kH / 4), 256), 256, fin_smem, st>>>(
+                DC, DMV, DMC, G, g->d_edge_var, g->d_edge_chk, g->d_edge_type, B, E, N, M, g->types, DC, pg + kPackedPerLayer);
+        else
+            gnn_finish_bwd_kernel<false><<<gnn_grid(B * E * (kH / 4), 256), 256, fin_smem, st>>>(
+                DC, DMV, DMC, G, g->d_edge_var, g->d_edge_chk, g->d_edge_type, B, E, N, M, g->types, DC, pg + kPackedPerLayer);
+        LDPC_CHECK_LAUNCH("gnn_finish_bwd_kernel");
+        float* tmp = G; G = DC; DC = tmp;      // dx of this layer is the output gradient of the layer below
+    }
+    gnn_embed_bwd_kernel<<<kNumSMs * 8, 256, 0, st>>>(G, llr, g->d_edge_var, B, E, N, lay, grad_params);
+    LDPC_CHECK_LAUNCH("gnn_embed_bwd_kernel");
+    gnn_unpack_grad_kernel<<<dim3(32, L), 256, 0, st>>>(PG, lay, (int)tw.pg_layer, grad_params);
+    LDPC_CHECK_LAUNCH("gnn_unpack_grad_kernel");
+    return LDPC_OK;
 }
 
 }  // extern "C"

@@ -121,6 +121,39 @@ class TannerToMessageGraph:
         return torch.tensor([rank[int(s)] if s >= 0 else 0 for s in sh], dtype=torch.long)
 
 
+class _GnnLossFn(torch.autograd.Function):
+    """loss = mean BCE(sigmoid(soft), gt) of the reference (:313-315), with the engine's backward:
+    forward runs ldpc_gnn_forward(training=1) + ldpc_gnn_backward and keeps d(loss)/d(params)."""
+
+    @staticmethod
+    def forward(ctx, flat, llr, gt, module):
+        dev = llr.device
+        h = module._handle(dev)
+        L = _native.lib()
+        B, N = llr.shape
+        params = flat.detach().to(device=dev, dtype=torch.float32).contiguous()
+        ws_bytes = L.ldpc_gnn_workspace_bytes(h, B, 1)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        prob = torch.empty((B, N), dtype=torch.float32, device=dev)
+        loss = torch.zeros((), dtype=torch.float32, device=dev)
+        grad = torch.zeros_like(params)
+        gt_f = gt.detach().to(device=dev, dtype=torch.float32).contiguous()
+        with torch.cuda.device(dev):
+            st = _native.stream_ptr(dev)
+            _native.check(L.ldpc_gnn_forward(h, _native.ptr(params), _native.ptr(llr), B, None, _native.ptr(prob),
+                                             _native.ptr(ws), ws_bytes, 1, st))
+            _native.check(L.ldpc_gnn_backward(h, _native.ptr(params), _native.ptr(llr), _native.ptr(gt_f), B,
+                                              _native.ptr(loss), _native.ptr(grad), _native.ptr(ws), ws_bytes, st))
+        ctx.save_for_backward(grad.to(flat.device))
+        ctx.mark_non_differentiable(prob)
+        return loss, prob
+
+    @staticmethod
+    def backward(ctx, g_loss, g_prob):
+        (grad,) = ctx.saved_tensors
+        return grad * g_loss.to(grad.device), None, None, None
+
+
 class MessageGNNDecoder(nn.Module):
     def __init__(self, num_messages, num_iterations=5, hidden_dim=64, num_message_types=1, code=None,
                  base_edge_types=None):
@@ -235,13 +268,21 @@ class MessageGNNDecoder(nn.Module):
         short = message_to_var_mapping is None and ground_truth is None
         if self._code is not None:
             self._check_mapping(message_to_var_mapping, message_types, None)
+        if ground_truth is not None and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            # training step: engine forward (activations kept) + engine backward; loss.backward() then
+            # delivers d(loss)/d(parameter) through the differentiable torch.cat below
+            if not input_llr.is_cuda:
+                raise RuntimeError("training needs CUDA tensors (no CPU fallback)")
+            llr = input_llr.detach().to(torch.float32).contiguous()
+            flat = torch.cat([p.reshape(-1) for p in self.parameters()])
+            loss, prob = _GnnLossFn.apply(flat, llr, ground_truth, self)
+            return prob, loss
         soft, prob = self._run(input_llr)
         soft, prob = soft.to(input_llr.device), prob.to(input_llr.device)
         if short:
             return soft, (prob > 0.5).float()
         if ground_truth is not None:
-            # mean BCE on the final output (reference :313-315); value only -- the engine's
-            # backward (ldpc_gnn_backward) is not built in this round
+            # mean BCE on the final output (reference :313-315)
             loss = F.binary_cross_entropy(prob, ground_truth.to(prob.device).float())
             return prob, loss
         return prob

@@ -42,6 +42,43 @@ def worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def grad_worker(rank, world, port, q):
+    import sys
+    sys.path.insert(0, ROOT)
+    import ldpc_b200  # noqa: F401
+    from ldpc_b200.training import allreduce_gradients
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    m = torch.nn.Sequential(torch.nn.Linear(3, 4), torch.nn.Linear(4, 1))
+    for i, p in enumerate(m.parameters()):
+        p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
+    list(m.parameters())[-1].grad = None if rank == 1 else torch.ones(1)     # a parameter without gradient on one rank
+    assert allreduce_gradients(m) == world
+    if rank == 0:
+        q.put([p.grad.reshape(-1).tolist() for p in m.parameters()])
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_two_gloo_ranks():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for i, g in enumerate(got[:-1]):
+        assert all(abs(x - 1.5 * (i + 1)) < 1e-6 for x in g)        # mean of rank 0 (x1) and rank 1 (x2)
+    assert abs(got[-1][0] - 0.5) < 1e-6
+
+
 def test_shard_range_partitions_exactly():
     for total in (0, 1, 7, 301, 10 ** 9):
         for world in (1, 2, 3, 8):

@@ -82,7 +82,7 @@ def test_forward_matches_reference_golden(name, Z):
     assert np.array_equal(hard.cpu().numpy().astype(np.uint8)[margin], unpack(g["hard"], code.N)[margin])
     assert torch.equal(hard, hard01)
     p2, loss = dec(llr, conv.message_var_index, types, None, None, ground_truth=torch.zeros_like(llr))
-    assert abs(float(loss) - float(g["loss"])) <= 1e-4 * max(1.0, abs(float(g["loss"])))
+    assert abs(float(loss.detach()) - float(g["loss"])) <= 1e-4 * max(1.0, abs(float(g["loss"])))
 
 
 @pytest.mark.gpu
@@ -111,3 +111,37 @@ def test_forward_vs_oracle_larger_batch_and_chunking():
     assert torch.equal(out, soft)
     assert _native.lib().ldpc_gnn_forward(h, _native.ptr(params), _native.ptr(llr_d), B, _native.ptr(out), None,
                                           _native.ptr(ws), 16, 0, None) == _native.ERR_INVALID
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,Z", [("gnn_z4_b4", 4), ("gnn_z32_b2", 32)])
+def test_training_step_gradients_match_reference_autograd(name, Z):
+    """loss.backward() through the engine == the reference module's autograd (golden `grad.*`),
+    including which parameters get no gradient at all (output_layer, inner output_projections)."""
+    g = load_golden(name)
+    code = QCCode.nr_2_0(Z)
+    dec, conv = create_message_gnn_decoder(code, 5, 64, base_graph=code.base_matrix(), Z=Z)
+    load_state(dec, g)
+    dec = dec.cuda()
+    llr = torch.from_numpy(g["llr"]).cuda()
+    types = conv.get_message_types(code.base_matrix(), Z)
+    probs, loss = dec(llr, conv.message_var_index, types, None, None, ground_truth=torch.zeros_like(llr))
+    assert abs(float(loss.detach()) - float(g["loss"])) <= 1e-5 * max(1.0, abs(float(g["loss"])))
+    assert np.max(np.abs(probs.detach().cpu().numpy() - g["probs"])) <= 2e-5
+    loss.backward()
+    worst = 0.0
+    for n, p in dec.named_parameters():
+        ref = g["grad." + n]
+        got = p.grad.cpu().numpy()
+        scale = max(np.abs(ref).max(), 1e-8)
+        err = np.abs(got - ref).max() / scale
+        worst = max(worst, err)
+        # fp32 accumulation over B*E rows in a different order than torch: 2e-4 of the tensor's scale
+        assert err <= 2e-4, (n, err)
+        if not bool(g["hasgrad." + n]):
+            assert not got.any(), n
+    # an SGD step with the reference's hyper-parameters runs (trainer.py:70)
+    opt = torch.optim.SGD(dec.parameters(), lr=1e-3, momentum=0.9, weight_decay=1e-4)
+    opt.step()
+    _, loss2 = dec(llr, conv.message_var_index, types, None, None, ground_truth=torch.zeros_like(llr))
+    assert float(loss2.detach()) < float(loss.detach())
