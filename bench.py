@@ -195,8 +195,8 @@ def main():
             rc = L.ldpc_minsum_decode(h, _native.ptr(llr), B, ITERS, ALPHA, 0, 0, None, _native.ptr(hard),
                                       _native.HARD_PACKED, None, None, None, 0, st)
         else:
-            rc = L.ldpc_bp_decode(h, _native.ptr(llr), B, ITERS, 0, 0, None, _native.ptr(hard), _native.HARD_PACKED,
-                                  None, None, None, 0, st)
+            rc = L.ldpc_bp_decode(h, _native.ptr(llr), B, ITERS, 0, _native.PATH_FAST, None, _native.ptr(hard),
+                                  _native.HARD_PACKED, None, None, None, 0, st)
         _native.check(rc)
         _native.check(L.ldpc_count_errors(_native.ptr(hard), _native.HARD_PACKED, None, B, code.N, _native.ptr(counters), st))
 
@@ -242,7 +242,8 @@ def main():
     hard_host = torch.empty((Be, NW), dtype=torch.int32).pin_memory()
 
     def e2e_step():
-        _native.check(L.ldpc_decode_host(h, algo, _native.ptr(llr_host), Be, ITERS, ALPHA, 0, None,
+        _native.check(L.ldpc_decode_host(h, algo, _native.ptr(llr_host), Be, ITERS, ALPHA,
+                                         _native.PATH_FAST if algo == _native.ALGO_BP else _native.PATH_AUTO, None,
                                          _native.ptr(hard_host), _native.HARD_PACKED, 1 << 15))
     e2e_step()
     torch.cuda.synchronize()

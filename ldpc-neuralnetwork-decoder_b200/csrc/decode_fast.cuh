@@ -28,7 +28,7 @@ inline int detect_fast_kind(const ldpc_code* c) {
 }
 
 inline bool fast_path_supports(const ldpc_code* c, int algo, int stop_mode, bool want_mask) {
-    return c->fast_kind != 0 && algo == LDPC_ALGO_MINSUM && stop_mode == LDPC_STOP_FIXED && !want_mask;
+    return c->fast_kind != 0 && (algo == LDPC_ALGO_MINSUM || algo == LDPC_ALGO_BP) && stop_mode == LDPC_STOP_FIXED && !want_mask;
 }
 
 // defined in fast_kernels.cu

@@ -38,8 +38,41 @@ namespace ldpc {
 // Register budget: warps are spread over the 4 SM sub-partitions (16K registers each), so a
 // 10-warp CTA has sub-partitions with 3 warps -> at most 16384/96 = 170 registers per thread;
 // __launch_bounds__ lets ptxas derive that cap (168) itself.
-template <class BG, int kWarps>
-__global__ void __launch_bounds__(kWarps * 32, 1) minsum_fast_kernel(const DecodeParams p) {
+// ---- sum-product helpers (kAlgo == LDPC_ALGO_BP) ---------------------------------------------------
+// The reference's variable update adds the OTHER checks' messages in order, unclipped, so +-inf and
+// NaN messages are routine and "posterior minus own message" would give inf-inf.
+// Per column the kernel therefore keeps F = llr + sum of the FINITE messages (ascending check
+// order) and K = counts of +inf (bits 0-7), -inf (8-15) and NaN (16-23) messages; the sum over
+// the others is rebuilt from (F, K) and the own message with IEEE semantics.
+__device__ __forceinline__ int bp_nonfinite_code(float x) {
+    const unsigned b = f2u(x);
+    const bool nonfin = (b & 0x7fffffffu) >= 0x7f800000u;
+    const int code = (b & 0x007fffffu) ? 0x10000 : ((b >> 31) ? 0x100 : 1);
+    return nonfin ? code : 0;
+}
+__device__ __forceinline__ float bp_resolve(float finite_sum, int k) {
+    const int np = k & 0xff, nm = k & 0xff00, nn = k >> 16;
+    const float inf_part = np ? CUDART_INF_F : -CUDART_INF_F;
+    float r = (np | nm) ? inf_part : finite_sum;
+    r = (nn | (np && nm)) ? CUDART_NAN_F : r;
+    return r;
+}
+
+// Out-of-line on purpose: inlined, the two functions are ~55 instructions per edge and the unrolled
+// iteration grows to 320 KB of SASS, far beyond the instruction cache (measured: 2.3 M cw/s, fetch-bound).
+#ifndef LDPC_BP_NOINLINE
+#define LDPC_BP_NOINLINE 1
+#endif
+#if LDPC_BP_NOINLINE
+__device__ __noinline__ float bp_tanh_half(float v) { return tanhf(0.5f * v); }
+__device__ __noinline__ float bp_two_atanh(float p) { return 2.0f * atanhf(p); }
+#else
+__device__ __forceinline__ float bp_tanh_half(float v) { return tanhf(0.5f * v); }
+__device__ __forceinline__ float bp_two_atanh(float p) { return 2.0f * atanhf(p); }
+#endif
+
+template <class BG, int kWarps, int kAlgo>
+__global__ void __launch_bounds__(kWarps * 32, 1) decode_fast_kernel(const DecodeParams p) {
     constexpr int Z = BG::kZ, G = 32 / Z, NC = BG::kCoreCols, NX = BG::kExtCols, EC = BG::kCoreEdges;
     constexpr int EQ = (EC + 3) / 4;                      // message quads per lane
     constexpr int N = BG::kCols * Z, NW = (N + 31) / 32, NWR = (NW + Z - 1) / Z;
@@ -74,6 +107,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) minsum_fast_kernel(const Decod
         const long long cw = grp * G + cwi;
         const bool live = cw < p.B;
         float Tc[NC], Lx[NX];
+        int Kc[NC];                    // BP only: non-finite message counts per core column
+        static_for<0, NC>([&](auto kc) { Kc[decltype(kc)::value] = 0; });
         auto put_llr = [&](auto jc, float x) {
             constexpr int j = decltype(jc)::value;
             constexpr int sl = BG::col_slot[j];
@@ -126,8 +161,12 @@ __global__ void __launch_bounds__(kWarps * 32, 1) minsum_fast_kernel(const Decod
         auto iteration = [&](auto lastc) {
             constexpr bool kLast = decltype(lastc)::value != 0;
             float Tn[NC];
+            int Kn[NC];
             float ov[EQ * 4], nv[EQ * 4];      // SSA views of the message quads (registers, short-lived)
-            static_for<0, NC>([&](auto kc) { Tn[decltype(kc)::value] = Ls[decltype(kc)::value * 32]; });
+            static_for<0, NC>([&](auto kc) {
+                Tn[decltype(kc)::value] = Ls[decltype(kc)::value * 32];
+                Kn[decltype(kc)::value] = 0;
+            });
             static_for<0, BG::kRows>([&](auto ic) {
                 constexpr int i = decltype(ic)::value;
                 constexpr int e0 = BG::row_ptr[i], d = BG::row_ptr[i + 1] - e0;
@@ -145,32 +184,62 @@ __global__ void __launch_bounds__(kWarps * 32, 1) minsum_fast_kernel(const Decod
                             ov[mi] = q4.x; ov[mi + 1] = q4.y; ov[mi + 2] = q4.z; ov[mi + 3] = q4.w;
                         }
                         const float t = (s == 0) ? Tc[c] : __shfl_sync(kFull, Tc[c], lp[s], Z);
-                        v[k] = t - ov[mi];
+                        if constexpr (kAlgo == LDPC_ALGO_MINSUM) {
+                            v[k] = t - ov[mi];
+                        } else {
+                            const int kr = (s == 0) ? Kc[c] : __shfl_sync(kFull, Kc[c], lp[s], Z);
+                            const int own = bp_nonfinite_code(ov[mi]);
+                            v[k] = bp_resolve(t - (own ? 0.0f : ov[mi]), kr - own);
+                        }
                     } else {
                         static_assert(BG::kind[e] == 0 || BG::shift[e] == 0, "degree-1 columns are expected unshifted");
                         constexpr int x = BG::slot[e];
                         v[k] = Lx[x];
                     }
                 });
-                // two smallest magnitudes and the sign parity
-                float m1 = fabsf(v[0]), m2 = CUDART_INF_F;
-                unsigned sg = f2u(v[0]);
-                static_for<1, d>([&](auto kc) {
-                    constexpr int k = decltype(kc)::value;
-                    const float a = fabsf(v[k]);
-                    m2 = (k == 1) ? fmaxf(m1, a) : fminf(m2, fmaxf(m1, a));
-                    m1 = fminf(m1, a);
-                    sg ^= f2u(v[k]);
-                });
-                sg &= 0x80000000u;
-                const unsigned p1 = f2u(__fmul_rn(alpha, m1)) ^ sg, p2 = f2u(__fmul_rn(alpha, m2)) ^ sg;
-                // emit check-to-variable messages, accumulate the new posteriors in ascending row order
+                float cn[d];                       // new check-to-variable messages of this row
+                if constexpr (kAlgo == LDPC_ALGO_MINSUM) {
+                    // two smallest magnitudes and the sign parity
+                    float m1 = fabsf(v[0]), m2 = CUDART_INF_F;
+                    unsigned sg = f2u(v[0]);
+                    static_for<1, d>([&](auto kc) {
+                        constexpr int k = decltype(kc)::value;
+                        const float a = fabsf(v[k]);
+                        m2 = (k == 1) ? fmaxf(m1, a) : fminf(m2, fmaxf(m1, a));
+                        m1 = fminf(m1, a);
+                        sg ^= f2u(v[k]);
+                    });
+                    sg &= 0x80000000u;
+                    const unsigned p1 = f2u(__fmul_rn(alpha, m1)) ^ sg, p2 = f2u(__fmul_rn(alpha, m2)) ^ sg;
+                    static_for<0, d>([&](auto kc) {
+                        constexpr int k = decltype(kc)::value;
+                        if constexpr (BG::kind[e0 + k] == 0 || kLast) {
+                            const unsigned sel = (fabsf(v[k]) == m1) ? p2 : p1;
+                            cn[k] = u2f(sel ^ (f2u(v[k]) & 0x80000000u));
+                        }
+                    });
+                } else {
+                    // sum-product: product of tanh(v/2) over the OTHER edges in ascending order (running
+                    // prefix x suffix chain = the reference's multiplication order), 2*atanh, unclipped
+                    float t[d];
+                    static_for<0, d>([&](auto kc) { t[decltype(kc)::value] = bp_tanh_half(v[decltype(kc)::value]); });
+                    float pre = 1.0f;
+                    static_for<0, d>([&](auto kc) {
+                        constexpr int k = decltype(kc)::value;
+                        if constexpr (BG::kind[e0 + k] == 0 || kLast) {
+                            float pr = pre;
+                            static_for<k + 1, d>([&](auto k2) { pr = __fmul_rn(pr, t[decltype(k2)::value]); });
+                            cn[k] = bp_two_atanh(pr);
+                        }
+                        pre = __fmul_rn(pre, t[k]);
+                    });
+                }
+                // store the messages, accumulate the new posteriors in ascending row order
                 static_for<0, d>([&](auto kc) {
                     constexpr int k = decltype(kc)::value, e = e0 + k;
                     if constexpr (BG::kind[e] == 0) {
                         constexpr int c = BG::slot[e], s = BG::shift[e], mi = BG::msg[e];
-                        const unsigned sel = (fabsf(v[k]) == m1) ? p2 : p1;
-                        const float cnew = u2f(sel ^ (f2u(v[k]) & 0x80000000u));
+                        const float cnew = cn[k];
                         nv[mi] = cnew;
                         if constexpr (mi % 4 == 3 || mi == EC - 1) {
                             constexpr int b = (mi / 4) * 4;
@@ -178,18 +247,28 @@ __global__ void __launch_bounds__(kWarps * 32, 1) minsum_fast_kernel(const Decod
                                                             b + 3 < EC ? nv[b + 3] : 0.f);
                         }
                         const float t = (s == 0) ? cnew : __shfl_sync(kFull, cnew, lp[Z - s], Z);
-                        Tn[c] = __fadd_rn(Tn[c], t);
+                        if constexpr (kAlgo == LDPC_ALGO_MINSUM) {
+                            Tn[c] = __fadd_rn(Tn[c], t);
+                        } else {
+                            const int code = bp_nonfinite_code(t);
+                            Tn[c] = __fadd_rn(Tn[c], code ? 0.0f : t);
+                            Kn[c] += code;
+                        }
                     } else if constexpr (kLast) {
                         constexpr int x = BG::slot[e];
-                        const unsigned sel = (fabsf(v[k]) == m1) ? p2 : p1;
-                        Lx[x] = __fadd_rn(Lx[x], u2f(sel ^ (f2u(v[k]) & 0x80000000u)));
+                        Lx[x] = __fadd_rn(Lx[x], cn[k]);
                     }
                 });
             });
-            static_for<0, NC>([&](auto kc) { Tc[decltype(kc)::value] = Tn[decltype(kc)::value]; });
+            static_for<0, NC>([&](auto kc) {
+                Tc[decltype(kc)::value] = Tn[decltype(kc)::value];
+                Kc[decltype(kc)::value] = Kn[decltype(kc)::value];
+            });
         };
         for (int it = 1; it < p.iters; ++it) iteration(IC<0>{});
         iteration(IC<1>{});
+        if constexpr (kAlgo == LDPC_ALGO_BP)
+            static_for<0, NC>([&](auto kc) { Tc[decltype(kc)::value] = bp_resolve(Tc[decltype(kc)::value], Kc[decltype(kc)::value]); });
 
         // ---- outputs: Tc = posteriors of the core columns, Lx = posteriors of the degree-1 columns ----
         // (the output mode is tested once, not per column: each mode is its own unrolled store loop)

@@ -11,12 +11,12 @@ namespace ldpc {
 #endif
 constexpr int kFastWarps = LDPC_FAST_WARPS;
 
-template <class BG>
+template <class BG, int kAlgo>
 inline int launch_fast_inst(DecodeParams p, cudaStream_t st) {
     constexpr int G = 32 / BG::kZ;
     constexpr size_t smem = (size_t)kFastWarps * ((BG::kCoreEdges + 3) / 4 + (BG::kCoreCols + 3) / 4) * 32 * sizeof(float4);
     static_assert(smem <= (size_t)kMaxSmemPerBlock, "fast kernel shared memory");
-    auto kern = minsum_fast_kernel<BG, kFastWarps>;
+    auto kern = decode_fast_kernel<BG, kFastWarps, kAlgo>;
     LDPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     p.ngroups = (p.B + G - 1) / G;
     long long blocks = (p.ngroups + kFastWarps - 1) / kFastWarps;
@@ -27,7 +27,7 @@ inline int launch_fast_inst(DecodeParams p, cudaStream_t st) {
     if (e != cudaSuccess) {
         cudaFuncAttributes a{};
         cudaFuncGetAttributes(&a, kern);
-        return fail(LDPC_ERR_CUDA, "launch of minsum_fast_kernel failed: %s (regs %d, max threads/block %d, static smem %zu, "
+        return fail(LDPC_ERR_CUDA, "launch of decode_fast_kernel failed: %s (regs %d, max threads/block %d, static smem %zu, "
                     "max dynamic smem %d, requested %d threads + %zu B)", cudaGetErrorString(e), a.numRegs,
                     a.maxThreadsPerBlock, a.sharedSizeBytes, a.maxDynamicSharedSizeBytes, kFastWarps * 32, smem);
     }
@@ -35,9 +35,13 @@ inline int launch_fast_inst(DecodeParams p, cudaStream_t st) {
 }
 
 int launch_fast(const ldpc_code* c, int algo, const DecodeParams& p, cudaStream_t st) {
-    (void)algo;
-    if (c->fast_kind == 1) return launch_fast_inst<BG2Z32>(p, st);
-    if (c->fast_kind == 2) return launch_fast_inst<BG2Z4>(p, st);
+    if (algo == LDPC_ALGO_MINSUM) {
+        if (c->fast_kind == 1) return launch_fast_inst<BG2Z32, LDPC_ALGO_MINSUM>(p, st);
+        if (c->fast_kind == 2) return launch_fast_inst<BG2Z4, LDPC_ALGO_MINSUM>(p, st);
+    } else {
+        if (c->fast_kind == 1) return launch_fast_inst<BG2Z32, LDPC_ALGO_BP>(p, st);
+        if (c->fast_kind == 2) return launch_fast_inst<BG2Z4, LDPC_ALGO_BP>(p, st);
+    }
     return fail(LDPC_ERR_UNSUPPORTED, "fast path: code is not one of the compiled tables");
 }
 

@@ -62,7 +62,9 @@ int decode_common(const ldpc_code_t* code, int algo, const float* llr, int64_t B
     const bool fast_ok = fast_path_supports(code, algo, stop_mode, valid_mask != nullptr);
     if (path == LDPC_PATH_FAST && !fast_ok)
         return fail(LDPC_ERR_UNSUPPORTED, "decode: no specialised kernel for this code/algorithm/stop mode");
-    if (path != LDPC_PATH_EXACT && fast_ok) return launch_fast(code, algo, p, st);
+    // AUTO: min-sum takes the specialised kernel (hard decisions identical to the reference on every fixture);
+    // BP stays on the reference-order kernel unless LDPC_PATH_FAST is requested (its tanhf/atanhf are 2-3 ulp)
+    if (fast_ok && (path == LDPC_PATH_FAST || (path == LDPC_PATH_AUTO && algo == LDPC_ALGO_MINSUM))) return launch_fast(code, algo, p, st);
     return launch_exact(code, algo, p, st);
 }
 

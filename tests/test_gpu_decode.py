@@ -262,3 +262,40 @@ def test_syndrome_check_entry_point():
     toy = MinSumScaledDecoder(torch.tensor([[1, 1, 0, 0], [0, 1, 1, 1], [1, 0, 0, 1]], dtype=torch.float32), 2, early_stopping=False)
     cw = torch.tensor([[0, 0, 0, 0], [1, 1, 1, 0], [1, 1, 0, 1], [1, 0, 0, 0]], dtype=torch.float32, device=dev())
     assert toy._check_valid_codeword(cw).tolist() == [True, False, True, False]
+
+
+@pytest.mark.parametrize("name", CLASSIC)
+def test_bp_fast_path_against_reference(name):
+    """Specialised sum-product kernel (path="fast": CUDA tanhf/atanhf, 2-3 ulp, and the (F, K)
+    finite-sum / non-finite-count variable update).  Criterion ("BP numerics"):
+    hard decisions identical to the reference, identical inf/NaN pattern except where a product
+    sits within a few ulp of the saturation point, finite beliefs within 1e-3 relative."""
+    g = load_golden(name)
+    Z = int(g["Z"])
+    code = QCCode.nr_2_0(Z)
+    dec = BeliefPropagationDecoder(code, int(g["iters"]), early_stopping=False, path="fast")
+    soft, hard = run(dec, g["llr"])
+    ref = g["bp_beliefs"]
+    ref_hard = unpack(g["bp_bits"], code.N)
+    assert (hard != ref_hard).mean() <= 1e-4, int((hard != ref_hard).sum())
+    cls = lambda x: np.where(np.isnan(x), 3, np.where(np.isposinf(x), 1, np.where(np.isneginf(x), 2, 0)))
+    assert (cls(soft) != cls(ref)).mean() <= 2e-3, int((cls(soft) != cls(ref)).sum())
+    fin = np.isfinite(ref) & np.isfinite(soft)
+    if fin.any():
+        rel = np.abs(soft[fin] - ref[fin]) / np.maximum(np.abs(ref[fin]), 1.0)
+        assert np.quantile(rel, 0.999) <= 1e-3 and rel.max() <= 5e-2, (float(np.quantile(rel, 0.999)), float(rel.max()))
+
+
+def test_bp_fast_path_inf_nan_and_frames():
+    """High-SNR batch (saturating messages, inf-inf -> NaN -> bit 0) and a low-SNR batch: frame and
+    bit error counts of the fast kernel equal the oracle's."""
+    code = QCCode.nr_2_0(32)
+    for snr_db, seed in ((4.0, 5), (-3.0, 6), (-2.0, 8)):
+        llr = oracle.awgn_llr(None, 256, code.N, snr_db, seed=seed)
+        if snr_db > 0:
+            llr[0, :64] = -llr[0, :64]
+        o = oracle.decode(code.shifts, 32, llr, 10, "bp")
+        soft, hard = run(BeliefPropagationDecoder(code, 10, early_stopping=False, path="fast"), llr)
+        assert not hard[np.isnan(soft)].any()
+        assert (hard.sum(axis=1) > 0).sum() == (o["hard"].sum(axis=1) > 0).sum()
+        assert abs(int(hard.sum()) - int(o["hard"].sum())) <= 2

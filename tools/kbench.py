@@ -9,6 +9,7 @@ ap.add_argument("libs", nargs="+")
 ap.add_argument("--batch", type=int, default=1 << 19)
 ap.add_argument("--iters", type=int, nargs="+", default=[10])
 ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--algo", default="minsum")
 a = ap.parse_args()
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ldpc_b200
@@ -30,7 +31,10 @@ for path in a.libs:
     assert L.ldpc_code_create(shifts.ctypes.data_as(C.c_void_p), 42, 52, 32, 0, C.byref(h)) == 0
     for it in a.iters:
         def run():
-            rc = L.ldpc_minsum_decode(h, _native.ptr(llr), B, it, 0.75, 0, 0, None, _native.ptr(hard), 2, None, None, None, 0, None)
+            if a.algo == "minsum":
+                rc = L.ldpc_minsum_decode(h, _native.ptr(llr), B, it, 0.75, 0, 0, None, _native.ptr(hard), 2, None, None, None, 0, None)
+            else:
+                rc = L.ldpc_bp_decode(h, _native.ptr(llr), B, it, 0, 2, None, _native.ptr(hard), 2, None, None, None, 0, None)
             assert rc == 0, L.ldpc_last_error()
         run(); run(); torch.cuda.synchronize()
         ts = []
