@@ -71,6 +71,44 @@ __device__ __forceinline__ float bp_tanh_half(float v) { return tanhf(0.5f * v);
 __device__ __forceinline__ float bp_two_atanh(float p) { return 2.0f * atanhf(p); }
 #endif
 
+// ---- optional: resident messages in Tensor Memory instead of shared memory (LDPC_FAST_TMEM=1) -------
+// TMEM is 128 lanes x 512 columns x 32 bit per SM; a warp reaches the 32 lanes of its quarter
+// (warp_id % 4) with tcgen05.ld/st.32x32b, i.e. exactly a per-lane private array: lane i <-> TMEM
+// lane, message quad q <-> columns 4q..4q+3.  Moving the 160 message words there takes 320 of the
+// 622 wavefronts per codeword-iteration off the shared-memory/shuffle pipe (the binding unit).
+#ifndef LDPC_FAST_TMEM
+#define LDPC_FAST_TMEM 2
+#endif
+__device__ __forceinline__ float4 tmem_ld4(uint32_t taddr) {
+    uint32_t a, b, c, d;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(taddr));
+    // the wait carries the loaded registers so that no consumer is scheduled above it
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(a), "+r"(b), "+r"(c), "+r"(d));
+    return make_float4(u2f(a), u2f(b), u2f(c), u2f(d));
+}
+// split form for software pipelining: issue now, settle (wait + re-define the registers) later
+__device__ __forceinline__ void tmem_ld4_issue(uint32_t taddr, float& a, float& b, float& c, float& d) {
+    uint32_t x, y, z, w;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(x), "=r"(y), "=r"(z), "=r"(w) : "r"(taddr));
+    a = u2f(x); b = u2f(y); c = u2f(z); d = u2f(w);
+}
+__device__ __forceinline__ void tmem_tie4(float& a, float& b, float& c, float& d) {
+    // empty volatile asm after the wait: consumers depend on these re-definitions, so none of them
+    // can be scheduled above the tcgen05.wait::ld that precedes it
+    asm volatile("" : "+f"(a), "+f"(b), "+f"(c), "+f"(d));
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, float4 v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+                 :: "r"(taddr), "r"(f2u(v.x)), "r"(f2u(v.y)), "r"(f2u(v.z)), "r"(f2u(v.w)) : "memory");
+}
+
+template <class BG>
+constexpr size_t fast_smem_bytes(int warps) {
+    return (size_t)warps * ((LDPC_FAST_TMEM ? 0 : (BG::kCoreEdges + 3) / 4) + (BG::kCoreCols + 3) / 4) * 32 * sizeof(float4);
+}
+
 template <class BG, int kWarps, int kAlgo>
 __global__ void __launch_bounds__(kWarps * 32, 1) decode_fast_kernel(const DecodeParams p) {
     constexpr int Z = BG::kZ, G = 32 / Z, NC = BG::kCoreCols, NX = BG::kExtCols, EC = BG::kCoreEdges;
@@ -80,10 +118,26 @@ __global__ void __launch_bounds__(kWarps * 32, 1) decode_fast_kernel(const Decod
     extern __shared__ float4 smem4[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // per-lane private storage: quad q of this lane at mq[q*32]; conflict-free 128-bit accesses
-    float4* mq = smem4 + warp * ((EQ + (NC + 3) / 4) * 32) + lane;
-    float* Ls = reinterpret_cast<float*>(smem4 + warp * ((EQ + (NC + 3) / 4) * 32) + EQ * 32) + lane;   // Ls[k*32]
+    constexpr int kMsgQuads = LDPC_FAST_TMEM ? 0 : EQ;    // messages live in TMEM when LDPC_FAST_TMEM != 0
+    float4* mq = smem4 + warp * ((kMsgQuads + (NC + 3) / 4) * 32) + lane;
+    float* Ls = reinterpret_cast<float*>(smem4 + warp * ((kMsgQuads + (NC + 3) / 4) * 32) + kMsgQuads * 32) + lane;   // Ls[k*32]
+    (void)mq;
     const int cwi = lane / Z, r = lane % Z;
     const float alpha = p.alpha;
+#if LDPC_FAST_TMEM
+    static_assert(((kWarps + 3) / 4) * EQ * 4 <= 512, "warps sharing a TMEM lane quarter each need EQ*4 columns");
+    __shared__ uint32_t tmem_base_s;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;"
+                     :: "r"((uint32_t)__cvta_generic_to_shared(&tmem_base_s)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+    const uint32_t tq = tmem_base + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)(warp >> 2) * (uint32_t)(EQ * 4);   // this warp's window
+#endif
     unsigned long long acc_bits = 0, acc_fe = 0, acc_frames = 0, acc_und = 0;
     // source-lane operands of the rotations, lane+t for t = 1..Z-1, kept in registers (opaque to
     // the compiler so they are not recomputed with an integer add in front of every shuffle)
@@ -91,7 +145,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) decode_fast_kernel(const Decod
 #define LDPC_FAST_LP 1
 #endif
 #ifndef LDPC_FAST_FENCE
-#define LDPC_FAST_FENCE 8
+#define LDPC_FAST_FENCE 2
 #endif
     int lp[Z];
     static_for<0, Z>([&](auto tc) {
@@ -154,15 +208,51 @@ __global__ void __launch_bounds__(kWarps * 32, 1) decode_fast_kernel(const Decod
                 }
             }
         }
+#if LDPC_FAST_TMEM
+        static_for<0, EQ>([&](auto qc) { tmem_st4(tq + decltype(qc)::value * 4, make_float4(0.f, 0.f, 0.f, 0.f)); });
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+#else
         static_for<0, EQ>([&](auto qc) { mq[decltype(qc)::value * 32] = make_float4(0.f, 0.f, 0.f, 0.f); });
+#endif
 
         // One flooding iteration, fully unrolled and branch-free.  kLast additionally forms the
         // posteriors of the degree-1 columns (in place of their channel LLR registers).
+        float ov[EQ * 4];                  // SSA view of the old message quads (registers, short-lived)
+#if LDPC_FAST_TMEM == 2
+        // software-pipelined TMEM loads: the quads first touched by row group g+1 are issued when
+        // group g starts, and settled (one tcgen05.wait::ld) when group g+1 starts
+        constexpr int kGrp = LDPC_FAST_FENCE, kNumGrp = (BG::kRows + kGrp - 1) / kGrp;
+        auto for_group_quads = [&](auto gc, auto&& fn) {
+            constexpr int g = decltype(gc)::value;
+            constexpr int ea = BG::row_ptr[g * kGrp], eb = BG::row_ptr[(g + 1) * kGrp < BG::kRows ? (g + 1) * kGrp : BG::kRows];
+            static_for<ea, eb>([&](auto ec) {
+                constexpr int e = decltype(ec)::value;
+                if constexpr (BG::kind[e] == 0) {
+                    constexpr int mi = BG::msg[e];
+                    if constexpr (mi % 4 == 0) fn(IC<mi>{});
+                }
+            });
+        };
+        auto issue_group = [&](auto gc) {
+            for_group_quads(gc, [&](auto mc) {
+                constexpr int mi = decltype(mc)::value;
+                tmem_ld4_issue(tq + mi, ov[mi], ov[mi + 1], ov[mi + 2], ov[mi + 3]);
+            });
+        };
+        auto settle_group = [&](auto gc) {
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            for_group_quads(gc, [&](auto mc) {
+                constexpr int mi = decltype(mc)::value;
+                tmem_tie4(ov[mi], ov[mi + 1], ov[mi + 2], ov[mi + 3]);
+            });
+        };
+        issue_group(IC<0>{});
+#endif
         auto iteration = [&](auto lastc) {
             constexpr bool kLast = decltype(lastc)::value != 0;
             float Tn[NC];
             int Kn[NC];
-            float ov[EQ * 4], nv[EQ * 4];      // SSA views of the message quads (registers, short-lived)
+            float nv[EQ * 4];
             static_for<0, NC>([&](auto kc) {
                 Tn[decltype(kc)::value] = Ls[decltype(kc)::value * 32];
                 Kn[decltype(kc)::value] = 0;
@@ -173,6 +263,12 @@ __global__ void __launch_bounds__(kWarps * 32, 1) decode_fast_kernel(const Decod
 #if LDPC_FAST_FENCE
                 if constexpr (i % LDPC_FAST_FENCE == 0 && i > 0) asm volatile("" ::: "memory");
 #endif
+#if LDPC_FAST_TMEM == 2
+                if constexpr (i % kGrp == 0) {
+                    settle_group(IC<i / kGrp>{});
+                    if constexpr (i / kGrp + 1 < kNumGrp) issue_group(IC<i / kGrp + 1>{});
+                }
+#endif
                 float v[d];
                 // gather variable-to-check messages, check-aligned: v = T - c2v (core), llr (degree-1)
                 static_for<0, d>([&](auto kc) {
@@ -180,8 +276,13 @@ __global__ void __launch_bounds__(kWarps * 32, 1) decode_fast_kernel(const Decod
                     if constexpr (BG::kind[e] == 0) {
                         constexpr int c = BG::slot[e], s = BG::shift[e], mi = BG::msg[e];
                         if constexpr (mi % 4 == 0) {
+#if LDPC_FAST_TMEM == 1
+                            const float4 q4 = tmem_ld4(tq + (mi / 4) * 4);
+                            ov[mi] = q4.x; ov[mi + 1] = q4.y; ov[mi + 2] = q4.z; ov[mi + 3] = q4.w;
+#elif LDPC_FAST_TMEM == 0
                             const float4 q4 = mq[(mi / 4) * 32];
                             ov[mi] = q4.x; ov[mi + 1] = q4.y; ov[mi + 2] = q4.z; ov[mi + 3] = q4.w;
+#endif
                         }
                         const float t = (s == 0) ? Tc[c] : __shfl_sync(kFull, Tc[c], lp[s], Z);
                         if constexpr (kAlgo == LDPC_ALGO_MINSUM) {
@@ -243,8 +344,13 @@ __global__ void __launch_bounds__(kWarps * 32, 1) decode_fast_kernel(const Decod
                         nv[mi] = cnew;
                         if constexpr (mi % 4 == 3 || mi == EC - 1) {
                             constexpr int b = (mi / 4) * 4;
-                            mq[(mi / 4) * 32] = make_float4(nv[b], b + 1 < EC ? nv[b + 1] : 0.f, b + 2 < EC ? nv[b + 2] : 0.f,
-                                                            b + 3 < EC ? nv[b + 3] : 0.f);
+                            const float4 q4 = make_float4(nv[b], b + 1 < EC ? nv[b + 1] : 0.f, b + 2 < EC ? nv[b + 2] : 0.f,
+                                                          b + 3 < EC ? nv[b + 3] : 0.f);
+#if LDPC_FAST_TMEM
+                            tmem_st4(tq + (mi / 4) * 4, q4);
+#else
+                            mq[(mi / 4) * 32] = q4;
+#endif
                         }
                         const float t = (s == 0) ? cnew : __shfl_sync(kFull, cnew, lp[Z - s], Z);
                         if constexpr (kAlgo == LDPC_ALGO_MINSUM) {
@@ -264,6 +370,12 @@ __global__ void __launch_bounds__(kWarps * 32, 1) decode_fast_kernel(const Decod
                 Tc[decltype(kc)::value] = Tn[decltype(kc)::value];
                 Kc[decltype(kc)::value] = Kn[decltype(kc)::value];
             });
+#if LDPC_FAST_TMEM
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+#endif
+#if LDPC_FAST_TMEM == 2
+            if constexpr (!kLast) issue_group(IC<0>{});      // first row group of the next iteration
+#endif
         };
         for (int it = 1; it < p.iters; ++it) iteration(IC<0>{});
         iteration(IC<1>{});
@@ -351,6 +463,11 @@ __global__ void __launch_bounds__(kWarps * 32, 1) decode_fast_kernel(const Decod
         }
     }
     if (p.counters) flush_counters(p.counters, acc_bits, acc_fe, acc_frames, acc_und);
+#if LDPC_FAST_TMEM
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem_base) : "memory");
+#endif
 }
 
 }  // namespace ldpc

@@ -14,7 +14,7 @@ constexpr int kFastWarps = LDPC_FAST_WARPS;
 template <class BG, int kAlgo>
 inline int launch_fast_inst(DecodeParams p, cudaStream_t st) {
     constexpr int G = 32 / BG::kZ;
-    constexpr size_t smem = (size_t)kFastWarps * ((BG::kCoreEdges + 3) / 4 + (BG::kCoreCols + 3) / 4) * 32 * sizeof(float4);
+    constexpr size_t smem = fast_smem_bytes<BG>(kFastWarps);
     static_assert(smem <= (size_t)kMaxSmemPerBlock, "fast kernel shared memory");
     auto kern = decode_fast_kernel<BG, kFastWarps, kAlgo>;
     LDPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
