@@ -30,11 +30,15 @@ K_INFO, N_BITS, BASE_EDGES, Z = 320, 1664, 197, 32
 ITERS, ALPHA, SNR_DB = 10, 0.75, -2.0
 ISSUE_SLOTS_PER_EDGE_ITER = 18          # 14 ALU + 4 MIO lane-ops per edge-iteration
 SM_COUNT = 148
-# Binding resource of the min-sum kernel (ncu: l1tex__data_pipe_lsu_wavefronts_mem_shared is the
-# busiest unit): the shared-memory/shuffle data pipe, 1 wavefront (32 lanes x 4 B) per clock per
-# SM.  Algorithmic wavefronts per codeword-iteration of BG2 (DESIGN.md "Roofline"): 159 core
-# cells x (1 load + 1 store of the resident message) + 145 shifted core cells x 2 rotations +
-# 14 channel-LLR reloads = 622.  Degree-1 columns and unshifted cells need no rotation.
+# Binding resource of the min-sum kernel (ncu r1d: sm__inst_executed_pipe_alu is the busiest unit,
+# 82 %): the ALU pipe (min/max, compare, select, logic), 64 lanes = 2 warp-instructions per clock
+# per SM.  ALU-pipe work per codeword-iteration of BG2 (DESIGN.md "Roofline"): magnitude scan
+# 2 FMNMX-class ops per cell incl. FMNMX3 fusions (374) + sign parity, one 3-input XOR per 2 cells
+# (98) + per core cell compare / select / sign-apply (3 x 159) + per row sign mask and two merged
+# scaled minima (3 x 42, less 33 fused) = 1042 warp-instructions (counted in the SASS of the
+# unrolled iteration).  Until the messages moved to Tensor Memory the shared-memory/shuffle pipe
+# was the bound (622 wavefronts per codeword-iteration, 1 per clock per SM); it is still reported.
+ALU_OPS_PER_CW_ITER = 1042
 SMEM_WAVEFRONTS_PER_CW_ITER = 159 * 2 + 145 * 2 + 14
 # DRAM bytes per codeword of the decode kernel measured by `ncu --set full` (profiles/r1_ncu_minsum_fast.md,
 # capture r1c: dram__bytes_read.sum + dram__bytes_write.sum = 1.8025 GB for 262144 codewords)
@@ -264,9 +268,10 @@ def main():
         peaks, peak_src = measured_peaks()
         kernel_ms = step_ms[len(step_ms) // 2]                    # median launch (decode + tiny count kernel)
         sm_max = float(peaks.get("sm_max_mhz", 1965.0))
-        wavefronts = B * SMEM_WAVEFRONTS_PER_CW_ITER * ITERS
-        achieved = wavefronts / (kernel_ms * 1e-3) / 1e9          # G wavefronts / s, one GPU
-        peak = SM_COUNT * sm_max * 1e6 / 1e9                      # 1 wavefront / clk / SM
+        achieved = B * ALU_OPS_PER_CW_ITER * ITERS / (kernel_ms * 1e-3) / 1e9     # G ALU warp-instr / s, one GPU
+        peak = SM_COUNT * 2 * sm_max * 1e6 / 1e9                                  # 2 warp-instr / clk / SM
+        smem_ach = B * SMEM_WAVEFRONTS_PER_CW_ITER * ITERS / (kernel_ms * 1e-3) / 1e9
+        smem_peak = SM_COUNT * sm_max * 1e6 / 1e9
         edge_iters = B * BASE_EDGES * Z * ITERS
         issue_ach = edge_iters / (kernel_ms * 1e-3) / 1e9
         issue_peak = SM_COUNT * 4 * 32 * sm_max * 1e6 / ISSUE_SLOTS_PER_EDGE_ITER / 1e9
@@ -284,14 +289,17 @@ def main():
             "e2e": {"value": e2e_value, "unit": "Gbit/s", "h2d_bytes_per_step": Be * code.N * 4,
                     "d2h_bytes_per_step": Be * NW * 4, "codewords_per_step": Be, "steps": args.e2e_steps,
                     "api": "ldpc_decode_host (pinned host LLRs -> packed hard bits)"},
-            "roofline": {"bound": "smem_pipe", "achieved": achieved, "peak": peak, "unit": "Gwavefront/s",
+            "roofline": {"bound": "alu_pipe", "achieved": achieved, "peak": peak, "unit": "Gwarp-instr/s",
                          "frac": achieved / peak,
                          "traffic": (NCU_DRAM_BYTES_PER_CW * B if args.workload == "minsum" else None),
-                         "traffic_unit": "bytes of DRAM per launch (ncu r1c), algorithmic = %d" % algo_bytes_fn(B),
-                         "model": f"{SMEM_WAVEFRONTS_PER_CW_ITER} shared-memory/shuffle wavefronts per codeword-iteration "
-                                  f"(algorithmic, DESIGN.md), 148 SMs x 1 wavefront/clk at {sm_max:.0f} MHz ({peak_src} max clock)",
+                         "traffic_unit": "bytes of DRAM per launch (ncu), algorithmic = %d" % algo_bytes_fn(B),
+                         "model": f"{ALU_OPS_PER_CW_ITER} ALU-pipe warp-instructions per codeword-iteration (DESIGN.md 3.1), "
+                                  f"148 SMs x 2 warp-instr/clk at {sm_max:.0f} MHz ({peak_src} max clock)",
                          "frac_at_measured_clock": (achieved / (peak * clocks["sm_mhz"] / sm_max)) if clocks and clocks.get("sm_mhz") else None,
                          "kernel_ms": kernel_ms,
+                         "smem_pipe_model": {"achieved": smem_ach, "peak": smem_peak, "unit": "Gwavefront/s", "frac": smem_ach / smem_peak,
+                                             "note": "622 shared-memory/shuffle wavefronts per codeword-iteration had the messages "
+                                                     "stayed in shared memory (the bound of the pre-TMEM kernel)"},
                          "survey_issue_model": {"achieved": issue_ach, "peak": issue_peak, "unit": "Gedge-iter/s",
                                                 "frac": issue_ach / issue_peak,
                                                 "note": "SURVEY 8d estimate of 18 issue slots per edge-iteration; the kernel "
