@@ -310,6 +310,28 @@ __global__ void __launch_bounds__(kWarps * 32, 1) decode_fast_kernel(const Decod
                         m1 = fminf(m1, a);
                         sg ^= f2u(v[k]);
                     });
+#ifndef LDPC_FAST_IMAD_SELECT
+#define LDPC_FAST_IMAD_SELECT 1
+#endif
+#if LDPC_FAST_IMAD_SELECT
+                    // ALU-pipe diet (the binding unit): the two candidate messages differ by an integer
+                    // constant per row, so the select is an integer multiply-add on the FMA pipe:
+                    //   c = p1 ^ (v & signbit)                 LOP3        (ALU)   [xor of the top bit == add mod 2^32]
+                    //   P = (|v| == m1)                        FSETP       (ALU)
+                    //   @P c += p2 - p1                        IMAD.IADD   (FMA pipe, predicated)
+                    const unsigned q1 = f2u(__fmul_rn(alpha, m1)), q2 = f2u(__fmul_rn(alpha, m2));
+                    const unsigned p1 = q1 ^ (sg & 0x80000000u);
+                    const int ndp = (int)q1 - (int)q2;
+                    static_for<0, d>([&](auto kc) {
+                        constexpr int k = decltype(kc)::value;
+                        if constexpr (BG::kind[e0 + k] == 0 || kLast) {
+                            unsigned c = p1 ^ (f2u(v[k]) & 0x80000000u);
+                            asm("{ .reg .pred p; setp.eq.f32 p, %1, %2; @p mad.lo.s32 %0, %3, 1, %0; }"
+                                : "+r"(c) : "f"(fabsf(v[k])), "f"(m1), "r"(-ndp));
+                            cn[k] = u2f(c);
+                        }
+                    });
+#else
                     sg &= 0x80000000u;
                     const unsigned p1 = f2u(__fmul_rn(alpha, m1)) ^ sg, p2 = f2u(__fmul_rn(alpha, m2)) ^ sg;
                     static_for<0, d>([&](auto kc) {
@@ -319,6 +341,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) decode_fast_kernel(const Decod
                             cn[k] = u2f(sel ^ (f2u(v[k]) & 0x80000000u));
                         }
                     });
+#endif
                 } else {
                     // sum-product: product of tanh(v/2) over the OTHER edges in ascending order (running
                     // prefix x suffix chain = the reference's multiplication order), 2*atanh, unclipped
