@@ -30,19 +30,21 @@ K_INFO, N_BITS, BASE_EDGES, Z = 320, 1664, 197, 32
 ITERS, ALPHA, SNR_DB = 10, 0.75, -2.0
 ISSUE_SLOTS_PER_EDGE_ITER = 18          # 14 ALU + 4 MIO lane-ops per edge-iteration
 SM_COUNT = 148
-# Binding resource of the min-sum kernel (ncu r1d: sm__inst_executed_pipe_alu is the busiest unit,
-# 82 %): the ALU pipe (min/max, compare, select, logic), 64 lanes = 2 warp-instructions per clock
-# per SM.  ALU-pipe work per codeword-iteration of BG2 (DESIGN.md "Roofline"): magnitude scan
-# 2 FMNMX-class ops per cell incl. FMNMX3 fusions (374) + sign parity, one 3-input XOR per 2 cells
-# (98) + per core cell compare / select / sign-apply (3 x 159) + per row sign mask and two merged
-# scaled minima (3 x 42, less 33 fused) = 1042 warp-instructions (counted in the SASS of the
-# unrolled iteration).  Until the messages moved to Tensor Memory the shared-memory/shuffle pipe
-# was the bound (622 wavefronts per codeword-iteration, 1 per clock per SM); it is still reported.
-ALU_OPS_PER_CW_ITER = 1042
+# Binding resource of the min-sum kernel (ncu capture r1e, profiles/r1_ncu_minsum_fast.md): the
+# instruction ISSUE rate -- sm__issue_active 74.6 % is the highest utilisation (ALU pipe 70 %, shared/
+# shuffle pipe 48 %, FMA pipe 25 %, TMEM 3 %, DRAM 3 %).  Work per codeword = 19 075 warp-instructions
+# (smsp__inst_executed.sum / codewords): 10 iterations x 1 870 (FMNMX/FMNMX3 374, FADD 318, LOP3 292,
+# SHFL 290, FSETP 159, IMAD 190, FMUL 84, LDTM+STTM 80, LDS 14, ...) + 375 per codeword for load,
+# message zeroing and output.  Peak: 4 warp-instructions per clock per SM.
+ISSUE_INSTR_PER_CW = 19075
+# earlier binding units, still reported: ALU pipe (825 ALU-pipe instructions per codeword-iteration at
+# 2 per clock per SM) and, before the messages moved to Tensor Memory, the shared-memory/shuffle pipe
+# (622 wavefronts per codeword-iteration at 1 per clock per SM).
+ALU_OPS_PER_CW_ITER = 825
 SMEM_WAVEFRONTS_PER_CW_ITER = 159 * 2 + 145 * 2 + 14
 # DRAM bytes per codeword of the decode kernel measured by `ncu --set full` (profiles/r1_ncu_minsum_fast.md,
-# capture r1c: dram__bytes_read.sum + dram__bytes_write.sum = 1.8025 GB for 262144 codewords)
-NCU_DRAM_BYTES_PER_CW = 6876.0
+# capture r1e: dram__bytes_read.sum + dram__bytes_write.sum = 1.8010 GB for 262144 codewords)
+NCU_DRAM_BYTES_PER_CW = 6870.0
 
 
 def measured_peaks():
@@ -268,8 +270,10 @@ def main():
         peaks, peak_src = measured_peaks()
         kernel_ms = step_ms[len(step_ms) // 2]                    # median launch (decode + tiny count kernel)
         sm_max = float(peaks.get("sm_max_mhz", 1965.0))
-        achieved = B * ALU_OPS_PER_CW_ITER * ITERS / (kernel_ms * 1e-3) / 1e9     # G ALU warp-instr / s, one GPU
-        peak = SM_COUNT * 2 * sm_max * 1e6 / 1e9                                  # 2 warp-instr / clk / SM
+        achieved = B * ISSUE_INSTR_PER_CW / (kernel_ms * 1e-3) / 1e9               # G warp-instructions / s, one GPU
+        peak = SM_COUNT * 4 * sm_max * 1e6 / 1e9                                   # 4 warp-instr / clk / SM
+        alu_ach = B * ALU_OPS_PER_CW_ITER * ITERS / (kernel_ms * 1e-3) / 1e9
+        alu_peak = SM_COUNT * 2 * sm_max * 1e6 / 1e9
         smem_ach = B * SMEM_WAVEFRONTS_PER_CW_ITER * ITERS / (kernel_ms * 1e-3) / 1e9
         smem_peak = SM_COUNT * sm_max * 1e6 / 1e9
         edge_iters = B * BASE_EDGES * Z * ITERS
@@ -289,14 +293,16 @@ def main():
             "e2e": {"value": e2e_value, "unit": "Gbit/s", "h2d_bytes_per_step": Be * code.N * 4,
                     "d2h_bytes_per_step": Be * NW * 4, "codewords_per_step": Be, "steps": args.e2e_steps,
                     "api": "ldpc_decode_host (pinned host LLRs -> packed hard bits)"},
-            "roofline": {"bound": "alu_pipe", "achieved": achieved, "peak": peak, "unit": "Gwarp-instr/s",
+            "roofline": {"bound": "issue", "achieved": achieved, "peak": peak, "unit": "Gwarp-instr/s",
                          "frac": achieved / peak,
                          "traffic": (NCU_DRAM_BYTES_PER_CW * B if args.workload == "minsum" else None),
                          "traffic_unit": "bytes of DRAM per launch (ncu), algorithmic = %d" % algo_bytes_fn(B),
-                         "model": f"{ALU_OPS_PER_CW_ITER} ALU-pipe warp-instructions per codeword-iteration (DESIGN.md 3.1), "
-                                  f"148 SMs x 2 warp-instr/clk at {sm_max:.0f} MHz ({peak_src} max clock)",
+                         "model": f"{ISSUE_INSTR_PER_CW} warp-instructions per codeword (ncu, 10 x 1870 + 375; DESIGN.md 3.1), "
+                                  f"148 SMs x 4 warp-instr/clk at {sm_max:.0f} MHz ({peak_src} max clock)",
                          "frac_at_measured_clock": (achieved / (peak * clocks["sm_mhz"] / sm_max)) if clocks and clocks.get("sm_mhz") else None,
                          "kernel_ms": kernel_ms,
+                         "alu_pipe_model": {"achieved": alu_ach, "peak": alu_peak, "unit": "Gwarp-instr/s", "frac": alu_ach / alu_peak,
+                                            "note": "825 ALU-pipe instructions per codeword-iteration at 2/clk/SM"},
                          "smem_pipe_model": {"achieved": smem_ach, "peak": smem_peak, "unit": "Gwavefront/s", "frac": smem_ach / smem_peak,
                                              "note": "622 shared-memory/shuffle wavefronts per codeword-iteration had the messages "
                                                      "stayed in shared memory (the bound of the pre-TMEM kernel)"},
