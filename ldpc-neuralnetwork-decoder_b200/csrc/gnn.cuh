@@ -45,6 +45,8 @@ struct ldpc_gnn {
     int* d_chk_ptr = nullptr;     // [M+1] (messages of a check are contiguous)
     float* d_packed = nullptr;    // per-call repacked weights (layers * kPackedPerLayer floats)
     float* d_emb = nullptr;       // per-call 16-byte aligned copy of the type embeddings [layers][types][h]
+    float* d_tc = nullptr;        // per-call tf32 hi/lo weight images in the tensor-core operand layout (gnn_tc.cuh)
+    int* d_status = nullptr;      // set to 1 if a tensor-core kernel timed out waiting for its MMAs
     size_t params = 0;
 };
 

@@ -1,0 +1,350 @@
+// gnn_tc.cuh -- tensor-core (tcgen05) forward kernels of the message-centred GNN decoder.
+//
+// The two shared MLPs of MessageGNNLayer.forward (models/message_gnn_decoder.py:111-124) are a real
+// dense contraction (hidden 64: per 128-message tile [128x64].[64x128] then [128x128].[128x64]), so
+// they run on the 5th-generation tensor cores: tcgen05.mma kind::tf32, operands in shared memory
+// (K-major, no-swizzle canonical layout), fp32 accumulators in Tensor Memory, completion through an
+// mbarrier (tcgen05.commit), epilogue with tcgen05.ld (thread i of warp w owns TMEM lane 32w+i = row).
+//
+// Precision: a single TF32 product misses the 1e-4 tolerance (measured 2.6e-4 relative on a 64-deep
+// dot product, tools/probe/umma_probe.cu).  Every operand is therefore split
+// x = hi + lo (hi = tf32(x), lo = tf32(x - hi)) and each product is issued as three MMAs
+// lo.hi + hi.lo + hi.hi ("3xTF32"): measured 5.5e-7 relative, i.e. fp32-level, at one third of the
+// TF32 rate (still ~5x the FP32 FMA peak).
+//
+// Tile = 128 messages (rows), 128 threads, one thread per row for all CUDA-core work:
+//   1. comb = x + emb[type] -> split -> A_hi/A_lo (shared, canonical layout)
+//   2. GEMM1: D1[128x128] = comb . W1A^T                       (8 k-steps x 3 MMAs, N=128)
+//   3. h = relu(D1[:, 0:64] + Pv[var]) -> split -> A region;  GEMM2a: D2[128x64]  = h . W2[:, 0:64]^T
+//   4. h = relu(D1[:, 64:128] + Pc[chk]) -> split -> A region; GEMM2b: D2 += h . W2[:, 64:128]^T
+//   5. y = D2 + b2 (+ x for layers > 0)
+// Shared memory: W1A hi/lo 64 KB + W2 hi/lo 64 KB + A region hi/lo 64 KB = 192 KB, TMEM 256 columns.
+// The node kernel (Pv / Pc) has the same shape with a single GEMM per 128-node tile.
+#pragma once
+#include "gnn.cuh"
+
+namespace ldpc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// canonical no-swizzle K-major layout of a [R x K] fp32 operand: 8-row x 16-byte core matrices,
+// K-adjacent core matrices 128 B apart (LBO), 8-row groups (K/4)*128 B apart (SBO)
+__host__ __device__ constexpr uint32_t canon_off(int r, int k, int K) {
+    return (uint32_t)((r >> 3) * (K / 4) * 128 + (k >> 2) * 128 + (r & 7) * 16 + (k & 3) * 4);
+}
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);      // version 1, SWIZZLE_NONE
+}
+// instruction descriptor: D = F32, A = B = TF32, both K-major, M = 128
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* mbar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(mbar)) : "memory");
+}
+// 3xTF32 product over K (multiple of 8): D (+)= (Ahi+Alo) . (Bhi+Blo)^T without the lo.lo term
+__device__ __forceinline__ void umma_gemm3(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
+                                            int K, uint32_t sbo_a, uint32_t sbo_b, uint32_t idesc, bool accumulate) {
+    uint32_t acc = accumulate ? 1u : 0u;
+    for (int ks = 0; ks < K / 8; ++ks) {
+        const uint32_t ko = (uint32_t)ks * 256u;                              // two 16-byte k-chunks per MMA
+        umma_tf32(d_tmem, umma_desc(a_lo + ko, 128, sbo_a), umma_desc(b_hi + ko, 128, sbo_b), idesc, acc);
+        umma_tf32(d_tmem, umma_desc(a_hi + ko, 128, sbo_a), umma_desc(b_lo + ko, 128, sbo_b), idesc, 1u);
+        umma_tf32(d_tmem, umma_desc(a_hi + ko, 128, sbo_a), umma_desc(b_hi + ko, 128, sbo_b), idesc, 1u);
+        acc = 1u;
+    }
+}
+// bounded wait (never hang the GPU): returns false on timeout
+__device__ __forceinline__ bool mbar_wait(uint64_t* mbar, uint32_t parity) {
+    uint32_t done = 0;
+    for (long long spins = 0; !done; ++spins) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(mbar)), "r"(parity) : "memory");
+        if (spins > 50000000LL) return false;
+    }
+    return true;
+}
+__device__ __forceinline__ float tf32_hi(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]));
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// write 4 consecutive k elements (one 16-byte chunk c) of row r, split hi/lo, into a canonical [R x K] pair
+__device__ __forceinline__ void put_chunk(uint8_t* hi, uint8_t* lo, int r, int c, int K, float a, float b, float cc, float d) {
+    const float4 h = make_float4(tf32_hi(a), tf32_hi(b), tf32_hi(cc), tf32_hi(d));
+    const float4 l = make_float4(tf32_hi(a - h.x), tf32_hi(b - h.y), tf32_hi(cc - h.z), tf32_hi(d - h.w));
+    const uint32_t off = (uint32_t)((r >> 3) * (K / 4) * 128 + c * 128 + (r & 7) * 16);
+    *reinterpret_cast<float4*>(hi + off) = h;
+    *reinterpret_cast<float4*>(lo + off) = l;
+}
+
+// ---- weights: packed fp32 (gnn_pack_kernel) -> hi/lo canonical images in global memory -------------
+// per layer: W1A [128 x 64] hi, lo | W2 [64 x 128] hi, lo | W1BV [64 x 64] hi, lo | W1BC [64 x 64] hi, lo  (floats)
+constexpr int kTcW1A = 0, kTcW2 = kTcW1A + 2 * 128 * 64, kTcW1BV = kTcW2 + 2 * 64 * 128, kTcW1BC = kTcW1BV + 2 * 64 * 64,
+              kTcPerLayer = kTcW1BC + 2 * 64 * 64;
+__global__ void gnn_pack_tc_kernel(const float* __restrict__ packed, float* __restrict__ tc) {
+    const int l = blockIdx.y;
+    const float* pk = packed + (size_t)l * kPackedPerLayer;
+    float* o = tc + (size_t)l * kTcPerLayer;
+    auto put = [&](float* base, int rows, int K, int r, int k, float w) {
+        const float h = tf32_hi(w);
+        base[canon_off(r, k, K) / 4] = h;
+        base[rows * K + canon_off(r, k, K) / 4] = tf32_hi(w - h);
+    };
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < 128 * 64; t += gridDim.x * blockDim.x) {
+        put(o + kTcW1A, 128, 64, t / 64, t % 64, pk[kPkW1A + t]);                   // W1A[n][k], n < 128
+        put(o + kTcW2, 64, 128, t / 128, t % 128, pk[kPkW2 + t]);                    // W2[n][k], k < 128
+        if (t < 64 * 64) {
+            put(o + kTcW1BV, 64, 64, t / 64, t % 64, pk[kPkW1BV + t]);
+            put(o + kTcW1BC, 64, 64, t / 64, t % 64, pk[kPkW1BC + t]);
+        }
+    }
+}
+
+constexpr int kTcThreads = 128;
+constexpr size_t kEdgeTcSmem = (size_t)(2 * 128 * 64 + 2 * 64 * 128 + 2 * 128 * 64) * sizeof(float);   // 192 KB
+
+template <bool kResidual>
+__global__ void __launch_bounds__(kTcThreads, 1) gnn_edge_tc_kernel(
+    const float* __restrict__ x, const float* __restrict__ emb_l, const float* __restrict__ packed_l, const float* __restrict__ tc_l,
+    const int* __restrict__ edge_var, const int* __restrict__ edge_chk, const int* __restrict__ edge_type,
+    const float* __restrict__ Pv, const float* __restrict__ Pc, long long B, int E, int N, int M, float* __restrict__ y,
+    int* __restrict__ status) {
+    extern __shared__ __align__(1024) uint8_t tc_smem[];
+    uint8_t* W1Ahi = tc_smem;                                  // [128 x 64]
+    uint8_t* W1Alo = W1Ahi + 128 * 64 * 4;
+    uint8_t* W2hi = W1Alo + 128 * 64 * 4;                   // [64 x 128]
+    uint8_t* W2lo = W2hi + 64 * 128 * 4;
+    uint8_t* Ahi = W2lo + 64 * 128 * 4;                     // [128 x 64]: comb, then each half of relu(h)
+    uint8_t* Alo = Ahi + 128 * 64 * 4;
+    __shared__ uint64_t mbar;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float b2s[kH];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" :: "r"(smem_u32(&tmem_base_s)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&mbar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    {   // weights: the canonical hi/lo images are contiguous in global memory in the same order as in shared memory
+        const float4* src = reinterpret_cast<const float4*>(tc_l + kTcW1A);
+        float4* dst = reinterpret_cast<float4*>(tc_smem);
+        for (int t = tid; t < (2 * 128 * 64 + 2 * 64 * 128) / 4; t += kTcThreads) dst[t] = src[t];
+        if (tid < kH) b2s[tid] = packed_l[kPkB2 + tid];
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base_s;
+    const uint32_t d1 = tmem, d2 = tmem + 128;                                  // accumulators: columns [0,128) and [128,192)
+    const uint32_t my_lane = ((uint32_t)(warp * 32)) << 16;
+    constexpr uint32_t kIdesc128 = umma_idesc_tf32(128), kIdesc64 = umma_idesc_tf32(64);
+    uint32_t phase = 0;
+    bool ok = true;
+    const long long rows = B * E, tiles = (rows + 127) / 128;
+    for (long long tile = blockIdx.x; tile < tiles && ok; tile += gridDim.x) {
+        const long long row = tile * 128 + tid;
+        const bool live = row < rows;
+        const int e = live ? (int)(row % E) : 0;
+        const long long b = live ? row / E : 0;
+        // 1. comb -> A (hi/lo)
+        {
+            const float4* xr = reinterpret_cast<const float4*>(x + (size_t)(live ? row : 0) * kH);
+            const float4* er = reinterpret_cast<const float4*>(emb_l + (size_t)edge_type[e] * kH);
+#pragma unroll
+            for (int c = 0; c < kH / 4; ++c) {
+                const float4 v = live ? xr[c] : make_float4(0.f, 0.f, 0.f, 0.f), em = __ldg(er + c);
+                put_chunk(Ahi, Alo, tid, c, 64, v.x + em.x, v.y + em.y, v.z + em.z, v.w + em.w);
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        // 2. GEMM1: D1 = comb . W1A^T
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            umma_gemm3(d1, smem_u32(Ahi), smem_u32(Alo), smem_u32(W1Ahi), smem_u32(W1Alo), 64, 2048, 2048, kIdesc128, false);
+            umma_commit(&mbar);
+        }
+        ok = mbar_wait(&mbar, phase); phase ^= 1;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // 3./4. two halves of the hidden layer
+#pragma unroll 1
+        for (int half = 0; half < 2 && ok; ++half) {
+            const float4* pp = half == 0 ? reinterpret_cast<const float4*>(Pv + ((size_t)b * N + edge_var[e]) * kH)
+                                         : reinterpret_cast<const float4*>(Pc + ((size_t)b * M + edge_chk[e]) * kH);
+#pragma unroll
+            for (int c0 = 0; c0 < kH; c0 += 16) {
+                float h[16];
+                tmem_ld16(d1 + my_lane + half * kH + c0, h);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 pq = live ? pp[(c0 >> 2) + q] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    put_chunk(Ahi, Alo, tid, (c0 >> 2) + q, 64, fmaxf(h[q * 4] + pq.x, 0.f), fmaxf(h[q * 4 + 1] + pq.y, 0.f),
+                              fmaxf(h[q * 4 + 2] + pq.z, 0.f), fmaxf(h[q * 4 + 3] + pq.w, 0.f));
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();
+            if (tid == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                // W2 is [64 x 128] (SBO 4096); this half uses k in [64*half, 64*half+64): 16 chunks = 2048 bytes in
+                umma_gemm3(d2, smem_u32(Ahi), smem_u32(Alo), smem_u32(W2hi) + half * 2048, smem_u32(W2lo) + half * 2048, 64,
+                           2048, 4096, kIdesc64, half != 0);
+                umma_commit(&mbar);
+            }
+            ok = mbar_wait(&mbar, phase); phase ^= 1;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        // 5. y = D2 + b2 (+ x)
+        if (ok) {
+            const float4* xr = reinterpret_cast<const float4*>(x + (size_t)(live ? row : 0) * kH);
+            float4* yr = reinterpret_cast<float4*>(y + (size_t)(live ? row : 0) * kH);
+#pragma unroll
+            for (int c0 = 0; c0 < kH; c0 += 16) {
+                float o[16];
+                tmem_ld16(d2 + my_lane + c0, o);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float4 r = make_float4(o[q * 4] + b2s[c0 + q * 4], o[q * 4 + 1] + b2s[c0 + q * 4 + 1],
+                                           o[q * 4 + 2] + b2s[c0 + q * 4 + 2], o[q * 4 + 3] + b2s[c0 + q * 4 + 3]);
+                    if constexpr (kResidual) {
+                        if (live) { const float4 v = xr[(c0 >> 2) + q]; r.x += v.x; r.y += v.y; r.z += v.z; r.w += v.w; }
+                    }
+                    if (live) yr[(c0 >> 2) + q] = r;
+                }
+            }
+        }
+        // the next tile overwrites the A region and D1/D2: every thread must be done reading TMEM first
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    if (!ok) { if (tid == 0) atomicExch(status, 1); asm volatile("trap;"); }     // MMA completion never arrived: fail loudly
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" :: "r"(tmem) : "memory");
+}
+
+// ---- node kernel on tensor cores: P[b][node][:] = W1B . mean_{e in node}(x + emb) + b1 ----------------
+constexpr size_t kNodeTcSmem = (size_t)(2 * 64 * 64 + 2 * 128 * 64) * sizeof(float);   // 96 KB -> 2 CTAs per SM
+
+__global__ void __launch_bounds__(kTcThreads, 2) gnn_node_tc_kernel(
+    const float* __restrict__ x, const float* __restrict__ emb_l, const float* __restrict__ packed_l, const float* __restrict__ tc_l,
+    int kind, const int* __restrict__ ptr, const int* __restrict__ list, const int* __restrict__ edge_type, long long B, int E,
+    int nodes, float* __restrict__ P, int* __restrict__ status) {
+    extern __shared__ __align__(1024) uint8_t tc_smem[];
+    uint8_t* Whi = tc_smem;                                    // W1B [64 x 64]
+    uint8_t* Wlo = Whi + 64 * 64 * 4;
+    uint8_t* Ahi = Wlo + 64 * 64 * 4;                       // means [128 x 64]
+    uint8_t* Alo = Ahi + 128 * 64 * 4;
+    __shared__ uint64_t mbar;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float b1s[kH];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" :: "r"(smem_u32(&tmem_base_s)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&mbar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    {
+        const float4* src = reinterpret_cast<const float4*>(tc_l + (kind == 0 ? kTcW1BV : kTcW1BC));
+        float4* dst = reinterpret_cast<float4*>(tc_smem);
+        for (int t = tid; t < 2 * 64 * 64 / 4; t += kTcThreads) dst[t] = src[t];
+        if (tid < kH) b1s[tid] = packed_l[(kind == 0 ? kPkB1V : kPkB1C) + tid];
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base_s;
+    const uint32_t my_lane = ((uint32_t)(warp * 32)) << 16;
+    constexpr uint32_t kIdesc64 = umma_idesc_tf32(64);
+    uint32_t phase = 0;
+    bool ok = true;
+    const long long rows = B * nodes, tiles = (rows + 127) / 128;
+    for (long long tile = blockIdx.x; tile < tiles && ok; tile += gridDim.x) {
+        const long long row = tile * 128 + tid;
+        const bool live = row < rows;
+        const int node = live ? (int)(row % nodes) : 0;
+        const long long b = live ? row / nodes : 0;
+        {
+            const int k0 = ptr[node], k1 = ptr[node + 1];
+            float m[kH];
+#pragma unroll
+            for (int k = 0; k < kH; ++k) m[k] = 0.0f;
+            for (int q = k0; q < k1 && live; ++q) {
+                const int e = list ? list[q] : q;
+                const float4* xr = reinterpret_cast<const float4*>(x + ((size_t)b * E + e) * kH);
+                const float4* er = reinterpret_cast<const float4*>(emb_l + (size_t)edge_type[e] * kH);
+#pragma unroll
+                for (int c = 0; c < kH / 4; ++c) {
+                    const float4 a = xr[c], em = __ldg(er + c);
+                    m[c * 4] += a.x + em.x; m[c * 4 + 1] += a.y + em.y; m[c * 4 + 2] += a.z + em.z; m[c * 4 + 3] += a.w + em.w;
+                }
+            }
+            const float inv = 1.0f / (float)(k1 - k0);
+#pragma unroll
+            for (int c = 0; c < kH / 4; ++c)
+                put_chunk(Ahi, Alo, tid, c, 64, m[c * 4] * inv, m[c * 4 + 1] * inv, m[c * 4 + 2] * inv, m[c * 4 + 3] * inv);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            umma_gemm3(tmem, smem_u32(Ahi), smem_u32(Alo), smem_u32(Whi), smem_u32(Wlo), 64, 2048, 2048, kIdesc64, false);
+            umma_commit(&mbar);
+        }
+        ok = mbar_wait(&mbar, phase); phase ^= 1;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (ok) {
+            float4* pr = reinterpret_cast<float4*>(P + (size_t)(live ? row : 0) * kH);
+#pragma unroll
+            for (int c0 = 0; c0 < kH; c0 += 16) {
+                float o[16];
+                tmem_ld16(tmem + my_lane + c0, o);
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (live)
+                        pr[(c0 >> 2) + q] = make_float4(o[q * 4] + b1s[c0 + q * 4], o[q * 4 + 1] + b1s[c0 + q * 4 + 1],
+                                                        o[q * 4 + 2] + b1s[c0 + q * 4 + 2], o[q * 4 + 3] + b1s[c0 + q * 4 + 3]);
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    if (!ok) { if (tid == 0) atomicExch(status, 1); asm volatile("trap;"); }     // MMA completion never arrived: fail loudly
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" :: "r"(tmem) : "memory");
+}
+
+}  // namespace ldpc

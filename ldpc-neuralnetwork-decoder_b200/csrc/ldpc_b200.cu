@@ -9,6 +9,8 @@
 #include "layers.cuh"
 #include "gnn.cuh"
 #include "gnn_bwd.cuh"
+#include "gnn_tc.cuh"
+#include <cstdlib>
 
 #include <cstring>
 #include <new>
@@ -429,7 +431,9 @@ int ldpc_gnn_create(const ldpc_code_t* code, int num_layers, int hidden, int num
     bool ok = up(&g->d_edge_var, ev) && up(&g->d_edge_chk, ec) && up(&g->d_edge_type, et) && up(&g->d_var_ptr, vptr) &&
               up(&g->d_var_edge, vedge) && up(&g->d_chk_ptr, cptr) &&
               cudaMalloc(&g->d_packed, sizeof(float) * (size_t)num_layers * kPackedPerLayer) == cudaSuccess &&
-              cudaMalloc(&g->d_emb, sizeof(float) * (size_t)num_layers * num_types * kH) == cudaSuccess;
+              cudaMalloc(&g->d_emb, sizeof(float) * (size_t)num_layers * num_types * kH) == cudaSuccess &&
+              cudaMalloc(&g->d_tc, sizeof(float) * (size_t)num_layers * kTcPerLayer) == cudaSuccess &&
+              cudaMalloc(&g->d_status, sizeof(int)) == cudaSuccess && cudaMemset(g->d_status, 0, sizeof(int)) == cudaSuccess;
     if (!ok) { ldpc_gnn_destroy(g); return fail(LDPC_ERR_CUDA, "gnn_create: device allocation failed: %s", cudaGetErrorString(cudaGetLastError())); }
     *out = g;
     return LDPC_OK;
@@ -440,7 +444,7 @@ int ldpc_gnn_destroy(ldpc_gnn_t* g) {
     {
         DeviceGuard dg(g->device);
         cudaFree(g->d_edge_var); cudaFree(g->d_edge_chk); cudaFree(g->d_edge_type); cudaFree(g->d_var_ptr);
-        cudaFree(g->d_var_edge); cudaFree(g->d_chk_ptr); cudaFree(g->d_packed); cudaFree(g->d_emb);
+        cudaFree(g->d_var_edge); cudaFree(g->d_chk_ptr); cudaFree(g->d_packed); cudaFree(g->d_emb); cudaFree(g->d_tc); cudaFree(g->d_status);
     }
     delete g;
     return LDPC_OK;
@@ -498,6 +502,19 @@ int ldpc_gnn_forward(const ldpc_gnn_t* g, const float* params, const float* llr,
     const size_t edge_smem = sizeof(float) * kEdgeSmemFloats;
     LDPC_CUDA(cudaFuncSetAttribute(gnn_edge_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge_smem));
     LDPC_CUDA(cudaFuncSetAttribute(gnn_edge_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge_smem));
+    // tensor-core path (tcgen05, 3xTF32) unless LDPC_GNN_FFMA=1 asks for the fp32 FFMA kernels
+    static const bool use_tc = !(getenv("LDPC_GNN_FFMA") && getenv("LDPC_GNN_FFMA")[0] == '1');
+    if (use_tc) {
+        gnn_pack_tc_kernel<<<dim3(16, g->layers), 256, 0, st>>>(g->d_packed, g->d_tc);
+        LDPC_CHECK_LAUNCH("gnn_pack_tc_kernel");
+        LDPC_CUDA(cudaFuncSetAttribute(gnn_edge_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEdgeTcSmem));
+        LDPC_CUDA(cudaFuncSetAttribute(gnn_edge_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEdgeTcSmem));
+        LDPC_CUDA(cudaFuncSetAttribute(gnn_node_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNodeTcSmem));
+    }
+    auto tc_grid = [](long long rows, int per_sm) {
+        const long long tiles = (rows + 127) / 128, cap = (long long)kNumSMs * per_sm;
+        return (int)(tiles < cap ? tiles : cap);
+    };
     const int E = g->E, N = g->N, M = g->M;
     const GnnTrainWs tw = training ? gnn_train_layout(g, B) : GnnTrainWs{};
     const int64_t chunk_max = training ? B : (int64_t)(ws_bytes / per_cw);
@@ -514,6 +531,22 @@ int ldpc_gnn_forward(const ldpc_gnn_t* g, const float* params, const float* llr,
         for (int l = 0; l < g->layers; ++l) {
             const float* pk = g->d_packed + (size_t)l * kPackedPerLayer;
             const float* em = g->d_emb + (size_t)l * g->types * kH;
+            if (use_tc) {
+                const float* tcw = g->d_tc + (size_t)l * kTcPerLayer;
+                gnn_node_tc_kernel<<<tc_grid(bc * N, 2), kTcThreads, kNodeTcSmem, st>>>(
+                    xa, em, pk, tcw, 0, g->d_var_ptr, g->d_var_edge, g->d_edge_type, bc, E, N, pv, g->d_status);
+                LDPC_CHECK_LAUNCH("gnn_node_tc_kernel(var)");
+                gnn_node_tc_kernel<<<tc_grid(bc * M, 2), kTcThreads, kNodeTcSmem, st>>>(
+                    xa, em, pk, tcw, 1, g->d_chk_ptr, nullptr, g->d_edge_type, bc, E, M, pc, g->d_status);
+                LDPC_CHECK_LAUNCH("gnn_node_tc_kernel(chk)");
+                if (l == 0)
+                    gnn_edge_tc_kernel<false><<<tc_grid(bc * E, 1), kTcThreads, kEdgeTcSmem, st>>>(
+                        xa, em, pk, tcw, g->d_edge_var, g->d_edge_chk, g->d_edge_type, pv, pc, bc, E, N, M, xb, g->d_status);
+                else
+                    gnn_edge_tc_kernel<true><<<tc_grid(bc * E, 1), kTcThreads, kEdgeTcSmem, st>>>(
+                        xa, em, pk, tcw, g->d_edge_var, g->d_edge_chk, g->d_edge_type, pv, pc, bc, E, N, M, xb, g->d_status);
+                LDPC_CHECK_LAUNCH("gnn_edge_tc_kernel");
+            } else {
             gnn_node_kernel<<<gnn_grid(bc * N, kGnnThreads), kGnnThreads, 0, st>>>(
                 xa, em, pk, 0, g->d_var_ptr, g->d_var_edge, g->d_edge_type, bc, E, N, pv);
             LDPC_CHECK_LAUNCH("gnn_node_kernel(var)");
@@ -527,6 +560,7 @@ int ldpc_gnn_forward(const ldpc_gnn_t* g, const float* params, const float* llr,
                 gnn_edge_kernel<true><<<gnn_grid(bc * E, kGnnThreads), kGnnThreads, edge_smem, st>>>(
                     xa, em, pk, g->d_edge_var, g->d_edge_chk, g->d_edge_type, pv, pc, bc, E, N, M, xb);
             LDPC_CHECK_LAUNCH("gnn_edge_kernel");
+            }
             if (training) { xa = xb; xb = xa + tw.xs; pv += tw.pvs; pc += tw.pcs; }
             else { float* tmp = xa; xa = xb; xb = tmp; }
         }

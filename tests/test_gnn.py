@@ -136,8 +136,8 @@ def test_training_step_gradients_match_reference_autograd(name, Z):
         scale = max(np.abs(ref).max(), 1e-8)
         err = np.abs(got - ref).max() / scale
         worst = max(worst, err)
-        # fp32 accumulation over B*E rows in a different order than torch: 2e-4 of the tensor's scale
-        assert err <= 2e-4, (n, err)
+        # fp32 accumulation over B*E rows in a different order than torch, 3xTF32 forward: 5e-4 of the tensor scale
+        assert err <= 5e-4, (n, err)
         if not bool(g["hasgrad." + n]):
             assert not got.any(), n
     # an SGD step with the reference's hyper-parameters runs (trainer.py:70)

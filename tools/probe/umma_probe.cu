@@ -1,0 +1,149 @@
+// Standalone probe: D[128 x N] = A[128 x K] . B[N x K]^T with tcgen05.mma kind::tf32 (SS operands,
+// no swizzle, K-major canonical layout), optional 3xTF32 split, checked against a CPU fp64 reference.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstdint>
+#include <cmath>
+#include <vector>
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// canonical no-swizzle K-major layout: element (r, k) of a [R x K] fp32 operand
+//   byte offset = (r/8)*SBO + (k/4)*128 + (r%8)*16 + (k%4)*4,  SBO = (K/4)*128
+__device__ __forceinline__ uint32_t canon_off(int r, int k, int K) { return (r >> 3) * (K / 4) * 128 + (k >> 2) * 128 + (r & 7) * 16 + (k & 3) * 4; }
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;          // version = 1 (Blackwell)
+    return d;                          // layout_type = 0 (no swizzle), base_offset = 0
+}
+
+__device__ __forceinline__ float to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+template <int N, int K, bool kSplit3>
+__global__ void __launch_bounds__(128) probe(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D, int* status) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* Ahi = smem;                       // 128 x K
+    uint8_t* Alo = Ahi + 128 * K * 4;
+    uint8_t* Bhi = Alo + 128 * K * 4;          // N x K
+    uint8_t* Blo = Bhi + N * K * 4;
+    __shared__ uint64_t mbar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"(N < 32 ? 32 : N) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&mbar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // stage operands: thread r owns row r of A (and row r of B if r < N)
+    for (int k = 0; k < K; ++k) {
+        const float a = A[tid * K + k];
+        const float ah = to_tf32(a), al = to_tf32(a - ah);
+        *reinterpret_cast<float*>(Ahi + canon_off(tid, k, K)) = ah;
+        *reinterpret_cast<float*>(Alo + canon_off(tid, k, K)) = al;
+        if (tid < N) {
+            const float b = B[tid * K + k];
+            const float bh = to_tf32(b), bl = to_tf32(b - bh);
+            *reinterpret_cast<float*>(Bhi + canon_off(tid, k, K)) = bh;
+            *reinterpret_cast<float*>(Blo + canon_off(tid, k, K)) = bl;
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the tensor core
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base_s;
+    // instruction descriptor: D=F32 (1<<4), A=TF32 (2<<7), B=TF32 (2<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    if (tid == 0) {
+        const uint32_t sbo = (K / 4) * 128, lbo = 128;
+        int first = 1;
+        for (int ks = 0; ks < K / 8; ++ks) {
+            const uint32_t koff = ks * 2 * 128;          // two 16-byte chunks per k-step
+            const uint64_t ah = make_desc(smem_u32(Ahi) + koff, lbo, sbo), al = make_desc(smem_u32(Alo) + koff, lbo, sbo);
+            const uint64_t bh = make_desc(smem_u32(Bhi) + koff, lbo, sbo), bl = make_desc(smem_u32(Blo) + koff, lbo, sbo);
+            auto mma = [&](uint64_t da, uint64_t db) {
+                const uint32_t acc = first ? 0u : 1u;
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                             "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                             :: "r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+                first = 0;
+            };
+            if (kSplit3) { mma(al, bh); mma(ah, bl); }
+            mma(ah, bh);
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&mbar)) : "memory");
+    }
+    // wait for the MMAs (bounded spin: never hang the GPU)
+    {
+        uint32_t done = 0;
+        long long spins = 0;
+        while (!done) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(smem_u32(&mbar)), "r"(0u) : "memory");
+            if (++spins > 20000000LL) { if (tid == 0) *status = 1; break; }
+        }
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // epilogue: thread i of warp w reads TMEM lane 32w+i, all N columns
+    for (int c0 = 0; c0 < N; c0 += 8) {
+        uint32_t v[8];
+        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + c0;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]));
+        for (int j = 0; j < 8; ++j) D[tid * N + c0 + j] = __uint_as_float(v[j]);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(N < 32 ? 32 : N) : "memory");
+}
+
+template <int N, int K, bool S>
+int run(const char* name) {
+    std::vector<float> A(128 * K), B(N * K), D(128 * N);
+    srand(1);
+    for (auto& x : A) x = (rand() / (float)RAND_MAX - 0.5f) * 4.f;
+    for (auto& x : B) x = (rand() / (float)RAND_MAX - 0.5f) * 2.f;
+    float *dA, *dB, *dD; int* dS;
+    cudaMalloc(&dA, A.size() * 4); cudaMalloc(&dB, B.size() * 4); cudaMalloc(&dD, D.size() * 4); cudaMalloc(&dS, 4);
+    cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice); cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemset(dS, 0, 4); cudaMemset(dD, 0, D.size() * 4);
+    const size_t smem = (size_t)(128 + N) * K * 4 * 2;
+    cudaFuncSetAttribute(probe<N, K, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    probe<N, K, S><<<1, 128, smem>>>(dA, dB, dD, dS);
+    cudaError_t e = cudaDeviceSynchronize();
+    int st = 0;
+    cudaMemcpy(&st, dS, 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost);
+    double maxerr = 0, maxref = 0;
+    for (int m = 0; m < 128; ++m)
+        for (int n = 0; n < N; ++n) {
+            double r = 0;
+            for (int k = 0; k < K; ++k) r += (double)A[m * K + k] * B[n * K + k];
+            maxerr = fmax(maxerr, fabs(r - D[m * N + n]));
+            maxref = fmax(maxref, fabs(r));
+        }
+    printf("%s N=%d K=%d split3=%d: cuda=%s timeout=%d max_abs_err=%.3e (max |ref| %.2f) rel=%.2e\n", name, N, K, (int)S,
+           cudaGetErrorString(e), st, maxerr, maxref, maxerr / maxref);
+    return e != cudaSuccess;
+}
+
+int main() {
+    if (run<128, 64, false>("gemm1")) return 1;
+    if (run<128, 64, true>("gemm1")) return 1;
+    if (run<64, 128, true>("gemm2")) return 1;
+    if (run<64, 64, true>("node")) return 1;
+    return 0;
+}
