@@ -50,16 +50,17 @@ __device__ __forceinline__ void umma_commit(uint64_t* mbar) {
 }
 // 3xTF32 product over K (multiple of 8): D (+)= (Ahi+Alo) . (Bhi+Blo)^T without the lo.lo term
 __device__ __forceinline__ void umma_gemm3(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
-                                            int K, uint32_t sbo_a, uint32_t sbo_b, uint32_t idesc, bool accumulate) {
+                                            int K, uint32_t lbo_a, uint32_t sbo_a, uint32_t sbo_b, uint32_t idesc, bool accumulate) {
     uint32_t acc = accumulate ? 1u : 0u;
     for (int ks = 0; ks < K / 8; ++ks) {
-        const uint32_t ko = (uint32_t)ks * 256u;                              // two 16-byte k-chunks per MMA
-        umma_tf32(d_tmem, umma_desc(a_lo + ko, 128, sbo_a), umma_desc(b_hi + ko, 128, sbo_b), idesc, acc);
-        umma_tf32(d_tmem, umma_desc(a_hi + ko, 128, sbo_a), umma_desc(b_lo + ko, 128, sbo_b), idesc, 1u);
-        umma_tf32(d_tmem, umma_desc(a_hi + ko, 128, sbo_a), umma_desc(b_hi + ko, 128, sbo_b), idesc, 1u);
+        const uint32_t ka = (uint32_t)ks * 2u * lbo_a, kb = (uint32_t)ks * 256u;  // two 16-byte k-chunks per MMA
+        umma_tf32(d_tmem, umma_desc(a_lo + ka, lbo_a, sbo_a), umma_desc(b_hi + kb, 128, sbo_b), idesc, acc);
+        umma_tf32(d_tmem, umma_desc(a_hi + ka, lbo_a, sbo_a), umma_desc(b_lo + kb, 128, sbo_b), idesc, 1u);
+        umma_tf32(d_tmem, umma_desc(a_hi + ka, lbo_a, sbo_a), umma_desc(b_hi + kb, 128, sbo_b), idesc, 1u);
         acc = 1u;
     }
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 // bounded wait (never hang the GPU): returns false on timeout
 __device__ __forceinline__ bool mbar_wait(uint64_t* mbar, uint32_t parity) {
     uint32_t done = 0;
@@ -87,11 +88,27 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
-// write 4 consecutive k elements (one 16-byte chunk c) of row r, split hi/lo, into a canonical [R x K] pair
+// Activation tiles ([128 x 64], written by the CUDA cores).  Tuning knobs, measured on B200 at B = 2048
+// (forward, 5 layers): thread-per-row loads + LBO 128 + no prefetch 57.5 ms (default); + prefetch.global.L2 of the
+// node terms 64.0 ms; padded layout LBO 144 (legal: any multiple of 16 B) 67.6 ms; cooperative coalesced loads with
+// LBO 144 58.5 ms.  The kernel is latency-bound (ncu: 62 % long_scoreboard with 4 warps per SM); the fix is a
+// warp-specialised, double-buffered pipeline, not a different staging pattern.
+#ifndef GNN_TC_LBO
+#define GNN_TC_LBO 128
+#endif
+#ifndef GNN_TC_COOP
+#define GNN_TC_COOP 0
+#endif
+#ifndef GNN_TC_PREFETCH
+#define GNN_TC_PREFETCH 0
+#endif
+constexpr uint32_t kALbo = GNN_TC_LBO, kASbo = 16 * kALbo, kATileBytes = 16 * kASbo;      // 36 864 B per image at LBO 144
+// write 4 consecutive k elements (one 16-byte chunk c) of row r, split hi/lo, into an activation tile pair
 __device__ __forceinline__ void put_chunk(uint8_t* hi, uint8_t* lo, int r, int c, int K, float a, float b, float cc, float d) {
+    (void)K;
     const float4 h = make_float4(tf32_hi(a), tf32_hi(b), tf32_hi(cc), tf32_hi(d));
     const float4 l = make_float4(tf32_hi(a - h.x), tf32_hi(b - h.y), tf32_hi(cc - h.z), tf32_hi(d - h.w));
-    const uint32_t off = (uint32_t)((r >> 3) * (K / 4) * 128 + c * 128 + (r & 7) * 16);
+    const uint32_t off = (uint32_t)((r >> 3) * kASbo + c * kALbo + (r & 7) * 16);
     *reinterpret_cast<float4*>(hi + off) = h;
     *reinterpret_cast<float4*>(lo + off) = l;
 }
@@ -120,7 +137,7 @@ __global__ void gnn_pack_tc_kernel(const float* __restrict__ packed, float* __re
 }
 
 constexpr int kTcThreads = 128;
-constexpr size_t kEdgeTcSmem = (size_t)(2 * 128 * 64 + 2 * 64 * 128 + 2 * 128 * 64) * sizeof(float);   // 192 KB
+constexpr size_t kEdgeTcSmem = (size_t)(2 * 128 * 64 + 2 * 64 * 128) * sizeof(float) + 2 * kATileBytes;   // 128 KB weights + 72 KB activations
 
 template <bool kResidual>
 __global__ void __launch_bounds__(kTcThreads, 1) gnn_edge_tc_kernel(
@@ -134,7 +151,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gnn_edge_tc_kernel(
     uint8_t* W2hi = W1Alo + 128 * 64 * 4;                   // [64 x 128]
     uint8_t* W2lo = W2hi + 64 * 128 * 4;
     uint8_t* Ahi = W2lo + 64 * 128 * 4;                     // [128 x 64]: comb, then each half of relu(h)
-    uint8_t* Alo = Ahi + 128 * 64 * 4;
+    uint8_t* Alo = Ahi + kATileBytes;
     __shared__ uint64_t mbar;
     __shared__ uint32_t tmem_base_s;
     __shared__ float b2s[kH];
@@ -169,7 +186,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) gnn_edge_tc_kernel(
         const bool live = row < rows;
         const int e = live ? (int)(row % E) : 0;
         const long long b = live ? row / E : 0;
-        // 1. comb -> A (hi/lo)
+        // prefetch what this thread's row needs later in this tile (its two node terms) and the next tile's x row
+        if (live && GNN_TC_PREFETCH) {
+            const char* pv = reinterpret_cast<const char*>(Pv + ((size_t)b * N + edge_var[e]) * kH);
+            const char* pc = reinterpret_cast<const char*>(Pc + ((size_t)b * M + edge_chk[e]) * kH);
+            prefetch_l2(pv); prefetch_l2(pv + 128); prefetch_l2(pc); prefetch_l2(pc + 128);
+            const long long nrow = row + (long long)gridDim.x * 128;
+            if (nrow < rows) { prefetch_l2(x + (size_t)nrow * kH); prefetch_l2(x + (size_t)nrow * kH + 32); }
+        }
+        // 1. comb -> A (hi/lo): 16 consecutive threads read the 16 chunks of one row (coalesced 256-byte rows)
+#if !GNN_TC_COOP
         {
             const float4* xr = reinterpret_cast<const float4*>(x + (size_t)(live ? row : 0) * kH);
             const float4* er = reinterpret_cast<const float4*>(emb_l + (size_t)edge_type[e] * kH);
@@ -179,13 +205,34 @@ __global__ void __launch_bounds__(kTcThreads, 1) gnn_edge_tc_kernel(
                 put_chunk(Ahi, Alo, tid, c, 64, v.x + em.x, v.y + em.y, v.z + em.z, v.w + em.w);
             }
         }
+#else
+        {
+            const int e_tile = (int)((tile * 128) % E);          // message index of the tile's first row
+            const int c = tid & 15;
+            float4 v[16];
+#pragma unroll
+            for (int it = 0; it < 16; ++it) {                    // all 16 loads in flight
+                const int rr = it * 8 + (tid >> 4);
+                v[it] = (tile * 128 + rr < rows) ? reinterpret_cast<const float4*>(x + (size_t)(tile * 128 + rr) * kH)[c]
+                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int it = 0; it < 16; ++it) {
+                const int rr = it * 8 + (tid >> 4);
+                int ee = e_tile + rr;
+                ee -= ee >= E ? E : 0;
+                const float4 em = __ldg(reinterpret_cast<const float4*>(emb_l + (size_t)edge_type[ee] * kH) + c);
+                put_chunk(Ahi, Alo, rr, c, 64, v[it].x + em.x, v[it].y + em.y, v[it].z + em.z, v[it].w + em.w);
+            }
+        }
+#endif
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
         // 2. GEMM1: D1 = comb . W1A^T
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            umma_gemm3(d1, smem_u32(Ahi), smem_u32(Alo), smem_u32(W1Ahi), smem_u32(W1Alo), 64, 2048, 2048, kIdesc128, false);
+            umma_gemm3(d1, smem_u32(Ahi), smem_u32(Alo), smem_u32(W1Ahi), smem_u32(W1Alo), 64, kALbo, kASbo, 2048, kIdesc128, false);
             umma_commit(&mbar);
         }
         ok = mbar_wait(&mbar, phase); phase ^= 1;
@@ -213,7 +260,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gnn_edge_tc_kernel(
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 // W2 is [64 x 128] (SBO 4096); this half uses k in [64*half, 64*half+64): 16 chunks = 2048 bytes in
                 umma_gemm3(d2, smem_u32(Ahi), smem_u32(Alo), smem_u32(W2hi) + half * 2048, smem_u32(W2lo) + half * 2048, 64,
-                           2048, 4096, kIdesc64, half != 0);
+                           kALbo, kASbo, 4096, kIdesc64, half != 0);
                 umma_commit(&mbar);
             }
             ok = mbar_wait(&mbar, phase); phase ^= 1;
@@ -250,7 +297,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gnn_edge_tc_kernel(
 }
 
 // ---- node kernel on tensor cores: P[b][node][:] = W1B . mean_{e in node}(x + emb) + b1 ----------------
-constexpr size_t kNodeTcSmem = (size_t)(2 * 64 * 64 + 2 * 128 * 64) * sizeof(float);   // 96 KB -> 2 CTAs per SM
+constexpr size_t kNodeTcSmem = (size_t)(2 * 64 * 64) * sizeof(float) + 2 * kATileBytes;   // 32 KB weights + 72 KB means -> 2 CTAs per SM
 
 __global__ void __launch_bounds__(kTcThreads, 2) gnn_node_tc_kernel(
     const float* __restrict__ x, const float* __restrict__ emb_l, const float* __restrict__ packed_l, const float* __restrict__ tc_l,
@@ -260,7 +307,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) gnn_node_tc_kernel(
     uint8_t* Whi = tc_smem;                                    // W1B [64 x 64]
     uint8_t* Wlo = Whi + 64 * 64 * 4;
     uint8_t* Ahi = Wlo + 64 * 64 * 4;                       // means [128 x 64]
-    uint8_t* Alo = Ahi + 128 * 64 * 4;
+    uint8_t* Alo = Ahi + kATileBytes;
     __shared__ uint64_t mbar;
     __shared__ uint32_t tmem_base_s;
     __shared__ float b1s[kH];
@@ -319,7 +366,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) gnn_node_tc_kernel(
         __syncthreads();
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            umma_gemm3(tmem, smem_u32(Ahi), smem_u32(Alo), smem_u32(Whi), smem_u32(Wlo), 64, 2048, 2048, kIdesc64, false);
+            umma_gemm3(tmem, smem_u32(Ahi), smem_u32(Alo), smem_u32(Whi), smem_u32(Wlo), 64, kALbo, kASbo, 2048, kIdesc64, false);
             umma_commit(&mbar);
         }
         ok = mbar_wait(&mbar, phase); phase ^= 1;

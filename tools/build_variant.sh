@@ -6,7 +6,12 @@ N=$1; shift
 P=ldpc-neuralnetwork-decoder_b200
 F="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo --expt-relaxed-constexpr -Xcompiler -fPIC"
 mkdir -p build_variants/obj
-nvcc $F "$@" -c -o build_variants/obj/fast_$N.o $P/csrc/fast_kernels.cu
-[ -f $P/build/ldpc_b200.o ] || nvcc $F -c -o $P/build/ldpc_b200.o $P/csrc/ldpc_b200.cu
-nvcc -shared -o build_variants/libldpc_b200_$N.so $P/build/ldpc_b200.o build_variants/obj/fast_$N.o
+if [ "${TU:-fast}" = "main" ]; then
+  nvcc $F "$@" -c -o build_variants/obj/main_$N.o $P/csrc/ldpc_b200.cu
+  nvcc -shared -o build_variants/libldpc_b200_$N.so build_variants/obj/main_$N.o $P/build/fast_kernels.o
+else
+  nvcc $F "$@" -c -o build_variants/obj/fast_$N.o $P/csrc/fast_kernels.cu
+  [ -f $P/build/ldpc_b200.o ] || nvcc $F -c -o $P/build/ldpc_b200.o $P/csrc/ldpc_b200.cu
+  nvcc -shared -o build_variants/libldpc_b200_$N.so $P/build/ldpc_b200.o build_variants/obj/fast_$N.o
+fi
 echo built $N

@@ -4,6 +4,9 @@ import argparse, json, os, sys, time
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ldpc_b200
+if os.environ.get("LDPC_LIB"):
+    from ldpc_b200 import _native as _n
+    _n.LIB_PATH = os.environ["LDPC_LIB"]
 from ldpc_b200 import _native
 from ldpc_b200.models import create_message_gnn_decoder
 from ldpc_b200.utils import QCCode
