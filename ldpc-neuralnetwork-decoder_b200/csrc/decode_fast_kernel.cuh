@@ -104,6 +104,16 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, float4 v) {
                  :: "r"(taddr), "r"(f2u(v.x)), "r"(f2u(v.y)), "r"(f2u(v.z)), "r"(f2u(v.w)) : "memory");
 }
 
+// Four channel LLRs (all-zero codeword) of one Philox block.  Out of line on purpose: inlined 13 times the
+// generator is ~80 KB of SASS in front of the iteration body and evicts it from the instruction cache once per
+// codeword (the fused simulation ran at half the decode-only rate).
+__device__ __noinline__ float4 gen_llr4(const GenParams g, unsigned long long frame, uint32_t blk) {
+    float z[4];
+    normal4(g.seed, frame, blk, z);
+    return make_float4(llr_from_noise(z[0], 1.0f, g), llr_from_noise(z[1], 1.0f, g), llr_from_noise(z[2], 1.0f, g),
+                       llr_from_noise(z[3], 1.0f, g));
+}
+
 template <class BG>
 constexpr size_t fast_smem_bytes(int warps) {
     return (size_t)warps * ((LDPC_FAST_TMEM ? 0 : (BG::kCoreEdges + 3) / 4) + (BG::kCoreCols + 3) / 4) * 32 * sizeof(float4);
@@ -181,12 +191,11 @@ __global__ void __launch_bounds__(kWarps * 32, 1) decode_fast_kernel(const Decod
                 static_for<0, P>([&](auto mc) {
                     constexpr int hi = decltype(hc)::value, jm = decltype(mc)::value;
                     if constexpr (hi * 4 * P + jm < BG::kCols) {
-                        float z[4];
-                        normal4(p.gen.seed, frame, (uint32_t)(hi * 32 + jm * Z + r), z);
+                        const float4 q = gen_llr4(p.gen, frame, (uint32_t)(hi * 32 + jm * Z + r));
+                        const float z[4] = {q.x, q.y, q.z, q.w};
                         static_for<0, 4>([&](auto cc) {
                             constexpr int j = (hi * 4 + decltype(cc)::value) * P + jm;
-                            if constexpr (j < BG::kCols)
-                                put_llr(IC<j>{}, live ? llr_from_noise(z[decltype(cc)::value], 1.0f, p.gen) : 0.0f);
+                            if constexpr (j < BG::kCols) put_llr(IC<j>{}, live ? z[decltype(cc)::value] : 0.0f);
                         });
                     }
                 });
