@@ -136,26 +136,47 @@ __global__ void gnn_pack_tc_kernel(const float* __restrict__ packed, float* __re
     }
 }
 
-constexpr int kTcThreads = 128;
-constexpr size_t kEdgeTcSmem = (size_t)(2 * 128 * 64 + 2 * 64 * 128) * sizeof(float) + 2 * kATileBytes;   // 128 KB weights + 72 KB activations
+constexpr int kTcThreads = 128;        // node kernel: one thread per row
+#ifndef GNN_TC_PARTS
+#define GNN_TC_PARTS 4                 // edge kernel: threads per message row (each owns 1/PARTS of the columns)
+#endif
+constexpr int kEdgeParts = GNN_TC_PARTS, kEdgeThreads = 128 * kEdgeParts;
+// 128 KB weight images + 64 KB activation tile (hi/lo) + 32 KB staging tile
+constexpr size_t kEdgeTcSmem = (size_t)(2 * 128 * 64 + 2 * 64 * 128) * sizeof(float) + 2 * kATileBytes + 128 * 64 * sizeof(float);
 
+// Staging tile S[128 rows][16 chunks of 16 B], chunk position XOR-swizzled by the row so that BOTH access
+// patterns are bank-conflict free: the cooperative one (16 consecutive threads move the 16 chunks of one row =
+// one coalesced 256-byte global access) and the per-row one (thread r reads/writes chunk c of its own row).
+__device__ __forceinline__ float4* stage_ptr(uint8_t* S, int r, int c) {
+    return reinterpret_cast<float4*>(S + r * 256 + ((c ^ (r & 15)) << 4));
+}
+
+// kEdgeParts threads serve one message row for the per-row work (warp w, w+4, ... share TMEM lane quarter w%4 and
+// split the columns).  Every global access of the kernel is a cooperative, fully coalesced 256-byte row transfer
+// through S (ncu on the first version: L1 throughput was the busiest unit because per-row 16-byte accesses touch
+// 32 different lines per request).
 template <bool kResidual>
-__global__ void __launch_bounds__(kTcThreads, 1) gnn_edge_tc_kernel(
+__global__ void __launch_bounds__(kEdgeThreads, 1) gnn_edge_tc_kernel(
     const float* __restrict__ x, const float* __restrict__ emb_l, const float* __restrict__ packed_l, const float* __restrict__ tc_l,
     const int* __restrict__ edge_var, const int* __restrict__ edge_chk, const int* __restrict__ edge_type,
     const float* __restrict__ Pv, const float* __restrict__ Pc, long long B, int E, int N, int M, float* __restrict__ y,
     int* __restrict__ status) {
     extern __shared__ __align__(1024) uint8_t tc_smem[];
-    uint8_t* W1Ahi = tc_smem;                                  // [128 x 64]
+    uint8_t* W1Ahi = tc_smem;                               // [128 x 64]
     uint8_t* W1Alo = W1Ahi + 128 * 64 * 4;
     uint8_t* W2hi = W1Alo + 128 * 64 * 4;                   // [64 x 128]
     uint8_t* W2lo = W2hi + 64 * 128 * 4;
     uint8_t* Ahi = W2lo + 64 * 128 * 4;                     // [128 x 64]: comb, then each half of relu(h)
     uint8_t* Alo = Ahi + kATileBytes;
+    uint8_t* S = Alo + kATileBytes;                         // staging tile
     __shared__ uint64_t mbar;
     __shared__ uint32_t tmem_base_s;
     __shared__ float b2s[kH];
+    __shared__ int row_node[2][128];                        // variable / check node of each row of the tile
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int rowi = tid & 127, part = tid >> 7;            // per-row work: row of the tile, column part
+    constexpr int kColsPerPart = kH / kEdgeParts;
+    constexpr int kCoopIters = 128 * 16 / kEdgeThreads;     // cooperative work: (row, chunk) pairs per thread
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" :: "r"(smem_u32(&tmem_base_s)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -167,7 +188,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gnn_edge_tc_kernel(
     {   // weights: the canonical hi/lo images are contiguous in global memory in the same order as in shared memory
         const float4* src = reinterpret_cast<const float4*>(tc_l + kTcW1A);
         float4* dst = reinterpret_cast<float4*>(tc_smem);
-        for (int t = tid; t < (2 * 128 * 64 + 2 * 64 * 128) / 4; t += kTcThreads) dst[t] = src[t];
+        for (int t = tid; t < (2 * 128 * 64 + 2 * 64 * 128) / 4; t += kEdgeThreads) dst[t] = src[t];
         if (tid < kH) b2s[tid] = packed_l[kPkB2 + tid];
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -176,80 +197,86 @@ __global__ void __launch_bounds__(kTcThreads, 1) gnn_edge_tc_kernel(
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_base_s;
     const uint32_t d1 = tmem, d2 = tmem + 128;                                  // accumulators: columns [0,128) and [128,192)
-    const uint32_t my_lane = ((uint32_t)(warp * 32)) << 16;
+    const uint32_t my_lane = ((uint32_t)((warp & 3) * 32)) << 16;
     constexpr uint32_t kIdesc128 = umma_idesc_tf32(128), kIdesc64 = umma_idesc_tf32(64);
     uint32_t phase = 0;
     bool ok = true;
     const long long rows = B * E, tiles = (rows + 127) / 128;
+    const int cc = tid & 15, cr0 = tid >> 4;                 // cooperative mapping: chunk, first row
+    // software pipeline through registers: the x rows of the NEXT tile are requested while this tile computes
+    float4 xr[kCoopIters];
+    auto load_x = [&](long long t) {
+#pragma unroll
+        for (int it = 0; it < kCoopIters; ++it) {
+            const long long row = t * 128 + it * (kEdgeThreads / 16) + cr0;
+            xr[it] = (t < tiles && row < rows) ? reinterpret_cast<const float4*>(x + (size_t)row * kH)[cc] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    load_x(blockIdx.x);
     for (long long tile = blockIdx.x; tile < tiles && ok; tile += gridDim.x) {
-        const long long row = tile * 128 + tid;
-        const bool live = row < rows;
-        const int e = live ? (int)(row % E) : 0;
-        const long long b = live ? row / E : 0;
-        // prefetch what this thread's row needs later in this tile (its two node terms) and the next tile's x row
-        if (live && GNN_TC_PREFETCH) {
-            const char* pv = reinterpret_cast<const char*>(Pv + ((size_t)b * N + edge_var[e]) * kH);
-            const char* pc = reinterpret_cast<const char*>(Pc + ((size_t)b * M + edge_chk[e]) * kH);
-            prefetch_l2(pv); prefetch_l2(pv + 128); prefetch_l2(pc); prefetch_l2(pc + 128);
-            const long long nrow = row + (long long)gridDim.x * 128;
-            if (nrow < rows) { prefetch_l2(x + (size_t)nrow * kH); prefetch_l2(x + (size_t)nrow * kH + 32); }
+        const long long row0 = tile * 128;
+        const int e0 = (int)(row0 % E);                      // message index of the tile's first row
+        const long long b0 = row0 / E;
+        // 0. cooperative: comb = x + emb -> S;  node ids of the rows
+        if (tid < 128) {
+            int ee = e0 + tid; long long bb = b0;
+            if (ee >= E) { ee -= E; bb += 1; }
+            const bool lv = row0 + tid < rows;
+            row_node[0][tid] = lv ? (int)(bb * N) + edge_var[ee] : -1;            // row of Pv (codeword-major)
+            row_node[1][tid] = lv ? (int)(bb * M) + edge_chk[ee] : -1;
         }
-        // 1. comb -> A (hi/lo): 16 consecutive threads read the 16 chunks of one row (coalesced 256-byte rows)
-#if !GNN_TC_COOP
-        {
-            const float4* xr = reinterpret_cast<const float4*>(x + (size_t)(live ? row : 0) * kH);
-            const float4* er = reinterpret_cast<const float4*>(emb_l + (size_t)edge_type[e] * kH);
 #pragma unroll
-            for (int c = 0; c < kH / 4; ++c) {
-                const float4 v = live ? xr[c] : make_float4(0.f, 0.f, 0.f, 0.f), em = __ldg(er + c);
-                put_chunk(Ahi, Alo, tid, c, 64, v.x + em.x, v.y + em.y, v.z + em.z, v.w + em.w);
-            }
+        for (int it = 0; it < kCoopIters; ++it) {
+            const int rr = it * (kEdgeThreads / 16) + cr0;
+            int ee = e0 + rr; ee -= ee >= E ? E : 0;
+            const float4 em = __ldg(reinterpret_cast<const float4*>(emb_l + (size_t)edge_type[ee] * kH) + cc);
+            *stage_ptr(S, rr, cc) = make_float4(xr[it].x + em.x, xr[it].y + em.y, xr[it].z + em.z, xr[it].w + em.w);
         }
-#else
-        {
-            const int e_tile = (int)((tile * 128) % E);          // message index of the tile's first row
-            const int c = tid & 15;
-            float4 v[16];
+        __syncthreads();
+        // requests in flight behind the tensor-core work: both node-term row sets of this tile, x of the next tile
+        float4 pn[2][kCoopIters];
 #pragma unroll
-            for (int it = 0; it < 16; ++it) {                    // all 16 loads in flight
-                const int rr = it * 8 + (tid >> 4);
-                v[it] = (tile * 128 + rr < rows) ? reinterpret_cast<const float4*>(x + (size_t)(tile * 128 + rr) * kH)[c]
-                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+        for (int half = 0; half < 2; ++half)
 #pragma unroll
-            for (int it = 0; it < 16; ++it) {
-                const int rr = it * 8 + (tid >> 4);
-                int ee = e_tile + rr;
-                ee -= ee >= E ? E : 0;
-                const float4 em = __ldg(reinterpret_cast<const float4*>(emb_l + (size_t)edge_type[ee] * kH) + c);
-                put_chunk(Ahi, Alo, rr, c, 64, v[it].x + em.x, v[it].y + em.y, v[it].z + em.z, v[it].w + em.w);
+            for (int it = 0; it < kCoopIters; ++it) {
+                const int nd = row_node[half][it * (kEdgeThreads / 16) + cr0];
+                pn[half][it] = nd >= 0 ? reinterpret_cast<const float4*>((half == 0 ? Pv : Pc) + (size_t)nd * kH)[cc] : make_float4(0.f, 0.f, 0.f, 0.f);
             }
+        load_x(tile + gridDim.x);
+        // 1. per row: S -> A (split hi/lo)
+#pragma unroll
+        for (int c = 0; c < kColsPerPart / 4; ++c) {
+            const int ch = part * (kColsPerPart / 4) + c;
+            const float4 v = *stage_ptr(S, rowi, ch);
+            put_chunk(Ahi, Alo, rowi, ch, 64, v.x, v.y, v.z, v.w);
         }
-#endif
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
-        // 2. GEMM1: D1 = comb . W1A^T
+        // 2. GEMM1: D1 = comb . W1A^T;  meanwhile stage the variable-node terms of the tile in S (cooperative gather)
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             umma_gemm3(d1, smem_u32(Ahi), smem_u32(Alo), smem_u32(W1Ahi), smem_u32(W1Alo), 64, kALbo, kASbo, 2048, kIdesc128, false);
             umma_commit(&mbar);
         }
-        ok = mbar_wait(&mbar, phase); phase ^= 1;
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // 3./4. two halves of the hidden layer
-#pragma unroll 1
-        for (int half = 0; half < 2 && ok; ++half) {
-            const float4* pp = half == 0 ? reinterpret_cast<const float4*>(Pv + ((size_t)b * N + edge_var[e]) * kH)
-                                         : reinterpret_cast<const float4*>(Pc + ((size_t)b * M + edge_chk[e]) * kH);
 #pragma unroll
-            for (int c0 = 0; c0 < kH; c0 += 16) {
+        for (int half = 0; half < 2; ++half) {
+            if (!ok) break;
+#pragma unroll
+            for (int it = 0; it < kCoopIters; ++it) *stage_ptr(S, it * (kEdgeThreads / 16) + cr0, cc) = pn[half][it];
+            __syncthreads();
+            ok = mbar_wait(&mbar, phase); phase ^= 1;        // GEMM1 (half 0) or GEMM2a (half 1) complete
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (!ok) break;
+#pragma unroll
+            for (int c0 = 0; c0 < kColsPerPart; c0 += 16) {
+                const int col = part * kColsPerPart + c0;
                 float h[16];
-                tmem_ld16(d1 + my_lane + half * kH + c0, h);
+                tmem_ld16(d1 + my_lane + half * kH + col, h);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const float4 pq = live ? pp[(c0 >> 2) + q] : make_float4(0.f, 0.f, 0.f, 0.f);
-                    put_chunk(Ahi, Alo, tid, (c0 >> 2) + q, 64, fmaxf(h[q * 4] + pq.x, 0.f), fmaxf(h[q * 4 + 1] + pq.y, 0.f),
+                    const float4 pq = *stage_ptr(S, rowi, (col >> 2) + q);
+                    put_chunk(Ahi, Alo, rowi, (col >> 2) + q, 64, fmaxf(h[q * 4] + pq.x, 0.f), fmaxf(h[q * 4 + 1] + pq.y, 0.f),
                               fmaxf(h[q * 4 + 2] + pq.z, 0.f), fmaxf(h[q * 4 + 3] + pq.w, 0.f));
                 }
             }
@@ -263,32 +290,40 @@ __global__ void __launch_bounds__(kTcThreads, 1) gnn_edge_tc_kernel(
                            kALbo, kASbo, 4096, kIdesc64, half != 0);
                 umma_commit(&mbar);
             }
-            ok = mbar_wait(&mbar, phase); phase ^= 1;
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
-        // 5. y = D2 + b2 (+ x)
+        if (ok) { ok = mbar_wait(&mbar, phase); phase ^= 1; }   // GEMM2b complete
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // 5. per row: y = D2 + b2 -> S;  cooperative: (+ x) -> global
         if (ok) {
-            const float4* xr = reinterpret_cast<const float4*>(x + (size_t)(live ? row : 0) * kH);
-            float4* yr = reinterpret_cast<float4*>(y + (size_t)(live ? row : 0) * kH);
 #pragma unroll
-            for (int c0 = 0; c0 < kH; c0 += 16) {
+            for (int c0 = 0; c0 < kColsPerPart; c0 += 16) {
+                const int col = part * kColsPerPart + c0;
                 float o[16];
-                tmem_ld16(d2 + my_lane + c0, o);
+                tmem_ld16(d2 + my_lane + col, o);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    float4 r = make_float4(o[q * 4] + b2s[c0 + q * 4], o[q * 4 + 1] + b2s[c0 + q * 4 + 1],
-                                           o[q * 4 + 2] + b2s[c0 + q * 4 + 2], o[q * 4 + 3] + b2s[c0 + q * 4 + 3]);
+                for (int q = 0; q < 4; ++q)
+                    *stage_ptr(S, rowi, (col >> 2) + q) = make_float4(o[q * 4] + b2s[col + q * 4], o[q * 4 + 1] + b2s[col + q * 4 + 1],
+                                                                      o[q * 4 + 2] + b2s[col + q * 4 + 2], o[q * 4 + 3] + b2s[col + q * 4 + 3]);
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();                                      // also: every thread is done reading TMEM before the next tile's MMAs
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (ok) {
+#pragma unroll
+            for (int it = 0; it < kCoopIters; ++it) {
+                const int rr = it * (kEdgeThreads / 16) + cr0;
+                if (row0 + rr < rows) {
+                    float4 r = *stage_ptr(S, rr, cc);
                     if constexpr (kResidual) {
-                        if (live) { const float4 v = xr[(c0 >> 2) + q]; r.x += v.x; r.y += v.y; r.z += v.z; r.w += v.w; }
+                        const float4 v = reinterpret_cast<const float4*>(x + (size_t)(row0 + rr) * kH)[cc];
+                        r.x += v.x; r.y += v.y; r.z += v.z; r.w += v.w;
                     }
-                    if (live) yr[(c0 >> 2) + q] = r;
+                    reinterpret_cast<float4*>(y + (size_t)(row0 + rr) * kH)[cc] = r;
                 }
             }
         }
-        // the next tile overwrites the A region and D1/D2: every thread must be done reading TMEM first
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        __syncthreads();                                      // S and row_node are rewritten by the next tile
     }
     if (!ok) { if (tid == 0) atomicExch(status, 1); asm volatile("trap;"); }     // MMA completion never arrived: fail loudly
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -297,21 +332,28 @@ __global__ void __launch_bounds__(kTcThreads, 1) gnn_edge_tc_kernel(
 }
 
 // ---- node kernel on tensor cores: P[b][node][:] = W1B . mean_{e in node}(x + emb) + b1 ----------------
-constexpr size_t kNodeTcSmem = (size_t)(2 * 64 * 64) * sizeof(float) + 2 * kATileBytes;   // 32 KB weights + 72 KB means -> 2 CTAs per SM
+// 512 threads per 128-node tile.  Cooperative phases (16 threads per node, one 16-byte chunk each) do all the
+// global traffic as coalesced 256-byte rows: gather-and-average the node's message rows, and store the P rows;
+// per-row phases (4 threads per node) split hi/lo into the operand tile and read the accumulator.
+constexpr int kNodeParts = 4;
+constexpr int kNodeThreads = 128 * kNodeParts;
+constexpr size_t kNodeTcSmem = (size_t)(2 * 64 * 64) * sizeof(float) + 2 * kATileBytes + 128 * 64 * sizeof(float);   // 32 + 64 + 32 KB
 
-__global__ void __launch_bounds__(kTcThreads, 2) gnn_node_tc_kernel(
+__global__ void __launch_bounds__(kNodeThreads, 1) gnn_node_tc_kernel(
     const float* __restrict__ x, const float* __restrict__ emb_l, const float* __restrict__ packed_l, const float* __restrict__ tc_l,
     int kind, const int* __restrict__ ptr, const int* __restrict__ list, const int* __restrict__ edge_type, long long B, int E,
     int nodes, float* __restrict__ P, int* __restrict__ status) {
     extern __shared__ __align__(1024) uint8_t tc_smem[];
-    uint8_t* Whi = tc_smem;                                    // W1B [64 x 64]
+    uint8_t* Whi = tc_smem;                                 // W1B [64 x 64]
     uint8_t* Wlo = Whi + 64 * 64 * 4;
     uint8_t* Ahi = Wlo + 64 * 64 * 4;                       // means [128 x 64]
     uint8_t* Alo = Ahi + kATileBytes;
+    uint8_t* S = Alo + kATileBytes;
     __shared__ uint64_t mbar;
     __shared__ uint32_t tmem_base_s;
     __shared__ float b1s[kH];
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int rowi = tid & 127, part = tid >> 7;
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" :: "r"(smem_u32(&tmem_base_s)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -323,7 +365,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) gnn_node_tc_kernel(
     {
         const float4* src = reinterpret_cast<const float4*>(tc_l + (kind == 0 ? kTcW1BV : kTcW1BC));
         float4* dst = reinterpret_cast<float4*>(tc_smem);
-        for (int t = tid; t < 2 * 64 * 64 / 4; t += kTcThreads) dst[t] = src[t];
+        for (int t = tid; t < 2 * 64 * 64 / 4; t += kNodeThreads) dst[t] = src[t];
         if (tid < kH) b1s[tid] = packed_l[(kind == 0 ? kPkB1V : kPkB1C) + tid];
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -331,35 +373,56 @@ __global__ void __launch_bounds__(kTcThreads, 2) gnn_node_tc_kernel(
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_base_s;
-    const uint32_t my_lane = ((uint32_t)(warp * 32)) << 16;
+    const uint32_t my_lane = ((uint32_t)((warp & 3) * 32)) << 16;
     constexpr uint32_t kIdesc64 = umma_idesc_tf32(64);
     uint32_t phase = 0;
     bool ok = true;
     const long long rows = B * nodes, tiles = (rows + 127) / 128;
+    const int cc = tid & 15, cr0 = tid >> 4;                 // cooperative mapping: chunk, first node of the pass
     for (long long tile = blockIdx.x; tile < tiles && ok; tile += gridDim.x) {
-        const long long row = tile * 128 + tid;
-        const bool live = row < rows;
-        const int node = live ? (int)(row % nodes) : 0;
-        const long long b = live ? row / nodes : 0;
-        {
-            const int k0 = ptr[node], k1 = ptr[node + 1];
-            float m[kH];
+        const long long row0 = tile * 128;
+        // 0. cooperative: mean over the node's messages of (x + emb), chunk cc -> S
+#pragma unroll 1
+        for (int it = 0; it < 128 * 16 / kNodeThreads; ++it) {
+            const int rr = it * (kNodeThreads / 16) + cr0;
+            const long long row = row0 + rr;
+            float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row < rows) {
+                const int node = (int)(row % nodes);
+                const long long b = row / nodes;
+                const int k0 = ptr[node], k1 = ptr[node + 1];
+                const float* xb = x + (size_t)b * E * kH;
+                int q = k0;
+                for (; q + 4 <= k1; q += 4) {                 // four message rows in flight per thread
+                    int e[4];
+                    float4 a[4], em[4];
 #pragma unroll
-            for (int k = 0; k < kH; ++k) m[k] = 0.0f;
-            for (int q = k0; q < k1 && live; ++q) {
-                const int e = list ? list[q] : q;
-                const float4* xr = reinterpret_cast<const float4*>(x + ((size_t)b * E + e) * kH);
-                const float4* er = reinterpret_cast<const float4*>(emb_l + (size_t)edge_type[e] * kH);
+                    for (int u = 0; u < 4; ++u) e[u] = list ? list[q + u] : q + u;
 #pragma unroll
-                for (int c = 0; c < kH / 4; ++c) {
-                    const float4 a = xr[c], em = __ldg(er + c);
-                    m[c * 4] += a.x + em.x; m[c * 4 + 1] += a.y + em.y; m[c * 4 + 2] += a.z + em.z; m[c * 4 + 3] += a.w + em.w;
+                    for (int u = 0; u < 4; ++u) {
+                        a[u] = reinterpret_cast<const float4*>(xb + (size_t)e[u] * kH)[cc];
+                        em[u] = __ldg(reinterpret_cast<const float4*>(emb_l + (size_t)edge_type[e[u]] * kH) + cc);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) { m.x += a[u].x + em[u].x; m.y += a[u].y + em[u].y; m.z += a[u].z + em[u].z; m.w += a[u].w + em[u].w; }
                 }
+                for (; q < k1; ++q) {
+                    const int e = list ? list[q] : q;
+                    const float4 a = reinterpret_cast<const float4*>(xb + (size_t)e * kH)[cc];
+                    const float4 em = __ldg(reinterpret_cast<const float4*>(emb_l + (size_t)edge_type[e] * kH) + cc);
+                    m.x += a.x + em.x; m.y += a.y + em.y; m.z += a.z + em.z; m.w += a.w + em.w;
+                }
+                const float inv = 1.0f / (float)(k1 - k0);
+                m.x *= inv; m.y *= inv; m.z *= inv; m.w *= inv;
             }
-            const float inv = 1.0f / (float)(k1 - k0);
+            *stage_ptr(S, rr, cc) = m;
+        }
+        __syncthreads();
+        // 1. per row: S -> A (split hi/lo)
 #pragma unroll
-            for (int c = 0; c < kH / 4; ++c)
-                put_chunk(Ahi, Alo, tid, c, 64, m[c * 4] * inv, m[c * 4 + 1] * inv, m[c * 4 + 2] * inv, m[c * 4 + 3] * inv);
+        for (int c = 0; c < 16 / kNodeParts; ++c) {
+            const float4 v = *stage_ptr(S, rowi, part * (16 / kNodeParts) + c);
+            put_chunk(Ahi, Alo, rowi, part * (16 / kNodeParts) + c, 64, v.x, v.y, v.z, v.w);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -371,22 +434,30 @@ __global__ void __launch_bounds__(kTcThreads, 2) gnn_node_tc_kernel(
         }
         ok = mbar_wait(&mbar, phase); phase ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // 2. per row: D + b1 -> S;  cooperative: S -> P (coalesced rows)
         if (ok) {
-            float4* pr = reinterpret_cast<float4*>(P + (size_t)(live ? row : 0) * kH);
 #pragma unroll
-            for (int c0 = 0; c0 < kH; c0 += 16) {
+            for (int c0 = 0; c0 < 64 / kNodeParts; c0 += 16) {
+                const int col = part * (64 / kNodeParts) + c0;
                 float o[16];
-                tmem_ld16(tmem + my_lane + c0, o);
+                tmem_ld16(tmem + my_lane + col, o);
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
-                    if (live)
-                        pr[(c0 >> 2) + q] = make_float4(o[q * 4] + b1s[c0 + q * 4], o[q * 4 + 1] + b1s[c0 + q * 4 + 1],
-                                                        o[q * 4 + 2] + b1s[c0 + q * 4 + 2], o[q * 4 + 3] + b1s[c0 + q * 4 + 3]);
+                    *stage_ptr(S, rowi, (col >> 2) + q) = make_float4(o[q * 4] + b1s[col + q * 4], o[q * 4 + 1] + b1s[col + q * 4 + 1],
+                                                                      o[q * 4 + 2] + b1s[col + q * 4 + 2], o[q * 4 + 3] + b1s[col + q * 4 + 3]);
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (ok) {
+#pragma unroll
+            for (int it = 0; it < 128 * 16 / kNodeThreads; ++it) {
+                const int rr = it * (kNodeThreads / 16) + cr0;
+                if (row0 + rr < rows) reinterpret_cast<float4*>(P + (size_t)(row0 + rr) * kH)[cc] = *stage_ptr(S, rr, cc);
+            }
+        }
+        __syncthreads();
     }
     if (!ok) { if (tid == 0) atomicExch(status, 1); asm volatile("trap;"); }     // MMA completion never arrived: fail loudly
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

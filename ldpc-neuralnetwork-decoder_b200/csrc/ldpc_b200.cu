@@ -533,17 +533,17 @@ int ldpc_gnn_forward(const ldpc_gnn_t* g, const float* params, const float* llr,
             const float* em = g->d_emb + (size_t)l * g->types * kH;
             if (use_tc) {
                 const float* tcw = g->d_tc + (size_t)l * kTcPerLayer;
-                gnn_node_tc_kernel<<<tc_grid(bc * N, 2), kTcThreads, kNodeTcSmem, st>>>(
+                gnn_node_tc_kernel<<<tc_grid(bc * N, 1), kNodeThreads, kNodeTcSmem, st>>>(
                     xa, em, pk, tcw, 0, g->d_var_ptr, g->d_var_edge, g->d_edge_type, bc, E, N, pv, g->d_status);
                 LDPC_CHECK_LAUNCH("gnn_node_tc_kernel(var)");
-                gnn_node_tc_kernel<<<tc_grid(bc * M, 2), kTcThreads, kNodeTcSmem, st>>>(
+                gnn_node_tc_kernel<<<tc_grid(bc * M, 1), kNodeThreads, kNodeTcSmem, st>>>(
                     xa, em, pk, tcw, 1, g->d_chk_ptr, nullptr, g->d_edge_type, bc, E, M, pc, g->d_status);
                 LDPC_CHECK_LAUNCH("gnn_node_tc_kernel(chk)");
                 if (l == 0)
-                    gnn_edge_tc_kernel<false><<<tc_grid(bc * E, 1), kTcThreads, kEdgeTcSmem, st>>>(
+                    gnn_edge_tc_kernel<false><<<tc_grid(bc * E, 1), kEdgeThreads, kEdgeTcSmem, st>>>(
                         xa, em, pk, tcw, g->d_edge_var, g->d_edge_chk, g->d_edge_type, pv, pc, bc, E, N, M, xb, g->d_status);
                 else
-                    gnn_edge_tc_kernel<true><<<tc_grid(bc * E, 1), kTcThreads, kEdgeTcSmem, st>>>(
+                    gnn_edge_tc_kernel<true><<<tc_grid(bc * E, 1), kEdgeThreads, kEdgeTcSmem, st>>>(
                         xa, em, pk, tcw, g->d_edge_var, g->d_edge_chk, g->d_edge_type, pv, pc, bc, E, N, M, xb, g->d_status);
                 LDPC_CHECK_LAUNCH("gnn_edge_tc_kernel");
             } else {

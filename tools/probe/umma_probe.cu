@@ -110,7 +110,96 @@ __global__ void __launch_bounds__(128) probe(const float* __restrict__ A, const 
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(N < 32 ? 32 : N) : "memory");
 }
 
-template <int N, int K, bool S>
+
+// TS variant: the A operand (hi and lo images) lives in Tensor Memory, written by tcgen05.st (thread i of warp w
+// owns lane 32w+i = row; element k of the row in column base + k), B from shared memory as above.
+template <int N, int K>
+__global__ void __launch_bounds__(128) probe_ts(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D, int* status) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* Bhi = smem;                       // N x K
+    uint8_t* Blo = Bhi + N * K * 4;
+    __shared__ uint64_t mbar;
+    __shared__ uint32_t tmem_base_s;
+    constexpr uint32_t kCols = (N + 2 * K) <= 256 ? 256 : 512;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"(kCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&mbar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < N)
+        for (int k = 0; k < K; ++k) {
+            const float b = B[tid * K + k];
+            const float bh = to_tf32(b), bl = to_tf32(b - bh);
+            *reinterpret_cast<float*>(Bhi + canon_off(tid, k, K)) = bh;
+            *reinterpret_cast<float*>(Blo + canon_off(tid, k, K)) = bl;
+        }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base_s;
+    const uint32_t a_hi = tmem + N, a_lo = tmem + N + K;      // columns [N, N+K) and [N+K, N+2K)
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    for (int k0 = 0; k0 < K; k0 += 4) {
+        uint32_t h[4], l[4];
+        for (int j = 0; j < 4; ++j) {
+            const float a = A[tid * K + k0 + j];
+            const float ah = to_tf32(a);
+            h[j] = __float_as_uint(ah); l[j] = __float_as_uint(to_tf32(a - ah));
+        }
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" :: "r"(a_hi + lane_base + k0), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" :: "r"(a_lo + lane_base + k0), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    if (tid == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sbo = (K / 4) * 128, lbo = 128;
+        int first = 1;
+        for (int ks = 0; ks < K / 8; ++ks) {
+            const uint32_t koff = ks * 2 * 128;
+            const uint64_t bh = make_desc(smem_u32(Bhi) + koff, lbo, sbo), bl = make_desc(smem_u32(Blo) + koff, lbo, sbo);
+            auto mma = [&](uint32_t ta, uint64_t db) {
+                const uint32_t acc = first ? 0u : 1u;
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                             "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+                             :: "r"(tmem), "r"(ta), "l"(db), "r"(idesc), "r"(acc) : "memory");
+                first = 0;
+            };
+            mma(a_lo + ks * 8, bh); mma(a_hi + ks * 8, bl); mma(a_hi + ks * 8, bh);
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&mbar)) : "memory");
+    }
+    {
+        uint32_t done = 0;
+        long long spins = 0;
+        while (!done) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(smem_u32(&mbar)), "r"(0u) : "memory");
+            if (++spins > 20000000LL) { if (tid == 0) *status = 1; break; }
+        }
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    for (int c0 = 0; c0 < N; c0 += 8) {
+        uint32_t v[8];
+        const uint32_t taddr = tmem + lane_base + c0;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]));
+        for (int j = 0; j < 8; ++j) D[tid * N + c0 + j] = __uint_as_float(v[j]);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(kCols) : "memory");
+}
+
+template <int N, int K, bool S, bool TS = false>
 int run(const char* name) {
     std::vector<float> A(128 * K), B(N * K), D(128 * N);
     srand(1);
@@ -121,8 +210,13 @@ int run(const char* name) {
     cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice); cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice);
     cudaMemset(dS, 0, 4); cudaMemset(dD, 0, D.size() * 4);
     const size_t smem = (size_t)(128 + N) * K * 4 * 2;
-    cudaFuncSetAttribute(probe<N, K, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    probe<N, K, S><<<1, 128, smem>>>(dA, dB, dD, dS);
+    if (TS) {
+        cudaFuncSetAttribute(probe_ts<N, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        probe_ts<N, K><<<1, 128, smem>>>(dA, dB, dD, dS);
+    } else {
+        cudaFuncSetAttribute(probe<N, K, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        probe<N, K, S><<<1, 128, smem>>>(dA, dB, dD, dS);
+    }
     cudaError_t e = cudaDeviceSynchronize();
     int st = 0;
     cudaMemcpy(&st, dS, 4, cudaMemcpyDeviceToHost);
@@ -145,5 +239,7 @@ int main() {
     if (run<128, 64, true>("gemm1")) return 1;
     if (run<64, 128, true>("gemm2")) return 1;
     if (run<64, 64, true>("node")) return 1;
+    if (run<128, 64, true, true>("gemm1-ts")) return 1;
+    if (run<64, 128, true, true>("gemm2-ts")) return 1;
     return 0;
 }
