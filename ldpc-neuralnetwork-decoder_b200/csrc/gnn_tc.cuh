@@ -76,6 +76,7 @@ __device__ __forceinline__ float tf32_hi(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
+__device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     uint32_t r[16];
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -106,8 +107,9 @@ constexpr uint32_t kALbo = GNN_TC_LBO, kASbo = 16 * kALbo, kATileBytes = 16 * kA
 // write 4 consecutive k elements (one 16-byte chunk c) of row r, split hi/lo, into an activation tile pair
 __device__ __forceinline__ void put_chunk(uint8_t* hi, uint8_t* lo, int r, int c, int K, float a, float b, float cc, float d) {
     (void)K;
-    const float4 h = make_float4(tf32_hi(a), tf32_hi(b), tf32_hi(cc), tf32_hi(d));
-    const float4 l = make_float4(tf32_hi(a - h.x), tf32_hi(b - h.y), tf32_hi(cc - h.z), tf32_hi(d - h.w));
+    // activations: hi by truncation (1 LOP3 instead of the 4-instruction cvt.rna expansion), lo = exact remainder
+    const float4 h = make_float4(tf32_trunc(a), tf32_trunc(b), tf32_trunc(cc), tf32_trunc(d));
+    const float4 l = make_float4(a - h.x, b - h.y, cc - h.z, d - h.w);
     const uint32_t off = (uint32_t)((r >> 3) * kASbo + c * kALbo + (r & 7) * 16);
     *reinterpret_cast<float4*>(hi + off) = h;
     *reinterpret_cast<float4*>(lo + off) = l;
@@ -147,8 +149,12 @@ constexpr size_t kEdgeTcSmem = (size_t)(2 * 128 * 64 + 2 * 64 * 128) * sizeof(fl
 // Staging tile S[128 rows][16 chunks of 16 B], chunk position XOR-swizzled by the row so that BOTH access
 // patterns are bank-conflict free: the cooperative one (16 consecutive threads move the 16 chunks of one row =
 // one coalesced 256-byte global access) and the per-row one (thread r reads/writes chunk c of its own row).
+// 16-byte shared accesses are served per quarter warp (8 lanes -> the 8 bank groups of 16 B), so the swizzle must
+// separate: 8 consecutive rows at one chunk (per-row readers), 8 consecutive chunks of one row (16-lane row movers)
+// and 2 consecutive rows x 4 consecutive chunks (the 4-lane row movers of gnn_tc_pipe.cuh).  XOR with the row's low
+// three bits rotated by one does all three.
 __device__ __forceinline__ float4* stage_ptr(uint8_t* S, int r, int c) {
-    return reinterpret_cast<float4*>(S + r * 256 + ((c ^ (r & 15)) << 4));
+    return reinterpret_cast<float4*>(S + r * 256 + ((c ^ (((r & 1) << 2) | ((r >> 1) & 3))) << 4));
 }
 
 // kEdgeParts threads serve one message row for the per-row work (warp w, w+4, ... share TMEM lane quarter w%4 and

@@ -10,6 +10,7 @@
 #include "gnn.cuh"
 #include "gnn_bwd.cuh"
 #include "gnn_tc.cuh"
+#include "gnn_tc_pipe.cuh"
 #include <cstdlib>
 
 #include <cstring>
@@ -504,12 +505,16 @@ int ldpc_gnn_forward(const ldpc_gnn_t* g, const float* params, const float* llr,
     LDPC_CUDA(cudaFuncSetAttribute(gnn_edge_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge_smem));
     // tensor-core path (tcgen05, 3xTF32) unless LDPC_GNN_FFMA=1 asks for the fp32 FFMA kernels
     static const bool use_tc = !(getenv("LDPC_GNN_FFMA") && getenv("LDPC_GNN_FFMA")[0] == '1');
+    // LDPC_GNN_EDGE=serial selects the single-buffered edge kernel (gnn_tc.cuh) instead of the pipelined one (diagnostics)
+    static const bool use_pipe = !(getenv("LDPC_GNN_EDGE") && getenv("LDPC_GNN_EDGE")[0] == 's');
     if (use_tc) {
         gnn_pack_tc_kernel<<<dim3(16, g->layers), 256, 0, st>>>(g->d_packed, g->d_tc);
         LDPC_CHECK_LAUNCH("gnn_pack_tc_kernel");
         LDPC_CUDA(cudaFuncSetAttribute(gnn_edge_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEdgeTcSmem));
         LDPC_CUDA(cudaFuncSetAttribute(gnn_edge_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEdgeTcSmem));
         LDPC_CUDA(cudaFuncSetAttribute(gnn_node_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNodeTcSmem));
+        LDPC_CUDA(cudaFuncSetAttribute(gnn_edge_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmem));
+        LDPC_CUDA(cudaFuncSetAttribute(gnn_edge_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmem));
     }
     auto tc_grid = [](long long rows, int per_sm) {
         const long long tiles = (rows + 127) / 128, cap = (long long)kNumSMs * per_sm;
@@ -539,7 +544,13 @@ int ldpc_gnn_forward(const ldpc_gnn_t* g, const float* params, const float* llr,
                 gnn_node_tc_kernel<<<tc_grid(bc * M, 1), kNodeThreads, kNodeTcSmem, st>>>(
                     xa, em, pk, tcw, 1, g->d_chk_ptr, nullptr, g->d_edge_type, bc, E, M, pc, g->d_status);
                 LDPC_CHECK_LAUNCH("gnn_node_tc_kernel(chk)");
-                if (l == 0)
+                if (use_pipe && l == 0)
+                    gnn_edge_pipe_kernel<false><<<tc_grid(bc * E, 1), kPipeThreads, kPipeSmem, st>>>(
+                        xa, em, pk, tcw, g->d_edge_var, g->d_edge_chk, g->d_edge_type, pv, pc, bc, E, N, M, xb, g->d_status);
+                else if (use_pipe)
+                    gnn_edge_pipe_kernel<true><<<tc_grid(bc * E, 1), kPipeThreads, kPipeSmem, st>>>(
+                        xa, em, pk, tcw, g->d_edge_var, g->d_edge_chk, g->d_edge_type, pv, pc, bc, E, N, M, xb, g->d_status);
+                else if (l == 0)
                     gnn_edge_tc_kernel<false><<<tc_grid(bc * E, 1), kEdgeThreads, kEdgeTcSmem, st>>>(
                         xa, em, pk, tcw, g->d_edge_var, g->d_edge_chk, g->d_edge_type, pv, pc, bc, E, N, M, xb, g->d_status);
                 else
