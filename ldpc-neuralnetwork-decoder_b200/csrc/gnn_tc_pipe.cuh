@@ -18,18 +18,28 @@
 //
 // Tensor Memory map (512 columns): [0,64) comb hi | [64,128) comb lo | [128,256) D1 (D2 reuses [128,192)) |
 //                                  [256,384) h hi | [384,512) h lo.
+// (Measured alternative: h hi written in place over D1 with D2 in its own columns, so that GEMM1(t+1) can be queued
+// right behind GEMM2(t): 2-3 ms SLOWER per forward at B = 2048 -- the accumulator drain, the in-place operand and the
+// MMAs then compete for the same Tensor Memory columns.)
 // Shared memory: 128 KB weights + 3 staging tiles of 32 KB: Sx (comb), Sp0 (variable-node rows, then y), Sp1 (check-node rows).
 //
 // Schedule per CTA (t = tile index of this CTA):
-//   row warps:  E1(t)  C(t+1)  E2(t)  ST(t)          MMA thread:  G2(t)  G1(t+1)
+//   row warps:  E1(t)  C(t+1)  E2(t)  ST(t)          MMA thread:  G2(t) first half | second half   G1(t+1)
 // so the tensor pipe runs G2(t) while the row warps convert tile t+1, and G1(t+1) while they store tile t.
+// (Also measured: starting G2(t) on the first half of the hidden columns while E1(t) produces the rest, which needs
+// the D2-in-own-columns map above: 35.4 ms.)
 // All hand-offs are mbarriers (one phase per tile); every wait is bounded and traps instead of hanging the GPU.
 #pragma once
 #include "gnn_tc.cuh"
 
 namespace ldpc {
 
-constexpr int kPipeRowWarps = 8, kPipeLoaderWarps = 8;
+#ifndef GNN_PIPE_PARTS
+#define GNN_PIPE_PARTS 2                // row warps per TMEM lane quarter (each owns 1/PARTS of the columns)
+#endif
+constexpr int kPipeParts = GNN_PIPE_PARTS;
+constexpr int kPipeRowWarps = 4 * kPipeParts, kPipeLoaderWarps = 8;
+constexpr int kPipeCw = 64 / kPipeParts, kPipeHw = 128 / kPipeParts;       // comb / output and hidden columns per row thread
 constexpr int kPipeMmaWarp = kPipeRowWarps;                                    // warp 8
 constexpr int kPipeThreads = (kPipeRowWarps + 1 + kPipeLoaderWarps) * 32;      // 544
 constexpr int kPipeRowThreads = kPipeRowWarps * 32, kPipeLoaderThreads = kPipeLoaderWarps * 32;
@@ -37,7 +47,7 @@ constexpr size_t kPipeStage = 128 * 64 * sizeof(float);                        /
 constexpr size_t kPipeSmem = (size_t)(2 * 128 * 64 + 2 * 64 * 128) * sizeof(float) + 3 * kPipeStage;   // 224 KB
 constexpr uint32_t kTmAcHi = 0, kTmAcLo = 64, kTmD1 = 128, kTmD2 = 128, kTmHHi = 256, kTmHLo = 384;
 
-enum PipeBar { kBarFullX = 0, kBarFreeX, kBarAReady, kBarD1Full, kBarFullP, kBarFreeP1, kBarHReady, kBarD2Full, kBarFreeP0,
+enum PipeBar { kBarFullX = 0, kBarFreeX, kBarAReady, kBarD1Full, kBarFullP, kBarFreeP, kBarHReady, kBarD2Full, kBarFreeY,
                kBarD2Drained, kNumPipeBars };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* mbar) {
@@ -47,6 +57,21 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
     asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
                  :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
                     "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+// split tcgen05.ld: issue now, wait later (tcgen05.wait::ld covers every outstanding load of the thread); the "+r"
+// ties keep the compiler from touching the destination registers before the wait
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&a)[16], uint32_t (&b)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]), "+r"(a[8]),
+                   "+r"(a[9]), "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15]));
+    asm volatile("" : "+r"(b[0]), "+r"(b[1]), "+r"(b[2]), "+r"(b[3]), "+r"(b[4]), "+r"(b[5]), "+r"(b[6]), "+r"(b[7]), "+r"(b[8]),
+                      "+r"(b[9]), "+r"(b[10]), "+r"(b[11]), "+r"(b[12]), "+r"(b[13]), "+r"(b[14]), "+r"(b[15]));
 }
 // A operand in Tensor Memory (lane = row, column = k), B operand in shared memory
 __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t db, uint32_t idesc, uint32_t accumulate) {
@@ -76,6 +101,19 @@ __device__ __forceinline__ void split16(const float (&v)[16], uint32_t (&hi)[16]
     }
 }
 
+#ifdef GNN_PIPE_TRACE
+#define PIPE_TRACE_DECL long long tr[12][8]; int trn = 0; const bool tracer = blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == kPipeMmaWarp || warp == kPipeMmaWarp + 1);
+#define PIPE_TRACE(ev) do { if (tracer && trn >= 2 && trn < 14) tr[trn - 2][ev] = clock64(); } while (0)
+#define PIPE_TRACE_NEXT() do { ++trn; } while (0)
+#define PIPE_TRACE_DUMP(role, nev) do { if (tracer) for (int i = 0; i < 12 && i + 2 < trn; ++i) { printf("%s tile %d:", role, i + 2); \
+    for (int e = 0; e < nev; ++e) printf(" %lld", tr[i][e] % 100000000LL); printf("\n"); } } while (0)
+#else
+#define PIPE_TRACE_DECL
+#define PIPE_TRACE(ev)
+#define PIPE_TRACE_NEXT()
+#define PIPE_TRACE_DUMP(role, nev)
+#endif
+
 template <bool kResidual>
 __global__ void __launch_bounds__(kPipeThreads, 1) gnn_edge_pipe_kernel(
     const float* __restrict__ x, const float* __restrict__ emb_l, const float* __restrict__ packed_l, const float* __restrict__ tc_l,
@@ -101,8 +139,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1) gnn_edge_pipe_kernel(
     if (tid == 0) {
         auto init = [&](int b, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&bars[b])), "r"(count) : "memory"); };
         init(kBarFullX, kPipeLoaderWarps); init(kBarFreeX, kPipeRowWarps); init(kBarAReady, kPipeRowWarps); init(kBarD1Full, 1);
-        init(kBarFullP, kPipeLoaderWarps); init(kBarFreeP1, kPipeRowWarps); init(kBarHReady, kPipeRowWarps); init(kBarD2Full, 1);
-        init(kBarFreeP0, kPipeRowWarps); init(kBarD2Drained, kPipeRowWarps);
+        init(kBarFullP, kPipeLoaderThreads); init(kBarFreeP, kPipeRowWarps); init(kBarHReady, kPipeRowWarps); init(kBarD2Full, 1);
+        init(kBarFreeY, kPipeRowWarps); init(kBarD2Drained, kPipeRowWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     {   // weights: canonical hi/lo images, contiguous in global memory in the same order as in shared memory
@@ -119,20 +157,21 @@ __global__ void __launch_bounds__(kPipeThreads, 1) gnn_edge_pipe_kernel(
     const long long rows = B * E, tiles = (rows + 127) / 128;
     const long long my_tiles = blockIdx.x < tiles ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     bool ok = true;
+    PIPE_TRACE_DECL
     auto wait = [&](int b, uint32_t parity) { if (ok) ok = mbar_wait(&bars[b], parity & 1u); };
     // one elected lane arrives for the warp once every lane has finished the work the barrier publishes
     auto warp_arrive = [&](int b) { __syncwarp(); if (lane == 0) mbar_arrive(&bars[b]); };
 
     if (warp < kPipeRowWarps) {
         // ================= row warps: thread <-> message row of the tile =================
-        const int rowi = tid & 127, part = tid >> 7;                         // part 0: variable-node half, part 1: check-node half
+        const int rowi = tid & 127, part = tid >> 7;                         // column part of this thread
         const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
         const int cc = tid & 15, cr0 = tid >> 4;                             // cooperative mapping of the y store
         const float4 bias = *reinterpret_cast<const float4*>(b2s + cc * 4);  // b2 of the 4 output columns this thread stores
         auto convert = [&]() {                                               // C: Sx -> comb hi/lo in TMEM, my 32 columns
 #pragma unroll
-            for (int c0 = 0; c0 < 32; c0 += 16) {
-                const int col = part * 32 + c0;
+            for (int c0 = 0; c0 < kPipeCw; c0 += 16) {
+                const int col = part * kPipeCw + c0;
                 float v[16];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -155,70 +194,101 @@ __global__ void __launch_bounds__(kPipeThreads, 1) gnn_edge_pipe_kernel(
             // E1: h = relu(D1 + node term) -> hi/lo in TMEM (my 64 hidden columns)
             wait(kBarD1Full, (uint32_t)k); wait(kBarFullP, (uint32_t)k);
             if (!ok) break;
+            PIPE_TRACE(0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             {
-                uint8_t* Sp = part == 0 ? Sp0 : Sp1;
+                uint8_t* Sp = part * kPipeHw < 64 ? Sp0 : Sp1;              // hidden columns [0,64): variable-node term, [64,128): check-node term
 #pragma unroll
-                for (int c0 = 0; c0 < 64; c0 += 16) {
-                    const int col = part * 64 + c0;
-                    float h[16];
-                    tmem_ld16(tmem + lane_base + kTmD1 + col, h);
+                for (int c0 = 0; c0 < kPipeHw; c0 += 32) {                   // two accumulator loads in flight per wait
+                    const int col = part * kPipeHw + c0;
+                    const int pch = (col & 63) >> 2;                         // first chunk of these columns in the staged row
+                    uint32_t ha[16], hb[16];
+                    tmem_ld16_issue(tmem + lane_base + kTmD1 + col, ha);
+                    tmem_ld16_issue(tmem + lane_base + kTmD1 + col + 16, hb);
+                    float4 pa[4], pb[4];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float4 pq = *stage_ptr(Sp, rowi, (c0 >> 2) + q);
-                        h[q * 4] = fmaxf(h[q * 4] + pq.x, 0.f); h[q * 4 + 1] = fmaxf(h[q * 4 + 1] + pq.y, 0.f);
-                        h[q * 4 + 2] = fmaxf(h[q * 4 + 2] + pq.z, 0.f); h[q * 4 + 3] = fmaxf(h[q * 4 + 3] + pq.w, 0.f);
-                    }
-                    uint32_t hi[16], lo[16];
-                    split16(h, hi, lo);
-                    tmem_st16(tmem + lane_base + kTmHHi + col, hi);
-                    tmem_st16(tmem + lane_base + kTmHLo + col, lo);
+                    for (int q = 0; q < 4; ++q) { pa[q] = *stage_ptr(Sp, rowi, pch + q); pb[q] = *stage_ptr(Sp, rowi, pch + 4 + q); }
+                    tmem_ld_wait(ha, hb);
+                    auto finish = [&](uint32_t (&hh)[16], const float4 (&pp)[4], int cofs) {
+                        uint32_t lo[16];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float add[4] = {pp[q].x, pp[q].y, pp[q].z, pp[q].w};
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float v = fmaxf(__uint_as_float(hh[q * 4 + i]) + add[i], 0.f);
+                                hh[q * 4 + i] = __float_as_uint(v) & 0xffffe000u;
+                                lo[q * 4 + i] = __float_as_uint(v - __uint_as_float(hh[q * 4 + i]));
+                            }
+                        }
+                        tmem_st16(tmem + lane_base + kTmHHi + col + cofs, hh);
+                        tmem_st16(tmem + lane_base + kTmHLo + col + cofs, lo);
+                    };
+                    finish(ha, pa, 0);
+                    finish(hb, pb, 16);
                 }
             }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             warp_arrive(kBarHReady);
-            warp_arrive(kBarFreeP1);
+            warp_arrive(kBarFreeP);
+            PIPE_TRACE(1);
             // C(t+1) while the tensor pipe runs GEMM2(t)
-            if (k + 1 < my_tiles) { wait(kBarFullX, (uint32_t)(k + 1)); if (!ok) break; convert(); }
-            // E2: D2 -> Sp0 (b2 and the residual are added by the store) (the variable-node rows of this tile are consumed: GEMM2 needed every row warp's h)
+            if (k + 1 < my_tiles) { wait(kBarFullX, (uint32_t)(k + 1)); if (!ok) break; PIPE_TRACE(2); convert(); }
+            PIPE_TRACE(3);
+            // E2: D2 -> Sx, which C(t+1) has just consumed: each thread overwrites exactly the chunks it read (b2 and the
+            // residual are added by the store) (the variable-node rows of this tile are consumed: GEMM2 needed every row warp's h)
+            // residual rows requested now (L2 hits: the loaders read them one tile ago), consumed by the store below
+            constexpr int kStIters = 128 * 16 / kPipeRowThreads;
+            float4 xv[kStIters];
+            if constexpr (kResidual) {
+#pragma unroll
+                for (int it = 0; it < kStIters; ++it) {
+                    const long long row = row0 + it * (kPipeRowThreads / 16) + cr0;
+                    xv[it] = row < rows ? reinterpret_cast<const float4*>(x + (size_t)row * kH)[cc] : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
             wait(kBarD2Full, (uint32_t)k);
             if (!ok) break;
+            PIPE_TRACE(4);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            {
+                const int col = part * kPipeCw;
+                uint32_t oa[16], ob[16];
+                tmem_ld16_issue(tmem + lane_base + kTmD2 + col, oa);
+                if constexpr (kPipeCw == 32) tmem_ld16_issue(tmem + lane_base + kTmD2 + col + 16, ob);
+                else {
 #pragma unroll
-            for (int c0 = 0; c0 < 32; c0 += 16) {
-                const int col = part * 32 + c0;
-                float o[16];
-                tmem_ld16(tmem + lane_base + kTmD2 + col, o);
+                    for (int i = 0; i < 16; ++i) ob[i] = 0;
+                }
+                tmem_ld_wait(oa, ob);
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    *stage_ptr(Sp0, rowi, (col >> 2) + q) = make_float4(o[q * 4], o[q * 4 + 1], o[q * 4 + 2], o[q * 4 + 3]);
+                for (int q = 0; q < 4; ++q) {
+                    *stage_ptr(Sx, rowi, (col >> 2) + q) = make_float4(__uint_as_float(oa[q * 4]), __uint_as_float(oa[q * 4 + 1]),
+                                                                        __uint_as_float(oa[q * 4 + 2]), __uint_as_float(oa[q * 4 + 3]));
+                    if constexpr (kPipeCw == 32)
+                        *stage_ptr(Sx, rowi, (col >> 2) + 4 + q) = make_float4(__uint_as_float(ob[q * 4]), __uint_as_float(ob[q * 4 + 1]),
+                                                                                __uint_as_float(ob[q * 4 + 2]), __uint_as_float(ob[q * 4 + 3]));
+                }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            warp_arrive(kBarD2Drained);                                      // GEMM1(t+1) may overwrite the accumulator columns
+            warp_arrive(kBarD2Drained);
+            PIPE_TRACE(5);
             asm volatile("bar.sync 1, %0;" :: "n"(kPipeRowThreads) : "memory");
             // ST: coalesced rows (+ residual x)
-            {
-                constexpr int kIters = 128 * 16 / kPipeRowThreads;
-                float4 xv[kIters];
-                if constexpr (kResidual) {
 #pragma unroll
-                    for (int it = 0; it < kIters; ++it) {
-                        const long long row = row0 + it * (kPipeRowThreads / 16) + cr0;
-                        xv[it] = row < rows ? reinterpret_cast<const float4*>(x + (size_t)row * kH)[cc] : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                }
-#pragma unroll
-                for (int it = 0; it < kIters; ++it) {
-                    const int rr = it * (kPipeRowThreads / 16) + cr0;
-                    float4 r = *stage_ptr(Sp0, rr, cc);
-                    r.x += bias.x; r.y += bias.y; r.z += bias.z; r.w += bias.w;
-                    if constexpr (kResidual) { r.x += xv[it].x; r.y += xv[it].y; r.z += xv[it].z; r.w += xv[it].w; }
-                    if (row0 + rr < rows) reinterpret_cast<float4*>(y + (size_t)(row0 + rr) * kH)[cc] = r;
-                }
+            for (int it = 0; it < kStIters; ++it) {
+                const int rr = it * (kPipeRowThreads / 16) + cr0;
+                float4 r = *stage_ptr(Sx, rr, cc);
+                r.x += bias.x; r.y += bias.y; r.z += bias.z; r.w += bias.w;
+                if constexpr (kResidual) { r.x += xv[it].x; r.y += xv[it].y; r.z += xv[it].z; r.w += xv[it].w; }
+                if (row0 + rr < rows) reinterpret_cast<float4*>(y + (size_t)(row0 + rr) * kH)[cc] = r;
             }
-            warp_arrive(kBarFreeP0);
+            warp_arrive(kBarFreeY);
+            PIPE_TRACE(6);
+            PIPE_TRACE_NEXT();
         }
+        PIPE_TRACE_DUMP("row", 7);
     } else if (warp == kPipeMmaWarp) {
         // ================= MMA issue (one thread) =================
         if (lane == 0) {
@@ -232,15 +302,22 @@ __global__ void __launch_bounds__(kPipeThreads, 1) gnn_edge_pipe_kernel(
             for (long long k = 0; k < my_tiles && ok; ++k) {
                 wait(kBarHReady, (uint32_t)k);
                 if (!ok) break;
+                PIPE_TRACE(0);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 umma_gemm3_ts(tmem + kTmD2, tmem + kTmHHi, tmem + kTmHLo, smem_u32(W2hi), smem_u32(W2lo), 128, 4096, kIdesc64);
                 umma_commit(&bars[kBarD2Full]);
+                PIPE_TRACE(1);
                 if (k + 1 < my_tiles) {
-                    wait(kBarAReady, (uint32_t)(k + 1)); wait(kBarD2Drained, (uint32_t)k);
+                    wait(kBarAReady, (uint32_t)(k + 1));
+                    wait(kBarD2Drained, (uint32_t)k);                     // D2(t) shares columns with D1
                     if (!ok) break;
+                    PIPE_TRACE(2);
                     gemm1();
+                    PIPE_TRACE(3);
                 }
+                PIPE_TRACE_NEXT();
             }
+            PIPE_TRACE_DUMP("mma", 4);
         }
     } else {
         // ================= loader warps: every global read, one tile ahead =================
@@ -256,41 +333,31 @@ __global__ void __launch_bounds__(kPipeThreads, 1) gnn_edge_pipe_kernel(
         const int stride_e = (int)(stride % E);
         struct Pos { long long b0; int e0; };                                 // (codeword, message) of a tile's first row
         auto advance = [&](Pos& p) { p.b0 += stride_b; p.e0 += stride_e; if (p.e0 >= E) { p.e0 -= E; ++p.b0; } };
-        float4 X[2][4], V[2][4];
-        int ty[2], vrow[2], crow[2], crow_next[2];                            // type, Pv row, Pc row (-1: past the end)
-        auto load_x = [&](long long k, const Pos& p) {                        // x rows + all indices of tile k
+        float4 X[2][4];
+        int ty[2], vrow[2], crow[2];                                          // message type; Pv / Pc row (-1: past the end)
+        int ev[2], ec[2], vb[2], cb[2];                                       // raw indices of the tile in flight
+        auto load_x = [&](long long k, const Pos& p) {                        // x rows + all indices of tile k (requests only)
             const long long row0 = (blockIdx.x + k * gridDim.x) * 128;
-            int ev[2], ec[2];
-            long long bb[2];
-            bool valid[2];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {                                     // every request first ...
+            for (int h = 0; h < 2; ++h) {
                 const int rr = lrow + 64 * h;
                 int e = p.e0 + rr;
                 long long b = p.b0;
                 while (e >= E) { e -= E; ++b; }
-                bb[h] = b;
-                valid[h] = row0 + rr < rows;
+                const bool valid = row0 + rr < rows;
                 const float4* src = reinterpret_cast<const float4*>(x + (size_t)(row0 + rr) * kH);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) X[h][j] = valid[h] ? src[4 * j + q4] : make_float4(0.f, 0.f, 0.f, 0.f);
-                ty[h] = valid[h] ? __ldg(edge_type + e) : 0;
-                ev[h] = valid[h] ? __ldg(edge_var + e) : 0;
-                ec[h] = valid[h] ? __ldg(edge_chk + e) : 0;
-            }
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {                                     // ... then the arithmetic that waits for them
-                vrow[h] = valid[h] ? (int)(bb[h] * N) + ev[h] : -1;
-                crow_next[h] = valid[h] ? (int)(bb[h] * M) + ec[h] : -1;
+                for (int j = 0; j < 4; ++j) X[h][j] = valid ? src[4 * j + q4] : make_float4(0.f, 0.f, 0.f, 0.f);
+                ty[h] = valid ? __ldg(edge_type + e) : 0;
+                ev[h] = valid ? __ldg(edge_var + e) : 0;
+                ec[h] = valid ? __ldg(edge_chk + e) : 0;
+                vb[h] = valid ? (int)(b * N) : -1;
+                cb[h] = valid ? (int)(b * M) : -1;
             }
         };
-        auto load_v = [&]() {                                                 // variable-node rows (indices from load_x)
+        auto take_indices = [&]() {                                           // first use of the index requests
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const float4* src = reinterpret_cast<const float4*>(Pv + (size_t)(vrow[h] < 0 ? 0 : vrow[h]) * kH);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) V[h][j] = vrow[h] >= 0 ? src[4 * j + q4] : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+            for (int h = 0; h < 2; ++h) { vrow[h] = vb[h] < 0 ? -1 : vb[h] + ev[h]; crow[h] = cb[h] < 0 ? -1 : cb[h] + ec[h]; }
         };
         auto publish_x = [&]() {                                              // comb = x + emb[type] -> Sx
 #pragma unroll
@@ -305,43 +372,41 @@ __global__ void __launch_bounds__(kPipeThreads, 1) gnn_edge_pipe_kernel(
             warp_arrive(kBarFullX);
         };
         Pos pos{((long long)blockIdx.x * 128) / E, (int)(((long long)blockIdx.x * 128) % E)};
-        if (my_tiles > 0) {
-            load_x(0, pos); load_v(); publish_x();
-            crow[0] = crow_next[0]; crow[1] = crow_next[1];
-        }
+        if (my_tiles > 0) { load_x(0, pos); take_indices(); publish_x(); }
         for (long long k = 0; k < my_tiles && ok; ++k) {
             const bool more = k + 1 < my_tiles;
             advance(pos);
             if (more) load_x(k + 1, pos);                                     // in flight during everything below
-            // check-node rows of tile k: asynchronous copies straight into Sp1 once E1(k-1) has released it
-            wait(kBarFreeP1, (uint32_t)k + 1u);
+            // node rows of tile k: asynchronous copies straight into Sp0 / Sp1 once E1(k-1) has released them; the
+            // copies signal the row warps themselves (cp.async.mbarrier.arrive), the loader does not wait for them
+            wait(kBarFreeP, (uint32_t)k + 1u);
             if (!ok) break;
+            PIPE_TRACE(0);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const float* src = Pc + (size_t)(crow[h] < 0 ? 0 : crow[h]) * kH;
+                const float* sv = Pv + (size_t)(vrow[h] < 0 ? 0 : vrow[h]) * kH;
+                const float* sc = Pc + (size_t)(crow[h] < 0 ? 0 : crow[h]) * kH;
+                const int nbytes = vrow[h] >= 0 ? 16 : 0;
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
+                for (int j = 0; j < 4; ++j) {
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(smem_u32(stage_ptr(Sp0, lrow + 64 * h, 4 * j + q4))),
+                                 "l"(sv + (4 * j + q4) * 4), "r"(nbytes) : "memory");
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(smem_u32(stage_ptr(Sp1, lrow + 64 * h, 4 * j + q4))),
-                                 "l"(src + (4 * j + q4) * 4), "r"(crow[h] >= 0 ? 16 : 0) : "memory");
+                                 "l"(sc + (4 * j + q4) * 4), "r"(nbytes) : "memory");
+                }
             }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            // variable-node rows of tile k (in registers since the previous iteration) -> Sp0 once y(k-1) has been stored
-            wait(kBarFreeP0, (uint32_t)k + 1u);
-            if (!ok) break;
-#pragma unroll
-            for (int h = 0; h < 2; ++h)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) *stage_ptr(Sp0, lrow + 64 * h, 4 * j + q4) = V[h][j];
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            warp_arrive(kBarFullP);
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(smem_u32(&bars[kBarFullP])) : "memory");
             if (more) {
-                load_v();
-                crow[0] = crow_next[0]; crow[1] = crow_next[1];
-                wait(kBarFreeX, (uint32_t)k);                                 // C(k) has consumed Sx
+                take_indices();                                               // of tile k+1, requested at the top
+                wait(kBarFreeX, (uint32_t)k); wait(kBarFreeY, (uint32_t)k + 1u);   // C(k) has read Sx and y(k-1) has left it
                 if (!ok) break;
+                PIPE_TRACE(1);
                 publish_x();
+                PIPE_TRACE(2);
             }
+            PIPE_TRACE_NEXT();
         }
+        PIPE_TRACE_DUMP("load", 3);
     }
     if (!ok) { atomicExch(status, 1); asm volatile("trap;"); }               // a hand-off never arrived: fail loudly
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
