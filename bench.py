@@ -263,6 +263,27 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = Be * world * args.e2e_steps * K_INFO / float(te.item()) / 1e9
+
+    # the same call with 8-bit LLRs (what a demapper produces): 4x fewer PCIe bytes, same fp32 arithmetic on q * scale
+    q_host = torch.empty((Be, code.N), dtype=torch.int8).pin_memory()
+    q_host.copy_(torch.clamp(torch.round(llr[:Be] * 4.0), -127, 127).to(torch.int8))
+
+    def e2e_q_step():
+        _native.check(L.ldpc_decode_host_q(h, algo, _native.ptr(q_host), _native.LLR_I8, 0.25, Be, ITERS, ALPHA,
+                                           _native.PATH_FAST if algo == _native.ALGO_BP else _native.PATH_AUTO, None,
+                                           _native.ptr(hard_host), _native.HARD_PACKED, 1 << 15))
+    e2e_q_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        e2e_q_step()
+    torch.cuda.synchronize()
+    tq = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tq, op=dist.ReduceOp.MAX)
+    e2e_q_value = Be * world * args.e2e_steps * K_INFO / float(tq.item()) / 1e9
     frame_errors = int(counters[1].item())
     frames = int(counters[2].item())
 
@@ -292,7 +313,10 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Gbit/s", "h2d_bytes_per_step": Be * code.N * 4,
                     "d2h_bytes_per_step": Be * NW * 4, "codewords_per_step": Be, "steps": args.e2e_steps,
-                    "api": "ldpc_decode_host (pinned host LLRs -> packed hard bits)"},
+                    "api": "ldpc_decode_host (pinned host fp32 LLRs -> packed hard bits)"},
+            "e2e_int8_llr": {"value": e2e_q_value, "unit": "Gbit/s", "h2d_bytes_per_step": Be * code.N,
+                             "d2h_bytes_per_step": Be * NW * 4,
+                             "api": "ldpc_decode_host_q (pinned host int8 LLRs, scale 0.25 -> packed hard bits)"},
             "roofline": {"bound": "issue", "achieved": achieved, "peak": peak, "unit": "Gwarp-instr/s",
                          "frac": achieved / peak,
                          "traffic": (NCU_DRAM_BYTES_PER_CW * B if args.workload == "minsum" else None),

@@ -111,6 +111,16 @@ int ldpc_syndrome_check(const ldpc_code_t* code, const void* hard, int hard_dtyp
 int ldpc_decode_host(const ldpc_code_t* code, int algo, const float* llr_host, int64_t B, int iters, float alpha,
                      int path, float* soft_host, void* hard_host, int hard_dtype, int64_t chunk);
 
+/* Quantised host LLRs.  A 5G receiver's demapper produces 8-bit (or half-precision) LLRs; shipping them as such
+ * cuts the PCIe bytes per codeword 4x (2x) -- the host path is PCIe-bound, see DESIGN.md section 4.  The decoder
+ * still computes in fp32 on llr = (float)q * llr_scale (LDPC_LLR_I8) or llr = (float)h * llr_scale (LDPC_LLR_F16);
+ * the outputs are bit-identical to the reference decoders (traditional_decoders.py:37-109,178-260) run on those
+ * float values.  LDPC_LLR_F32 ignores llr_scale and is ldpc_decode_host.                                       */
+enum { LDPC_LLR_F32 = 0, LDPC_LLR_F16 = 1, LDPC_LLR_I8 = 2 };
+int ldpc_decode_host_q(const ldpc_code_t* code, int algo, const void* llr_host, int llr_format, float llr_scale,
+                       int64_t B, int iters, float alpha, int path, float* soft_host, void* hard_host,
+                       int hard_dtype, int64_t chunk);
+
 /* ---- channel + metrics -------------------------------------------------------------
  * ldpc_awgn_llr replaces AWGNChannel.transmit (utils/channel.py:205-231): BPSK 0->+1,
  * sigma = 1/sqrt(10^(snr_db/10)), llr = 2*(s+n)/sigma^2, noise from Philox4x32-10 keyed by

@@ -14,6 +14,7 @@ HARD_F32, HARD_U8, HARD_PACKED = 0, 1, 2
 STOP_FIXED, STOP_PER_CODEWORD = 0, 1
 PATH_AUTO, PATH_EXACT, PATH_FAST = 0, 1, 2
 ALGO_MINSUM, ALGO_BP = 0, 1
+LLR_F32, LLR_F16, LLR_I8 = 0, 1, 2
 PATHS = {"auto": PATH_AUTO, "exact": PATH_EXACT, "fast": PATH_FAST}
 
 _p, _i, _i64, _u64, _f, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_float, C.c_size_t
@@ -31,6 +32,7 @@ PROTOTYPES = {
     "ldpc_bp_decode": (_i, [_p, _p, _i64, _i, _i, _i, _p, _p, _i, _p, _p, _p, _i, _p]),
     "ldpc_syndrome_check": (_i, [_p, _p, _i, _i64, _p, _p]),
     "ldpc_decode_host": (_i, [_p, _i, _p, _i64, _i, _f, _i, _p, _p, _i, _i64]),
+    "ldpc_decode_host_q": (_i, [_p, _i, _p, _i, _f, _i64, _i, _f, _i, _p, _p, _i, _i64]),
     "ldpc_awgn_llr": (_i, [_p, _i64, _i64, _f, _u64, _u64, _p, _p]),
     "ldpc_count_errors": (_i, [_p, _i, _p, _i64, _i64, _p, _p]),
     "ldpc_sim_fer": (_i, [_p, _i, _i, _f, _f, _u64, _u64, _u64, _p, _p]),

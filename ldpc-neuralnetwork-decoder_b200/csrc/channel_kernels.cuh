@@ -1,6 +1,7 @@
 // channel_kernels.cuh -- stand-alone channel / error-count kernels (device helpers: channel.cuh).
 // Included by ldpc_b200.cu only.
 #pragma once
+#include <cuda_fp16.h>
 #include "channel.cuh"
 
 namespace ldpc {
@@ -70,5 +71,17 @@ __global__ void __launch_bounds__(256) count_errors_kernel(const void* __restric
         atomicAdd(&counters[2], frames);
     }
 }
+
+// quantised LLRs as transferred -> the fp32 values the decoder (and the reference) computes on
+template <typename T>
+__global__ void llr_dequant_kernel(const T* __restrict__ raw, float scale, long long n, float* __restrict__ out) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float v;
+        if constexpr (sizeof(T) == 1) v = (float)raw[i];
+        else v = __half2float(raw[i]);
+        out[i] = v * scale;
+    }
+}
+
 
 }  // namespace ldpc

@@ -9,6 +9,7 @@
 #include "layers.cuh"
 #include "gnn.cuh"
 #include "gnn_bwd.cuh"
+#include <cuda_fp16.h>
 #include "gnn_tc.cuh"
 #include "gnn_tc_pipe.cuh"
 #include <cstdlib>
@@ -116,7 +117,7 @@ int ldpc_code_destroy(ldpc_code_t* code) {
         if (code->d_tab) cudaFree(code->d_tab);
         for (int s = 0; s < HostStage::kStages; ++s) {
             if (code->stage.st[s]) { cudaStreamSynchronize(code->stage.st[s]); cudaStreamDestroy(code->stage.st[s]); }
-            cudaFree(code->stage.d_llr[s]); cudaFree(code->stage.d_hard[s]); cudaFree(code->stage.d_soft[s]);
+            cudaFree(code->stage.d_llr[s]); cudaFree(code->stage.d_hard[s]); cudaFree(code->stage.d_soft[s]); cudaFree(code->stage.d_raw[s]);
         }
     }
     if (code->slot >= 0) {
@@ -165,14 +166,17 @@ int ldpc_syndrome_check(const ldpc_code_t* code, const void* hard, int hard_dtyp
     return launch_syndrome(code, hard, hard_dtype, B, syndrome_ok, (cudaStream_t)stream);
 }
 
-int ldpc_decode_host(const ldpc_code_t* code, int algo, const float* llr_host, int64_t B, int iters, float alpha,
-                     int path, float* soft_host, void* hard_host, int hard_dtype, int64_t chunk) {
+int ldpc_decode_host_q(const ldpc_code_t* code, int algo, const void* llr_host, int llr_format, float llr_scale,
+                       int64_t B, int iters, float alpha, int path, float* soft_host, void* hard_host,
+                       int hard_dtype, int64_t chunk) {
     if (!code) return fail(LDPC_ERR_INVALID, "decode_host: null code handle");
     if (B < 0) return fail(LDPC_ERR_INVALID, "decode_host: negative batch");
     if (B == 0) return LDPC_OK;
     if (!llr_host || !hard_host) return fail(LDPC_ERR_INVALID, "decode_host: null host buffer");
     if (algo != LDPC_ALGO_MINSUM && algo != LDPC_ALGO_BP) return fail(LDPC_ERR_INVALID, "decode_host: unknown algo %d", algo);
     if (hard_dtype < LDPC_HARD_F32 || hard_dtype > LDPC_HARD_PACKED) return fail(LDPC_ERR_INVALID, "decode_host: unknown hard_dtype");
+    if (llr_format < LDPC_LLR_F32 || llr_format > LDPC_LLR_I8) return fail(LDPC_ERR_INVALID, "decode_host: unknown llr_format %d", llr_format);
+    const size_t raw_elem = llr_format == LDPC_LLR_I8 ? 1 : llr_format == LDPC_LLR_F16 ? 2 : 0;   // 0: fp32 goes straight to d_llr
     DeviceGuard g(code->device);
     if (!g.ok) return fail(LDPC_ERR_CUDA, "decode_host: cannot select device %d", code->device);
     const int N = code->N;
@@ -184,13 +188,18 @@ int ldpc_decode_host(const ldpc_code_t* code, int algo, const float* llr_host, i
     HostStage& hs = code->stage;
     std::lock_guard<std::mutex> lk(hs.mu);
     const size_t need_llr = sizeof(float) * (size_t)chunk * N, need_hard = hard_row * (size_t)chunk;
-    const size_t need_soft = soft_host ? need_llr : 0;
+    const size_t need_soft = soft_host ? need_llr : 0, need_raw = raw_elem * (size_t)chunk * N;
     for (int s = 0; s < HostStage::kStages; ++s) {
         if (!hs.st[s]) LDPC_CUDA(cudaStreamCreateWithFlags(&hs.st[s], cudaStreamNonBlocking));
         if (hs.cap_llr[s] < need_llr) {
             LDPC_CUDA(cudaStreamSynchronize(hs.st[s]));
             cudaFree(hs.d_llr[s]); hs.d_llr[s] = nullptr; hs.cap_llr[s] = 0;
             LDPC_CUDA(cudaMalloc(&hs.d_llr[s], need_llr)); hs.cap_llr[s] = need_llr;
+        }
+        if (hs.cap_raw[s] < need_raw) {
+            LDPC_CUDA(cudaStreamSynchronize(hs.st[s]));
+            cudaFree(hs.d_raw[s]); hs.d_raw[s] = nullptr; hs.cap_raw[s] = 0;
+            LDPC_CUDA(cudaMalloc(&hs.d_raw[s], need_raw)); hs.cap_raw[s] = need_raw;
         }
         if (hs.cap_hard[s] < need_hard) {
             LDPC_CUDA(cudaStreamSynchronize(hs.st[s]));
@@ -208,8 +217,20 @@ int ldpc_decode_host(const ldpc_code_t* code, int algo, const float* llr_host, i
         const int s = it % HostStage::kStages;
         const int64_t b = (B - done) < chunk ? (B - done) : chunk;
         // same-stream ordering makes reuse of stage s safe: its previous D2H precedes this H2D
-        LDPC_CUDA(cudaMemcpyAsync(hs.d_llr[s], llr_host + (size_t)done * N, sizeof(float) * (size_t)b * N,
-                                  cudaMemcpyHostToDevice, hs.st[s]));
+        if (raw_elem == 0) {
+            LDPC_CUDA(cudaMemcpyAsync(hs.d_llr[s], (const float*)llr_host + (size_t)done * N, sizeof(float) * (size_t)b * N,
+                                      cudaMemcpyHostToDevice, hs.st[s]));
+        } else {
+            const long long n = (long long)b * N;
+            LDPC_CUDA(cudaMemcpyAsync(hs.d_raw[s], (const char*)llr_host + raw_elem * (size_t)done * N, raw_elem * (size_t)n,
+                                      cudaMemcpyHostToDevice, hs.st[s]));
+            const int grid = (int)((n + 1023) / 1024 < (long long)kNumSMs * 8 ? (n + 1023) / 1024 : (long long)kNumSMs * 8);
+            if (llr_format == LDPC_LLR_I8)
+                llr_dequant_kernel<int8_t><<<grid, 256, 0, hs.st[s]>>>((const int8_t*)hs.d_raw[s], llr_scale, n, (float*)hs.d_llr[s]);
+            else
+                llr_dequant_kernel<__half><<<grid, 256, 0, hs.st[s]>>>((const __half*)hs.d_raw[s], llr_scale, n, (float*)hs.d_llr[s]);
+            LDPC_CHECK_LAUNCH("llr_dequant_kernel");
+        }
         int rc = decode_common(code, algo, (const float*)hs.d_llr[s], b, iters, alpha, LDPC_STOP_FIXED, path,
                                soft_host ? (float*)hs.d_soft[s] : nullptr, hs.d_hard[s], hard_dtype, nullptr, nullptr,
                                nullptr, 0, hs.st[s]);
@@ -222,6 +243,11 @@ int ldpc_decode_host(const ldpc_code_t* code, int algo, const float* llr_host, i
     }
     for (int s = 0; s < HostStage::kStages; ++s) LDPC_CUDA(cudaStreamSynchronize(hs.st[s]));
     return LDPC_OK;
+}
+
+int ldpc_decode_host(const ldpc_code_t* code, int algo, const float* llr_host, int64_t B, int iters, float alpha,
+                     int path, float* soft_host, void* hard_host, int hard_dtype, int64_t chunk) {
+    return ldpc_decode_host_q(code, algo, llr_host, LDPC_LLR_F32, 1.0f, B, iters, alpha, path, soft_host, hard_host, hard_dtype, chunk);
 }
 
 // ---- channel + metrics ------------------------------------------------------------------

@@ -48,9 +48,10 @@ struct HostStage {
     std::mutex mu;
     cudaStream_t st[kStages] = {};
     void* d_llr[kStages] = {};
+    void* d_raw[kStages] = {};     // quantised LLRs as transferred (ldpc_decode_host_q)
     void* d_soft[kStages] = {};
     char* d_hard[kStages] = {};
-    size_t cap_llr[kStages] = {}, cap_soft[kStages] = {}, cap_hard[kStages] = {};
+    size_t cap_llr[kStages] = {}, cap_soft[kStages] = {}, cap_hard[kStages] = {}, cap_raw[kStages] = {};
 };
 
 struct ldpc_code {

@@ -225,6 +225,36 @@ def test_host_buffer_entry_point():
     assert np.array_equal(h, o["hard"]) and np.array_equal(soft.numpy(), o["beliefs"])
 
 
+@pytest.mark.parametrize("fmt", ["i8", "f16"])
+def test_host_buffer_quantised_llrs(fmt):
+    """ldpc_decode_host_q: 8-bit / half-precision host LLRs decode bit-identically to the fp32 values they stand for
+    (llr = q * scale), on batches that exercise the chunking (ragged last chunk) and both output kinds."""
+    code = QCCode.nr_2_0(32)
+    B, iters = 2500, 10
+    llr = oracle.awgn_llr(None, B, code.N, -2.0, seed=33)
+    if fmt == "i8":
+        scale = np.float32(0.25)
+        q = np.clip(np.rint(llr / scale), -127, 127).astype(np.int8)
+        deq = q.astype(np.float32) * scale
+        raw, code_fmt = torch.from_numpy(q).pin_memory(), _native.LLR_I8
+    else:
+        scale = np.float32(1.0)
+        q = llr.astype(np.float16)
+        deq = q.astype(np.float32)
+        raw, code_fmt = torch.from_numpy(q).pin_memory(), _native.LLR_F16
+    hard = torch.empty((B, (code.N + 31) // 32), dtype=torch.int32).pin_memory()
+    soft = torch.empty((B, code.N), dtype=torch.float32).pin_memory()
+    _native.check(_native.lib().ldpc_decode_host_q(code.handle(dev()), _native.ALGO_MINSUM, _native.ptr(raw), code_fmt, float(scale),
+                                                   B, iters, 0.75, _native.PATH_AUTO, _native.ptr(soft), _native.ptr(hard),
+                                                   _native.HARD_PACKED, 1024))
+    o = oracle.decode(code.shifts, 32, deq, iters, "minsum", 0.75, order="fast")
+    h = np.unpackbits(hard.numpy().view(np.uint8), axis=1, bitorder="little")[:, :code.N]
+    assert np.array_equal(h, o["hard"]) and np.array_equal(soft.numpy(), o["beliefs"])
+    with pytest.raises(_native.LdpcError):
+        _native.check(_native.lib().ldpc_decode_host_q(code.handle(dev()), _native.ALGO_MINSUM, _native.ptr(raw), 7, 1.0, B, iters,
+                                                       0.75, _native.PATH_AUTO, None, _native.ptr(hard), _native.HARD_PACKED, 0))
+
+
 def test_linearity_at_full_batch_size():
     """Size-independent property at a bench-sized batch: min-sum is odd-symmetric under a
     codeword flip -- decoding llr*(1-2c) for a codeword c gives the decisions XOR c -- and
