@@ -98,6 +98,7 @@ def cpu_baseline(workload, seconds=12.0):
     import ldpc_b200
     from ldpc_b200.utils import QCCode
     code = QCCode.nr_2_0(Z)
+    os.sched_setaffinity(0, ALL_CPUS)                    # undo the GPU-local binding of the e2e leg: the CPU arm gets every core
     threads = os.cpu_count() or oracle.num_threads()     # torchrun exports OMP_NUM_THREADS=1: ask for all cores explicitly
     probe = 64 * threads
     llr = oracle.awgn_llr(None, probe, code.N, SNR_DB, seed=1)
@@ -150,6 +151,27 @@ def workload_config(args, B):
             "sharding": "independent codeword ranges per GPU, counters all-reduced once"}
 
 
+def bind_to_gpu_numa_node(local):
+    """Pin this rank's host threads to the CPUs next to its GPU (sysfs local_cpulist of the GPU's PCI function), so
+    that the pinned staging buffers of the e2e path are first-touched on the GPU's NUMA node and the H2D copies do
+    not cross the socket interconnect.  Best effort: returns the cpulist used, or None."""
+    try:
+        p = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        cpulist = open(f"/sys/bus/pci/devices/{bdf}/local_cpulist").read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return cpulist
+    except Exception:
+        pass
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -179,6 +201,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -313,7 +336,7 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Gbit/s", "h2d_bytes_per_step": Be * code.N * 4,
                     "d2h_bytes_per_step": Be * NW * 4, "codewords_per_step": Be, "steps": args.e2e_steps,
-                    "api": "ldpc_decode_host (pinned host fp32 LLRs -> packed hard bits)"},
+                    "api": "ldpc_decode_host (pinned host fp32 LLRs -> packed hard bits)", "host_cpus_rank0": numa},
             "e2e_int8_llr": {"value": e2e_q_value, "unit": "Gbit/s", "h2d_bytes_per_step": Be * code.N,
                              "d2h_bytes_per_step": Be * NW * 4,
                              "api": "ldpc_decode_host_q (pinned host int8 LLRs, scale 0.25 -> packed hard bits)"},
