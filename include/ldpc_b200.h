@@ -128,6 +128,15 @@ int ldpc_decode_host_q(const ldpc_code_t* code, int algo, const void* llr_host, 
  * count.  bits: [B,N] uint8 or NULL (= all-zero codeword, as every reference sweep uses). */
 int ldpc_awgn_llr(const uint8_t* bits, int64_t B, int64_t N, float snr_db, uint64_t seed, uint64_t first_frame,
                   float* llr_out, void* stream);
+
+/* ldpc_qpsk_llr replaces the chain qpsk_modulate -> awgn_channel -> qpsk_demodulate (utils/channel.py:4-60, 62-89,
+ * 91-154) that every shipped training / evaluation loop of the reference uses (trainer.py:89-95,
+ * comparative_evaluation.py:138-146): bit 2k rides on I and bit 2k+1 on Q of symbol k with amplitude 1/sqrt(2), each
+ * component sees N(0, 1/(2*snr_linear)), llr = 2*r/noise_var with noise_var = 1/snr_linear -- the reference's
+ * scaling (its LLRs are 1/sqrt(2) of the true ones; min-sum is scale-invariant, BP and the GNN are not).
+ * true_llr = 1 selects the exact LLR 2*sqrt(2)*r*snr_linear instead.  Noise as in ldpc_awgn_llr.  [B,N] out.   */
+int ldpc_qpsk_llr(const uint8_t* bits, int64_t B, int64_t N, float snr_db, int true_llr, uint64_t seed,
+                  uint64_t first_frame, float* llr_out, void* stream);
 /* ldpc_count_errors replaces compute_ber_fer (utils/channel.py:156-190) with integer
  * counters: counters[0]+=bit errors, [1]+=frame errors, [2]+=frames.  tx may be NULL
  * (all-zero).  hard per hard_dtype.                                                      */

@@ -34,6 +34,7 @@ PROTOTYPES = {
     "ldpc_decode_host": (_i, [_p, _i, _p, _i64, _i, _f, _i, _p, _p, _i, _i64]),
     "ldpc_decode_host_q": (_i, [_p, _i, _p, _i, _f, _i64, _i, _f, _i, _p, _p, _i, _i64]),
     "ldpc_awgn_llr": (_i, [_p, _i64, _i64, _f, _u64, _u64, _p, _p]),
+    "ldpc_qpsk_llr": (_i, [_p, _i64, _i64, _f, _i, _u64, _u64, _p, _p]),
     "ldpc_count_errors": (_i, [_p, _i, _p, _i64, _i64, _p, _p]),
     "ldpc_sim_fer": (_i, [_p, _i, _i, _f, _f, _u64, _u64, _u64, _p, _p]),
     "ldpc_check_layer_fwd": (_i, [_p, _p, _i64, _i64, _i, _p, _p, _p]),

@@ -22,6 +22,7 @@ struct GenParams {
     int enabled;                 // 0: read LLRs from memory
     float sigma;                 // fp32(1/sqrt(snr_linear))
     float var;                   // fp32(sigma_d * sigma_d)
+    float amp;                   // symbol amplitude: 1 (BPSK, AWGNChannel) or fp32(1/sqrt(2)) (QPSK component)
     unsigned long long seed;
     unsigned long long first_frame;
 };

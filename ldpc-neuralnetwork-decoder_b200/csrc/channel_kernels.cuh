@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(256) awgn_llr_kernel(const uint8_t* __restrict
         for (int comp = 0; comp < 4; ++comp) {
             const long long n = ((long long)(blk >> 5) << 7) + ((long long)comp << 5) + (blk & 31);
             if (n < N) {
-                const float s = bits ? 1.0f - 2.0f * (float)bits[b * N + n] : 1.0f;
+                const float s = bits && bits[b * N + n] ? -g.amp : g.amp;
                 out[b * N + n] = llr_from_noise(z[comp], s, g);
             }
         }

@@ -258,6 +258,7 @@ static int make_gen(float snr_db, uint64_t seed, uint64_t first_frame, GenParams
     g->enabled = 1;
     g->sigma = (float)sigma;
     g->var = (float)(sigma * sigma);
+    g->amp = 1.0f;
     g->seed = seed;
     g->first_frame = first_frame;
     return LDPC_OK;
@@ -274,6 +275,32 @@ int ldpc_awgn_llr(const uint8_t* bits, int64_t B, int64_t N, float snr_db, uint6
     const int grid = (int)(blocks_needed < kNumSMs * 8 ? blocks_needed : kNumSMs * 8);
     awgn_llr_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(bits, B, N, g, llr_out);
     LDPC_CHECK_LAUNCH("awgn_llr_kernel");
+    return LDPC_OK;
+}
+
+int ldpc_qpsk_llr(const uint8_t* bits, int64_t B, int64_t N, float snr_db, int true_llr, uint64_t seed,
+                  uint64_t first_frame, float* llr_out, void* stream) {
+    if (!llr_out) return fail(LDPC_ERR_INVALID, "qpsk_llr: null output");
+    if (B < 0 || N <= 0) return fail(LDPC_ERR_INVALID, "qpsk_llr: bad shape [%lld,%lld]", (long long)B, (long long)N);
+    if (B == 0) return LDPC_OK;
+    // utils/channel.py:39 (symbol components +-1/sqrt(2)), :75-82 (noise_power = 1/snr_linear, each component
+    // N(0, noise_power/2)), :120-138 (llr = 2*r/noise_var with noise_var = 1/snr_linear): all scalars are Python
+    // float64 rounded to fp32 where they meet a tensor
+    const double snr_linear = pow(10.0, (double)snr_db / 10.0);
+    const double noise_power = 1.0 / snr_linear;
+    GenParams g;
+    g.enabled = 1;
+    g.amp = (float)(1.0 / sqrt(2.0));
+    g.sigma = (float)sqrt(noise_power / 2.0);
+    // the reference divides by the TOTAL noise variance although each component carries half of it and the symbol
+    // amplitude is 1/sqrt(2): its LLRs are 1/sqrt(2) of the true ones.  true_llr = 1 divides by noise_power/sqrt(2).
+    g.var = true_llr ? (float)(noise_power / sqrt(2.0)) : (float)noise_power;
+    g.seed = seed;
+    g.first_frame = first_frame;
+    const long long blocks_needed = (B * ((((long long)N + 127) >> 7) << 5) + 255) / 256;
+    const int grid = (int)(blocks_needed < kNumSMs * 8 ? blocks_needed : kNumSMs * 8);
+    awgn_llr_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(bits, B, N, g, llr_out);
+    LDPC_CHECK_LAUNCH("awgn_llr_kernel(qpsk)");
     return LDPC_OK;
 }
 

@@ -264,3 +264,35 @@ int oracle_awgn_llr(const uint8_t* bits, int64_t B, int64_t N, float snr_db, uin
     }
     return 0;
 }
+
+/* qpsk_modulate -> awgn_channel -> qpsk_demodulate, utils/channel.py:39, 75-82, 120-138 (noise: the engine's Philox) */
+int oracle_qpsk_llr(const uint8_t* bits, int64_t B, int64_t N, float snr_db, int true_llr, uint64_t seed,
+                    uint64_t first_frame, float* out) {
+    if (!out || B < 0 || N <= 0) return -1;
+    const double snr_linear = pow(10.0, (double)snr_db / 10.0);
+    const double noise_power = 1.0 / snr_linear;
+    const volatile float amp = (float)(1.0 / sqrt(2.0)), sigma = (float)sqrt(noise_power / 2.0),
+                         var = true_llr ? (float)(noise_power / sqrt(2.0)) : (float)noise_power;
+    const int64_t nblk = ((N + 127) >> 7) << 5;
+    for (int64_t b = 0; b < B; ++b) {
+        const uint64_t frame = first_frame + (uint64_t)b;
+        for (int64_t blk = 0; blk < nblk; ++blk) {
+            uint32_t x[4];
+            philox4x32_10((uint32_t)frame, (uint32_t)(frame >> 32), (uint32_t)blk, 0u, (uint32_t)seed,
+                          (uint32_t)(seed >> 32), x);
+            const float r0 = sqrtf(-2.0f * logf(u01(x[0]))), r1 = sqrtf(-2.0f * logf(u01(x[2])));
+            const float a0 = 6.2831853071795865f * u01(x[1]), a1 = 6.2831853071795865f * u01(x[3]);
+            const float z[4] = {r0 * cosf(a0), r0 * sinf(a0), r1 * cosf(a1), r1 * sinf(a1)};
+            for (int comp = 0; comp < 4; ++comp) {
+                const int64_t n = ((blk >> 5) << 7) + ((int64_t)comp << 5) + (blk & 31);
+                if (n >= N) continue;
+                const float s = bits && bits[b * N + n] ? -amp : amp;
+                const float noise = z[comp] * sigma;
+                const float received = s + noise;
+                const float twice = 2.0f * received;
+                out[b * N + n] = twice / var;
+            }
+        }
+    }
+    return 0;
+}

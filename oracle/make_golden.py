@@ -41,7 +41,8 @@ from ldpc_neural_decoder.models import (  # noqa: E402
     ResidualLayer, OutputLayer, create_message_gnn_decoder)
 from ldpc_neural_decoder.utils.ldpc_utils import (  # noqa: E402
     load_base_matrix, expand_base_matrix, create_LLR_mapping)
-from ldpc_neural_decoder.utils.channel import AWGNChannel, compute_ber_fer  # noqa: E402
+from ldpc_neural_decoder.utils.channel import (  # noqa: E402
+    AWGNChannel, compute_ber_fer, qpsk_modulate, awgn_channel, qpsk_demodulate)
 
 TABLES = {4: os.path.join(REF_ROOT, "5G LDPC CODES", "NR_2_0_4.txt"),
           32: os.path.join(REF_ROOT, "5G LDPC CODES", "NR_2_0_32.txt")}
@@ -217,6 +218,30 @@ def gnn(Z, B, snr_db, tag, with_grad):
     print(f"gnn_{tag}: build {t_build:.1f}s fwd {t_fwd:.1f}s params {sum(v.size for v in sd.values())}")
 
 
+def qpsk():
+    """The reference's QPSK chain (utils/channel.py:4-154) on fixed inputs: random bits of even and odd length,
+    the symbols it maps them to, a fixed received block and the LLRs it demodulates, plus one pass through its
+    awgn_channel under a fixed torch seed (statistics only: the engine's noise source is Philox)."""
+    g = torch.Generator().manual_seed(2024)
+    out = {}
+    for tag, n in (("even", 208), ("odd", 51)):
+        bits = torch.randint(0, 2, (6, n), generator=g).float()
+        sym = qpsk_modulate(bits)
+        out[f"bits_{tag}"] = bits.numpy().astype(np.uint8)
+        out[f"sym_{tag}"] = torch.view_as_real(sym).numpy()
+        rx = sym + torch.complex(torch.randn(sym.shape, generator=g) * 0.4, torch.randn(sym.shape, generator=g) * 0.4)
+        for snr in (-2.0, 1.5, 6.0):
+            out[f"llr_{tag}_snr{snr}"] = qpsk_demodulate(rx, snr).numpy()
+        out[f"rx_{tag}"] = torch.view_as_real(rx).numpy()
+    one = qpsk_demodulate(qpsk_modulate(torch.tensor([0., 1., 1.])), 0.0)        # un-batched, odd length
+    out["llr_unbatched"] = one.numpy()
+    torch.manual_seed(7)
+    zeros = torch.zeros(512, 208)
+    llr = qpsk_demodulate(awgn_channel(qpsk_modulate(zeros), 1.0), 1.0)
+    out["chain_snr1_mean_std"] = np.array([llr.mean().item(), llr.std().item()], dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, "qpsk.npz"), **out)
+
+
 JOBS = {
     "mapping_layers": mapping_and_layers,
     # BASELINE.json config 1 (plumbing): Z=4, B=1024, 5 iters, alpha 0.75, snr_db 2.0, seed 1234
@@ -229,6 +254,7 @@ JOBS = {
     "earlystop_z4": lambda: early_stop(4, 8, 20, 1.0, 5, "z4_b8"),
     "gnn_z4": lambda: gnn(4, 4, 1.0, "z4_b4", True),
     "gnn_z32": lambda: gnn(32, 2, -2.0, "z32_b2", True),
+    "qpsk": qpsk,
 }
 
 if __name__ == "__main__":

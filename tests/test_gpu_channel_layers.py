@@ -9,7 +9,7 @@ from oracle import oracle
 import ldpc_b200
 from ldpc_b200 import _native
 from ldpc_b200.models import CheckLayer, VariableLayer, ResidualLayer, OutputLayer
-from ldpc_b200.utils import QCCode, AWGNChannel, compute_ber_fer, count_errors
+from ldpc_b200.utils import QCCode, AWGNChannel, QPSKChannel, compute_ber_fer, count_errors
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -33,6 +33,29 @@ def test_awgn_generator_matches_oracle():
     assert np.max(np.abs(llr - ref)) <= 1e-3
     one = AWGNChannel(seed=5).transmit(bits[0], 3.0)
     assert one.shape == (208,)
+
+
+def test_qpsk_generator_matches_oracle():
+    """ldpc_qpsk_llr == oracle_qpsk_llr (same Philox stream, same fp32 operation order; libm vs CUDA log/sincos
+    differ in the last ulp -> 2e-5 of the LLR scale), for random bits, both LLR scalings, ragged N."""
+    for N, snr_db, true_llr in ((1664, -2.0, False), (208, 1.5, False), (51, 6.0, True)):
+        bits = (torch.rand(33, N, device=DEV) > 0.5).float()
+        ch = QPSKChannel(seed=77, true_llr=true_llr)
+        llr = ch.transmit(bits, snr_db).cpu().numpy()
+        ref = oracle.qpsk_llr(bits.cpu().numpy().astype(np.uint8), 33, N, snr_db, 77, true_llr=true_llr)
+        scale = 2.0 / (10 ** (-snr_db / 10)) * (np.sqrt(2) if true_llr else 1.0)
+        assert np.max(np.abs(llr - ref)) <= 2e-5 * scale * 8
+        nxt = ch.transmit(bits[:5], snr_db).cpu().numpy()                              # frame counter advanced
+        ref2 = oracle.qpsk_llr(bits[:5].cpu().numpy().astype(np.uint8), 5, N, snr_db, 77, first_frame=33, true_llr=true_llr)
+        assert np.max(np.abs(nxt - ref2)) <= 2e-5 * scale * 8
+    # min-sum is scale-invariant: decoding the reference-scaled and the true LLRs of the same frames gives the same bits
+    code = QCCode.nr_2_0(32)
+    from ldpc_b200.models import MinSumScaledDecoder
+    dec = MinSumScaledDecoder(code, 10, 0.75, early_stopping=False)
+    zeros = torch.zeros(256, code.N, device=DEV)
+    a, _ = dec.decode(QPSKChannel(seed=5).transmit(zeros, -2.0))
+    b, _ = dec.decode(QPSKChannel(seed=5, true_llr=True).transmit(zeros, -2.0))
+    assert torch.equal(a, b)
 
 
 def test_compute_ber_fer_known_answers():

@@ -105,3 +105,44 @@ def test_cpu_tensor_without_gpu_raises():
     dec = MinSumScaledDecoder(QCCode.nr_2_0(4), max_iterations=2, early_stopping=False)
     with pytest.raises(RuntimeError):
         dec.decode(torch.zeros(1, 208))
+
+
+def test_qpsk_helpers_equal_the_reference():
+    """qpsk_modulate / qpsk_demodulate (utils/channel.py:4-60, 91-154) against golden vectors produced by the
+    reference itself (oracle/make_golden.py:qpsk): bit-identical, including odd lengths and un-batched input."""
+    from ldpc_b200.utils import qpsk_modulate, qpsk_demodulate, awgn_channel
+    g = load_golden("qpsk")
+    for tag in ("even", "odd"):
+        bits = torch.from_numpy(g[f"bits_{tag}"]).float()
+        sym = qpsk_modulate(bits)
+        assert np.array_equal(torch.view_as_real(sym).numpy(), g[f"sym_{tag}"])
+        rx = torch.view_as_complex(torch.from_numpy(g[f"rx_{tag}"]).contiguous())
+        for snr in (-2.0, 1.5, 6.0):
+            assert np.array_equal(qpsk_demodulate(rx, snr).numpy(), g[f"llr_{tag}_snr{snr}"])
+    one = qpsk_demodulate(qpsk_modulate(torch.tensor([0., 1., 1.])), 0.0)
+    assert one.shape == (4,) and np.array_equal(one.numpy(), g["llr_unbatched"])
+    # the noisy chain is statistical: same mean / spread as the reference's run (512 x 208 LLRs)
+    torch.manual_seed(11)
+    llr = qpsk_demodulate(awgn_channel(qpsk_modulate(torch.zeros(512, 208)), 1.0), 1.0)
+    m, sd = g["chain_snr1_mean_std"]
+    assert abs(llr.mean().item() - m) < 0.02 * abs(m) and abs(llr.std().item() - sd) < 0.02 * sd
+
+
+def test_oracle_qpsk_generator_statistics():
+    """oracle_qpsk_llr (the CPU restatement the device kernel is checked against): mean 2*a/noise_var, standard
+    deviation 2*sqrt(noise_var/2)/noise_var, sign flip for 1-bits, true_llr = sqrt(2) x the reference scaling."""
+    from oracle import oracle
+    snr_db = 1.0
+    nv = 1 / (10 ** (snr_db / 10))
+    a = oracle.qpsk_llr(None, 512, 208, snr_db, seed=3)
+    assert abs(a.mean() - 2 * (1 / np.sqrt(2)) / nv) < 0.02 and abs(a.std() - 2 * np.sqrt(nv / 2) / nv) < 0.02
+    g = load_golden("qpsk")
+    m, sd = g["chain_snr1_mean_std"]
+    assert abs(a.mean() - m) < 0.02 * abs(m) and abs(a.std() - sd) < 0.02 * sd
+    bits = np.ones((4, 208), dtype=np.uint8)
+    b = oracle.qpsk_llr(bits, 4, 208, snr_db, seed=3)
+    z = oracle.qpsk_llr(None, 4, 208, snr_db, seed=3)
+    amp2 = np.float32(2) * np.float32(1 / np.sqrt(2))
+    assert np.allclose(z - b, 2 * amp2 / np.float32(nv), rtol=1e-5)
+    t = oracle.qpsk_llr(None, 4, 208, snr_db, seed=3, true_llr=True)
+    assert np.allclose(t, z * np.sqrt(2), rtol=1e-6)
