@@ -12,13 +12,16 @@
 // lo.hi + hi.lo + hi.hi ("3xTF32"): measured 5.5e-7 relative, i.e. fp32-level, at one third of the
 // TF32 rate (still ~5x the FP32 FMA peak).
 //
-// Tile = 128 messages (rows), 128 threads, one thread per row for all CUDA-core work:
+// This file holds the weight packing, the MMA / TMEM helpers, the node kernel and the single-buffered edge kernel
+// (LDPC_GNN_EDGE=serial; the default edge kernel is the warp-specialised pipeline in gnn_tc_pipe.cuh).  Per
+// 128-message tile the single-buffered edge kernel runs, each step behind a CTA-wide barrier:
 //   1. comb = x + emb[type] -> split -> A_hi/A_lo (shared, canonical layout)
 //   2. GEMM1: D1[128x128] = comb . W1A^T                       (8 k-steps x 3 MMAs, N=128)
 //   3. h = relu(D1[:, 0:64] + Pv[var]) -> split -> A region;  GEMM2a: D2[128x64]  = h . W2[:, 0:64]^T
 //   4. h = relu(D1[:, 64:128] + Pc[chk]) -> split -> A region; GEMM2b: D2 += h . W2[:, 64:128]^T
 //   5. y = D2 + b2 (+ x for layers > 0)
-// Shared memory: W1A hi/lo 64 KB + W2 hi/lo 64 KB + A region hi/lo 64 KB = 192 KB, TMEM 256 columns.
+// with every global access staged as coalesced 256-byte rows through a swizzled tile (stage_ptr).
+// Shared memory: W1A hi/lo 64 KB + W2 hi/lo 64 KB + A region hi/lo 64 KB + staging 32 KB = 224 KB, TMEM 256 columns.
 // The node kernel (Pv / Pc) has the same shape with a single GEMM per 128-node tile.
 #pragma once
 #include "gnn.cuh"
@@ -60,7 +63,6 @@ __device__ __forceinline__ void umma_gemm3(uint32_t d_tmem, uint32_t a_hi, uint3
         acc = 1u;
     }
 }
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 // bounded wait (never hang the GPU): returns false on timeout
 __device__ __forceinline__ bool mbar_wait(uint64_t* mbar, uint32_t parity) {
     uint32_t done = 0;
@@ -89,21 +91,10 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
-// Activation tiles ([128 x 64], written by the CUDA cores).  Tuning knobs, measured on B200 at B = 2048
-// (forward, 5 layers): thread-per-row loads + LBO 128 + no prefetch 57.5 ms (default); + prefetch.global.L2 of the
-// node terms 64.0 ms; padded layout LBO 144 (legal: any multiple of 16 B) 67.6 ms; cooperative coalesced loads with
-// LBO 144 58.5 ms.  The kernel is latency-bound (ncu: 62 % long_scoreboard with 4 warps per SM); the fix is a
-// warp-specialised, double-buffered pipeline, not a different staging pattern.
-#ifndef GNN_TC_LBO
-#define GNN_TC_LBO 128
-#endif
-#ifndef GNN_TC_COOP
-#define GNN_TC_COOP 0
-#endif
-#ifndef GNN_TC_PREFETCH
-#define GNN_TC_PREFETCH 0
-#endif
-constexpr uint32_t kALbo = GNN_TC_LBO, kASbo = 16 * kALbo, kATileBytes = 16 * kASbo;      // 36 864 B per image at LBO 144
+// Activation tiles ([128 x 64], written by the CUDA cores) of the shared-memory-operand kernels (node kernel and the
+// single-buffered edge kernel).  Measured on B200 at B = 2048 (forward, 5 layers): a padded layout (LBO 144, legal: any
+// multiple of 16 B) and prefetch.global.L2 of the node rows were both slower than this plain LBO 128 layout.
+constexpr uint32_t kALbo = 128, kASbo = 16 * kALbo, kATileBytes = 16 * kASbo;
 // write 4 consecutive k elements (one 16-byte chunk c) of row r, split hi/lo, into an activation tile pair
 __device__ __forceinline__ void put_chunk(uint8_t* hi, uint8_t* lo, int r, int c, int K, float a, float b, float cc, float d) {
     (void)K;
@@ -138,7 +129,6 @@ __global__ void gnn_pack_tc_kernel(const float* __restrict__ packed, float* __re
     }
 }
 
-constexpr int kTcThreads = 128;        // node kernel: one thread per row
 #ifndef GNN_TC_PARTS
 #define GNN_TC_PARTS 4                 // edge kernel: threads per message row (each owns 1/PARTS of the columns)
 #endif

@@ -1,3 +1,5 @@
+#!/bin/bash
+# 2/4/8-GPU bench lines + the reference arm on one 8-GPU box: gpurun --gpus 8 -- bash tools/scale_run.sh
 for n in 2 4 8; do
   timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --steps 10 --warmup 3 > gpurun_out/scale_n$n.json 2> gpurun_out/scale_n$n.err; echo "n=$n rc=$?"; tail -c 300 gpurun_out/scale_n$n.err | tail -2
 done
