@@ -415,4 +415,149 @@ __global__ void __launch_bounds__(kPipeThreads, 1) gnn_edge_pipe_kernel(
     if (warp == kPipeMmaWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem) : "memory");
 }
 
+// ---- node kernel on tensor cores: P[b][node][:] = W1B . mean_{e in node}(x + emb) + b1 ----------------
+// 512 threads per 128-node tile.  Cooperative phases (16 threads per node, one 16-byte chunk each) do all the
+// global traffic as coalesced 256-byte rows: gather-and-average the node's message rows, and store the P rows;
+// per-row phases (4 threads per node) split the means hi/lo into TENSOR MEMORY (the A operand, as in the edge
+// kernel) and read the accumulator.  Without an activation tile in shared memory the CTA needs 64 KB (W1B hi/lo +
+// staging) and 256 TMEM columns, so TWO CTAs are resident per SM and one CTA's gather (latency-bound: a dependent
+// walk over the node's edge list) overlaps the other's MMA, epilogue and store.
+constexpr int kNodeParts = 4;
+constexpr int kNodeThreads = 128 * kNodeParts;
+constexpr size_t kNodeTcSmem = (size_t)(2 * 64 * 64) * sizeof(float) + 128 * 64 * sizeof(float);   // 32 + 32 KB
+constexpr uint32_t kTmNodeAHi = 0, kTmNodeALo = 64, kTmNodeD = 128;
+
+__global__ void __launch_bounds__(kNodeThreads, 2) gnn_node_tc_kernel(
+    const float* __restrict__ x, const float* __restrict__ emb_l, const float* __restrict__ packed_l, const float* __restrict__ tc_l,
+    int kind, const int* __restrict__ ptr, const int* __restrict__ list, const int* __restrict__ edge_type, long long B, int E,
+    int nodes, float* __restrict__ P, int* __restrict__ status) {
+    extern __shared__ __align__(1024) uint8_t tc_smem[];
+    uint8_t* Whi = tc_smem;                                 // W1B [64 x 64]
+    uint8_t* Wlo = Whi + 64 * 64 * 4;
+    uint8_t* S = Wlo + 64 * 64 * 4;
+    __shared__ uint64_t mbar;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float b1s[kH];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int rowi = tid & 127, part = tid >> 7;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" :: "r"(smem_u32(&tmem_base_s)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&mbar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    {
+        const float4* src = reinterpret_cast<const float4*>(tc_l + (kind == 0 ? kTcW1BV : kTcW1BC));
+        float4* dst = reinterpret_cast<float4*>(tc_smem);
+        for (int t = tid; t < 2 * 64 * 64 / 4; t += kNodeThreads) dst[t] = src[t];
+        if (tid < kH) b1s[tid] = packed_l[(kind == 0 ? kPkB1V : kPkB1C) + tid];
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base_s;
+    const uint32_t my_lane = ((uint32_t)((warp & 3) * 32)) << 16;
+    constexpr uint32_t kIdesc64 = umma_idesc_tf32(64);
+    uint32_t phase = 0;
+    bool ok = true;
+    const long long rows = B * nodes, tiles = (rows + 127) / 128;
+    const int cc = tid & 15, cr0 = tid >> 4;                 // cooperative mapping: chunk, first node of the pass
+    for (long long tile = blockIdx.x; tile < tiles && ok; tile += gridDim.x) {
+        const long long row0 = tile * 128;
+        // 0. cooperative: mean over the node's messages of (x + emb), chunk cc -> S
+#pragma unroll 1
+        for (int it = 0; it < 128 * 16 / kNodeThreads; ++it) {
+            const int rr = it * (kNodeThreads / 16) + cr0;
+            const long long row = row0 + rr;
+            float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row < rows) {
+                const int node = (int)(row % nodes);
+                const long long b = row / nodes;
+                const int k0 = ptr[node], k1 = ptr[node + 1];
+                const float* xb = x + (size_t)b * E * kH;
+                int q = k0;
+                for (; q + 4 <= k1; q += 4) {                 // four message rows in flight per thread
+                    int e[4];
+                    float4 a[4], em[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) e[u] = list ? list[q + u] : q + u;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        a[u] = reinterpret_cast<const float4*>(xb + (size_t)e[u] * kH)[cc];
+                        em[u] = __ldg(reinterpret_cast<const float4*>(emb_l + (size_t)edge_type[e[u]] * kH) + cc);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) { m.x += a[u].x + em[u].x; m.y += a[u].y + em[u].y; m.z += a[u].z + em[u].z; m.w += a[u].w + em[u].w; }
+                }
+                for (; q < k1; ++q) {
+                    const int e = list ? list[q] : q;
+                    const float4 a = reinterpret_cast<const float4*>(xb + (size_t)e * kH)[cc];
+                    const float4 em = __ldg(reinterpret_cast<const float4*>(emb_l + (size_t)edge_type[e] * kH) + cc);
+                    m.x += a.x + em.x; m.y += a.y + em.y; m.z += a.z + em.z; m.w += a.w + em.w;
+                }
+                const float inv = 1.0f / (float)(k1 - k0);
+                m.x *= inv; m.y *= inv; m.z *= inv; m.w *= inv;
+            }
+            *stage_ptr(S, rr, cc) = m;
+        }
+        __syncthreads();
+        // 1. per row: S -> split hi/lo -> Tensor Memory (A operand)
+        {
+            constexpr int kCols = 64 / kNodeParts;               // 16
+            float v[16];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 t = *stage_ptr(S, rowi, part * (kCols / 4) + q);
+                v[q * 4] = t.x; v[q * 4 + 1] = t.y; v[q * 4 + 2] = t.z; v[q * 4 + 3] = t.w;
+            }
+            uint32_t hi[16], lo[16];
+            split16(v, hi, lo);
+            tmem_st16(tmem + my_lane + kTmNodeAHi + part * kCols, hi);
+            tmem_st16(tmem + my_lane + kTmNodeALo + part * kCols, lo);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            umma_gemm3_ts(tmem + kTmNodeD, tmem + kTmNodeAHi, tmem + kTmNodeALo, smem_u32(Whi), smem_u32(Wlo), 64, 2048, kIdesc64);
+            umma_commit(&mbar);
+        }
+        ok = mbar_wait(&mbar, phase); phase ^= 1;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // 2. per row: D + b1 -> S;  cooperative: S -> P (coalesced rows)
+        if (ok) {
+#pragma unroll
+            for (int c0 = 0; c0 < 64 / kNodeParts; c0 += 16) {
+                const int col = part * (64 / kNodeParts) + c0;
+                float o[16];
+                tmem_ld16(tmem + my_lane + kTmNodeD + col, o);
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    *stage_ptr(S, rowi, (col >> 2) + q) = make_float4(o[q * 4] + b1s[col + q * 4], o[q * 4 + 1] + b1s[col + q * 4 + 1],
+                                                                      o[q * 4 + 2] + b1s[col + q * 4 + 2], o[q * 4 + 3] + b1s[col + q * 4 + 3]);
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (ok) {
+#pragma unroll
+            for (int it = 0; it < 128 * 16 / kNodeThreads; ++it) {
+                const int rr = it * (kNodeThreads / 16) + cr0;
+                if (row0 + rr < rows) reinterpret_cast<float4*>(P + (size_t)(row0 + rr) * kH)[cc] = *stage_ptr(S, rr, cc);
+            }
+        }
+        __syncthreads();
+    }
+    if (!ok) { if (tid == 0) atomicExch(status, 1); asm volatile("trap;"); }     // MMA completion never arrived: fail loudly
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" :: "r"(tmem) : "memory");
+}
+
+
 }  // namespace ldpc

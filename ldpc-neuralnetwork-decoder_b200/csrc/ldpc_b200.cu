@@ -591,10 +591,10 @@ int ldpc_gnn_forward(const ldpc_gnn_t* g, const float* params, const float* llr,
             const float* em = g->d_emb + (size_t)l * g->types * kH;
             if (use_tc) {
                 const float* tcw = g->d_tc + (size_t)l * kTcPerLayer;
-                gnn_node_tc_kernel<<<tc_grid(bc * N, 1), kNodeThreads, kNodeTcSmem, st>>>(
+                gnn_node_tc_kernel<<<tc_grid(bc * N, 2), kNodeThreads, kNodeTcSmem, st>>>(
                     xa, em, pk, tcw, 0, g->d_var_ptr, g->d_var_edge, g->d_edge_type, bc, E, N, pv, g->d_status);
                 LDPC_CHECK_LAUNCH("gnn_node_tc_kernel(var)");
-                gnn_node_tc_kernel<<<tc_grid(bc * M, 1), kNodeThreads, kNodeTcSmem, st>>>(
+                gnn_node_tc_kernel<<<tc_grid(bc * M, 2), kNodeThreads, kNodeTcSmem, st>>>(
                     xa, em, pk, tcw, 1, g->d_chk_ptr, nullptr, g->d_edge_type, bc, E, M, pc, g->d_status);
                 LDPC_CHECK_LAUNCH("gnn_node_tc_kernel(chk)");
                 if (use_pipe && l == 0)
