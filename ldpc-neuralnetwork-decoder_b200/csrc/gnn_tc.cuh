@@ -108,8 +108,10 @@ __device__ __forceinline__ void put_chunk(uint8_t* hi, uint8_t* lo, int r, int c
 
 // ---- weights: packed fp32 (gnn_pack_kernel) -> hi/lo canonical images in global memory -------------
 // per layer: W1A [128 x 64] hi, lo | W2 [64 x 128] hi, lo | W1BV [64 x 64] hi, lo | W1BC [64 x 64] hi, lo  (floats)
+//            | W2T [128 x 64] hi, lo (W2 transposed: B operand of dH = G . W2) | W1AT [64 x 128] hi, lo (B operand of
+//              dcomb = dH . W1A) -- the two backward images (gnn_bwd_tc.cuh)
 constexpr int kTcW1A = 0, kTcW2 = kTcW1A + 2 * 128 * 64, kTcW1BV = kTcW2 + 2 * 64 * 128, kTcW1BC = kTcW1BV + 2 * 64 * 64,
-              kTcPerLayer = kTcW1BC + 2 * 64 * 64;
+              kTcW2T = kTcW1BC + 2 * 64 * 64, kTcW1AT = kTcW2T + 2 * 128 * 64, kTcPerLayer = kTcW1AT + 2 * 64 * 128;
 __global__ void gnn_pack_tc_kernel(const float* __restrict__ packed, float* __restrict__ tc) {
     const int l = blockIdx.y;
     const float* pk = packed + (size_t)l * kPackedPerLayer;
@@ -122,6 +124,8 @@ __global__ void gnn_pack_tc_kernel(const float* __restrict__ packed, float* __re
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < 128 * 64; t += gridDim.x * blockDim.x) {
         put(o + kTcW1A, 128, 64, t / 64, t % 64, pk[kPkW1A + t]);                   // W1A[n][k], n < 128
         put(o + kTcW2, 64, 128, t / 128, t % 128, pk[kPkW2 + t]);                    // W2[n][k], k < 128
+        put(o + kTcW2T, 128, 64, t % 128, t / 128, pk[kPkW2 + t]);                   // W2T[k][n] = W2[n][k]
+        put(o + kTcW1AT, 64, 128, t % 64, t / 64, pk[kPkW1A + t]);                   // W1AT[k][n] = W1A[n][k]
         if (t < 64 * 64) {
             put(o + kTcW1BV, 64, 64, t / 64, t % 64, pk[kPkW1BV + t]);
             put(o + kTcW1BC, 64, 64, t / 64, t % 64, pk[kPkW1BC + t]);

@@ -12,6 +12,7 @@
 #include <cuda_fp16.h>
 #include "gnn_tc.cuh"
 #include "gnn_tc_pipe.cuh"
+#include "gnn_bwd_tc.cuh"
 #include <cstdlib>
 
 #include <cstring>
@@ -670,6 +671,13 @@ int ldpc_gnn_backward(const ldpc_gnn_t* g, const float* params, const float* llr
     LDPC_CUDA(cudaFuncSetAttribute(gnn_edge_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ebwd_smem));
     const size_t fin_smem = sizeof(float) * (size_t)g->types * kH;
     const int outer_grid = kNumSMs * 2;
+    // data gradients on the tensor cores (gnn_bwd_tc.cuh) unless LDPC_GNN_FFMA=1; the weight images are those the
+    // training forward packed from the same parameters
+    static const bool bwd_tc = !(getenv("LDPC_GNN_FFMA") && getenv("LDPC_GNN_FFMA")[0] == '1');
+    if (bwd_tc) {
+        LDPC_CUDA(cudaFuncSetAttribute(gnn_edge_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEdgeBwdTcSmem));
+        LDPC_CUDA(cudaFuncSetAttribute(gnn_dcomb_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDcombTcSmem));
+    }
     for (int l = L - 1; l >= 0; --l) {
         const float* x = base + tw.X + (size_t)l * tw.xs;
         const float* pv = base + tw.PV + (size_t)l * tw.pvs;
@@ -679,11 +687,22 @@ int ldpc_gnn_backward(const ldpc_gnn_t* g, const float* params, const float* llr
         float* pg = PG + (size_t)l * tw.pg_layer;
         LDPC_CUDA(cudaMemsetAsync(DPV, 0, sizeof(float) * tw.pvs, st));
         LDPC_CUDA(cudaMemsetAsync(DPC, 0, sizeof(float) * tw.pcs, st));
+        if (bwd_tc) {
+            const float* tcw = g->d_tc + (size_t)l * kTcPerLayer;
+            const long long tiles = ((long long)B * E + 127) / 128;
+            const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
+            gnn_edge_bwd_tc_kernel<<<grid, kBwdThreads, kEdgeBwdTcSmem, st>>>(
+                x, em, tcw, g->d_edge_var, g->d_edge_chk, g->d_edge_type, pv, pc, G, B, E, N, M, HR, DH, DPV, DPC, g->d_status);
+            LDPC_CHECK_LAUNCH("gnn_edge_bwd_tc_kernel");
+            gnn_dcomb_tc_kernel<<<grid, kBwdThreads, kDcombTcSmem, st>>>(DH, tcw, (long long)B * E, DC, g->d_status);
+            LDPC_CHECK_LAUNCH("gnn_dcomb_tc_kernel");
+        } else {
         gnn_edge_bwd_kernel<<<gnn_grid(B * E, kGnnThreads), kGnnThreads, ebwd_smem, st>>>(
             x, em, pk, g->d_edge_var, g->d_edge_chk, g->d_edge_type, pv, pc, G, B, E, N, M, HR, DH, DPV, DPC);
         LDPC_CHECK_LAUNCH("gnn_edge_bwd_kernel");
         gnn_dcomb_kernel<<<gnn_grid(B * E, kGnnThreads), kGnnThreads, 0, st>>>(DH, pk, (long long)B * E, DC);
         LDPC_CHECK_LAUNCH("gnn_dcomb_kernel");
+        }
         // dW2[n][k] += G^T . relu(h);   d(b2) += colsum(G)
         gnn_outer_kernel<kH, 2 * kH, 0><<<outer_grid, 256, 0, st>>>(G, HR, (long long)B * E, nullptr, nullptr, E, pg + kPkW2, pg + kPkB2);
         LDPC_CHECK_LAUNCH("gnn_outer_kernel(dW2)");
