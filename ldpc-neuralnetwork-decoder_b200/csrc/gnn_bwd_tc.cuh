@@ -326,4 +326,154 @@ __global__ void __launch_bounds__(kBwdThreads, 1) gnn_dcomb_tc_kernel(const floa
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem) : "memory");
 }
 
+// ---- weight gradients on the tensor cores ---------------------------------------------------------------------
+// dW[m][n] += sum_r A[r][m] * Bm[r][n]   (A rows 128 wide: relu(h) or dH;  Bm rows 64 wide: G or comb = x + emb)
+// The contraction runs over the message rows, so both operands are MN-major for the MMA (K = row index).  The only
+// shared-memory layout tcgen05.mma accepts for MN-major TF32 operands is SWIZZLE_128B_BASE32B (descriptor layout type
+// 1; validated against fp64 in tools/probe/umma_probe.cu, `outer-mn mode=1`): atoms of 32 MN elements (128 B) x 4 K
+// rows 128 B apart with the 32-byte chunk index XOR (row % 4), K groups 512 B apart (SBO), MN groups (R/4)*512 B
+// apart (LBO).  One persistent CTA per SM keeps D[128 x 64] in Tensor Memory over all its tiles and flushes it with
+// atomics once; the next tile's rows are requested into registers while the MMAs of the current tile run.
+constexpr int kOuterThreads = 512;
+constexpr uint32_t kOuterMnStride = (128 / 4) * 512;                                   // 16 KB per group of 32 MN elements
+constexpr size_t kOuterTcSmem = (size_t)(2 * 128 * 128 + 2 * 128 * 64) * sizeof(float);   // A hi/lo 128 KB + B hi/lo 64 KB
+
+__device__ __forceinline__ uint32_t outer_off(int q, int r) {                           // 16-byte chunk q (4 MN elements), row r
+    return (uint32_t)((q >> 3) * kOuterMnStride + (r >> 2) * 512 + (r & 3) * 128 + ((((q & 7) >> 1) ^ (r & 3)) << 5) + (q & 1) * 16);
+}
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)((kOuterMnStride >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((512u >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)1 << 61);   // version 1, SWIZZLE_128B_BASE32B
+}
+
+template <bool kAddEmb>
+__global__ void __launch_bounds__(kOuterThreads, 1) gnn_outer_tc_kernel(
+    const float* __restrict__ A, const float* __restrict__ Bm, long long rows, const float* __restrict__ emb_l,
+    const int* __restrict__ edge_type, int E, float* __restrict__ dW, int stride_m, int stride_n, float* __restrict__ csumA,
+    float* __restrict__ csumB, int* __restrict__ status) {
+    extern __shared__ __align__(1024) uint8_t tc_smem[];
+    uint8_t* Ahi = tc_smem;
+    uint8_t* Alo = Ahi + 128 * 128 * 4;
+    uint8_t* Bhi = Alo + 128 * 128 * 4;
+    uint8_t* Blo = Bhi + 128 * 64 * 4;
+    __shared__ uint64_t mbar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" :: "r"(smem_u32(&tmem_base_s)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&mbar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base_s;
+    // a_major = b_major = MN (bits 15, 16), D = F32, A = B = TF32, N = 64, M = 128
+    constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    // loader mapping: lane = (chunk_sub, row_sub): one warp instruction reads 64 contiguous bytes of 8 rows, and the 8
+    // lanes of a quarter warp write 8 consecutive rows of one chunk
+    const int row_sub = lane & 7, chunk_sub = lane >> 3;
+    const int qa = (warp & 7) * 4 + chunk_sub, ra0 = (warp >> 3) * 64 + row_sub;        // A: 32 chunks x 128 rows, 8 per thread
+    const int qb = (warp & 3) * 4 + chunk_sub, rb0 = (warp >> 2) * 32 + row_sub;        // B: 16 chunks x 128 rows, 4 per thread
+    const long long tiles = (rows + 127) / 128;
+    float4 av[8], bv[4];
+    float4 sa = make_float4(0.f, 0.f, 0.f, 0.f), sb = sa;
+    auto load_tile = [&](long long tile) {
+        const long long row0 = tile * 128;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const long long row = row0 + ra0 + it * 8;
+            av[it] = (tile < tiles && row < rows) ? reinterpret_cast<const float4*>(A + (size_t)row * 2 * kH)[qa] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const long long row = row0 + rb0 + it * 8;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (tile < tiles && row < rows) {
+                v = reinterpret_cast<const float4*>(Bm + (size_t)row * kH)[qb];
+                if constexpr (kAddEmb) {
+                    const float4 em = __ldg(reinterpret_cast<const float4*>(emb_l + (size_t)edge_type[(int)(row % E)] * kH) + qb);
+                    v.x += em.x; v.y += em.y; v.z += em.z; v.w += em.w;
+                }
+            }
+            bv[it] = v;
+        }
+    };
+    uint32_t phase = 0;
+    bool ok = true, first = true;
+    load_tile(blockIdx.x);
+    for (long long tile = blockIdx.x; tile < tiles && ok; tile += gridDim.x) {
+        if (!first) { ok = mbar_wait(&mbar, phase); phase ^= 1; if (!ok) break; }      // MMAs of the previous tile have read smem
+        // registers -> hi/lo images (truncation split), column sums on the way
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const float4 v = av[it];
+            const float4 h = make_float4(tf32_trunc(v.x), tf32_trunc(v.y), tf32_trunc(v.z), tf32_trunc(v.w));
+            const uint32_t o = outer_off(qa, ra0 + it * 8);
+            *reinterpret_cast<float4*>(Ahi + o) = h;
+            *reinterpret_cast<float4*>(Alo + o) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+            sa.x += v.x; sa.y += v.y; sa.z += v.z; sa.w += v.w;
+        }
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const float4 v = bv[it];
+            const float4 h = make_float4(tf32_trunc(v.x), tf32_trunc(v.y), tf32_trunc(v.z), tf32_trunc(v.w));
+            const uint32_t o = outer_off(qb, rb0 + it * 8);
+            *reinterpret_cast<float4*>(Bhi + o) = h;
+            *reinterpret_cast<float4*>(Blo + o) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+            sb.x += v.x; sb.y += v.y; sb.z += v.z; sb.w += v.w;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t acc = first ? 0u : 1u;
+            for (int ks = 0; ks < 16; ++ks) {                                         // 8 rows (two K groups of 4) per MMA
+                const uint32_t ko = (uint32_t)ks * 1024u;
+                const uint64_t ah = umma_desc_mn(smem_u32(Ahi) + ko), al = umma_desc_mn(smem_u32(Alo) + ko);
+                const uint64_t bh = umma_desc_mn(smem_u32(Bhi) + ko), bl = umma_desc_mn(smem_u32(Blo) + ko);
+                umma_tf32(tmem, al, bh, kIdesc, acc);
+                umma_tf32(tmem, ah, bl, kIdesc, 1u);
+                umma_tf32(tmem, ah, bh, kIdesc, 1u);
+                acc = 1u;
+            }
+            umma_commit(&mbar);
+        }
+        first = false;
+        load_tile(tile + gridDim.x);                                                  // in flight while the tensor pipe works
+    }
+    if (!first && ok) { ok = mbar_wait(&mbar, phase); phase ^= 1; }
+    if (!ok) { if (tid == 0) atomicExch(status, 1); asm volatile("trap;"); }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (!first && warp < 4) {                                                         // lane of TMEM = m
+        const int m = tid;
+#pragma unroll
+        for (int c0 = 0; c0 < 64; c0 += 16) {
+            float o[16];
+            tmem_ld16(tmem + (((uint32_t)(warp * 32)) << 16) + c0, o);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) atomicAdd(dW + (size_t)m * stride_m + (size_t)(c0 + j) * stride_n, o[j]);
+        }
+    }
+    // column sums: lanes with the same chunk (row_sub = 0..7) first, then one atomic per chunk and warp
+#pragma unroll
+    for (int s = 1; s < 8; s <<= 1) {
+        sa.x += __shfl_xor_sync(0xffffffffu, sa.x, s); sa.y += __shfl_xor_sync(0xffffffffu, sa.y, s);
+        sa.z += __shfl_xor_sync(0xffffffffu, sa.z, s); sa.w += __shfl_xor_sync(0xffffffffu, sa.w, s);
+        sb.x += __shfl_xor_sync(0xffffffffu, sb.x, s); sb.y += __shfl_xor_sync(0xffffffffu, sb.y, s);
+        sb.z += __shfl_xor_sync(0xffffffffu, sb.z, s); sb.w += __shfl_xor_sync(0xffffffffu, sb.w, s);
+    }
+    if (row_sub == 0) {
+        if (csumA) red_add_v4(csumA + qa * 4, sa);
+        if (csumB) red_add_v4(csumB + qb * 4, sb);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" :: "r"(tmem) : "memory");
+}
+
 }  // namespace ldpc

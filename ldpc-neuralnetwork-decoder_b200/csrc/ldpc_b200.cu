@@ -677,6 +677,8 @@ int ldpc_gnn_backward(const ldpc_gnn_t* g, const float* params, const float* llr
     if (bwd_tc) {
         LDPC_CUDA(cudaFuncSetAttribute(gnn_edge_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEdgeBwdTcSmem));
         LDPC_CUDA(cudaFuncSetAttribute(gnn_dcomb_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDcombTcSmem));
+        LDPC_CUDA(cudaFuncSetAttribute(gnn_outer_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kOuterTcSmem));
+        LDPC_CUDA(cudaFuncSetAttribute(gnn_outer_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kOuterTcSmem));
     }
     for (int l = L - 1; l >= 0; --l) {
         const float* x = base + tw.X + (size_t)l * tw.xs;
@@ -703,12 +705,25 @@ int ldpc_gnn_backward(const ldpc_gnn_t* g, const float* params, const float* llr
         gnn_dcomb_kernel<<<gnn_grid(B * E, kGnnThreads), kGnnThreads, 0, st>>>(DH, pk, (long long)B * E, DC);
         LDPC_CHECK_LAUNCH("gnn_dcomb_kernel");
         }
+        if (bwd_tc) {
+            const long long tiles = ((long long)B * E + 127) / 128;
+            const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
+            // dW2[n][k] += sum_r G[r][n] relu(h)[r][k]  (D[m = k][n]);   d(b2) += colsum(G)
+            gnn_outer_tc_kernel<false><<<grid, kOuterThreads, kOuterTcSmem, st>>>(
+                HR, G, (long long)B * E, nullptr, nullptr, E, pg + kPkW2, 1, 2 * kH, nullptr, pg + kPkB2, g->d_status);
+            LDPC_CHECK_LAUNCH("gnn_outer_tc_kernel(dW2)");
+            // dW1A[n][k] += sum_r dH[r][n] comb[r][k]   (D[m = n][k]);   d(b1v|b1c) += colsum(dH)
+            gnn_outer_tc_kernel<true><<<grid, kOuterThreads, kOuterTcSmem, st>>>(
+                DH, x, (long long)B * E, em, g->d_edge_type, E, pg + kPkW1A, kH, 1, pg + kPkB1V, nullptr, g->d_status);
+            LDPC_CHECK_LAUNCH("gnn_outer_tc_kernel(dW1A)");
+        } else {
         // dW2[n][k] += G^T . relu(h);   d(b2) += colsum(G)
         gnn_outer_kernel<kH, 2 * kH, 0><<<outer_grid, 256, 0, st>>>(G, HR, (long long)B * E, nullptr, nullptr, E, pg + kPkW2, pg + kPkB2);
         LDPC_CHECK_LAUNCH("gnn_outer_kernel(dW2)");
         // dW1A[n][k] += dH^T . comb;   d(b1v|b1c) += colsum(dH)
         gnn_outer_kernel<2 * kH, kH, 2><<<outer_grid, 256, 0, st>>>(DH, x, (long long)B * E, em, g->d_edge_type, E, pg + kPkW1A, pg + kPkB1V);
         LDPC_CHECK_LAUNCH("gnn_outer_kernel(dW1A)");
+        }
         gnn_node_bwd_kernel<<<gnn_grid(B * N, kGnnThreads), kGnnThreads, 0, st>>>(
             x, em, pk, 0, g->d_var_ptr, g->d_var_edge, g->d_edge_type, DPV, B, E, N, MV, DMV);
         LDPC_CHECK_LAUNCH("gnn_node_bwd_kernel(var)");

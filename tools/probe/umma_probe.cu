@@ -234,6 +234,140 @@ int run(const char* name) {
     return e != cudaSuccess;
 }
 
+// MN-major variant (the weight-gradient contraction): D[M x N] = sum_r A[r][m] * B[r][n], both operands stored row r
+// first (r = the MMA's K index), i.e. MN-major.  Canonical no-swizzle MN-major layout (cute/atom/mma_traits_sm100.hpp:
+// ((T,1,m),(8,k)):((1,T,SBO),(1T,LBO)), T = 4 tf32): 16-byte chunks of 4 consecutive MN elements, 8 consecutive K rows
+// 16 B apart (one 128-byte core matrix), MN groups SBO apart, K groups LBO apart.  Here [chunk][r/8][r%8][4]:
+// SBO = (R/8)*128, LBO = 128.  kSwap exchanges the two fields to test the other reading of the descriptor.
+template <int M, int N, int R, bool kSwap, int kMode = 0>
+__global__ void __launch_bounds__(128) probe_mn(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D, int* status) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* Ahi = smem;                       // M x R
+    uint8_t* Alo = Ahi + M * R * 4;
+    uint8_t* Bhi = Alo + M * R * 4;            // N x R
+    uint8_t* Blo = Bhi + N * R * 4;
+    __shared__ uint64_t mbar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"(N < 32 ? 32 : N) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&mbar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // kMode 1: SWIZZLE_128B_BASE32B, "the only available smem layout for MN-major tf32 operands" (CUTLASS sm100_common.inl:92):
+    // atom = 32 MN elements (128 B) x 4 K rows 128 B apart, 32-byte chunk index XOR (K row % 4)  [Swizzle<2,5,2> on bytes];
+    // K groups of 4 rows 512 B apart, MN groups of 32 elements (R/4)*512 B apart
+    auto off = [](int mn, int r) {
+        if (kMode == 0) return (uint32_t)((mn >> 2) * (R / 8) * 128 + (r >> 3) * 128 + (r & 7) * 16 + (mn & 3) * 4);
+        const int g = mn >> 5, c32 = (mn & 31) >> 3, w = mn & 7;
+        return (uint32_t)(g * (R / 4) * 512 + (r >> 2) * 512 + (r & 3) * 128 + ((c32 ^ (r & 3)) << 5) + w * 4);
+    };
+    for (int r = tid; r < R; r += 128) {
+        for (int m = 0; m < M; ++m) {
+            const float a = A[r * M + m];
+            const float ah = to_tf32(a);
+            *reinterpret_cast<float*>(Ahi + off(m, r)) = ah;
+            *reinterpret_cast<float*>(Alo + off(m, r)) = to_tf32(a - ah);
+        }
+        for (int n = 0; n < N; ++n) {
+            const float b = B[r * N + n];
+            const float bh = to_tf32(b);
+            *reinterpret_cast<float*>(Bhi + off(n, r)) = bh;
+            *reinterpret_cast<float*>(Blo + off(n, r)) = to_tf32(b - bh);
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base_s;
+    // a_major (bit 15) = b_major (bit 16) = 1: MN-major
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+    if (tid == 0) {
+        const uint32_t mn_stride = kMode == 0 ? (R / 8) * 128 : (R / 4) * 512, k_stride = kMode == 0 ? 128 : 512;
+        const uint32_t sbo = kSwap ? mn_stride : k_stride, lbo = kSwap ? k_stride : mn_stride;
+        const uint64_t lt = kMode == 0 ? 0ull : (1ull << 61);        // layout_type 1 = SWIZZLE_128B_BASE32B
+        int first = 1;
+        for (int ks = 0; ks < R / 8; ++ks) {
+            const uint32_t koff = ks * (kMode == 0 ? 128 : 1024);      // next 8 K rows
+            const uint64_t ah = make_desc(smem_u32(Ahi) + koff, lbo, sbo) | lt, al = make_desc(smem_u32(Alo) + koff, lbo, sbo) | lt;
+            const uint64_t bh = make_desc(smem_u32(Bhi) + koff, lbo, sbo) | lt, bl = make_desc(smem_u32(Blo) + koff, lbo, sbo) | lt;
+            auto mma = [&](uint64_t da, uint64_t db) {
+                const uint32_t acc = first ? 0u : 1u;
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                             "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                             :: "r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+                first = 0;
+            };
+            mma(al, bh); mma(ah, bl); mma(ah, bh);
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&mbar)) : "memory");
+    }
+    {
+        uint32_t done = 0;
+        long long spins = 0;
+        while (!done) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(smem_u32(&mbar)), "r"(0u) : "memory");
+            if (++spins > 20000000LL) { if (tid == 0) *status = 1; break; }
+        }
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    for (int c0 = 0; c0 < N; c0 += 8) {
+        uint32_t v[8];
+        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + c0;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]));
+        for (int j = 0; j < 8; ++j) D[tid * N + c0 + j] = __uint_as_float(v[j]);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(N < 32 ? 32 : N) : "memory");
+}
+
+template <int M, int N, int R, bool kSwap, int kMode = 0>
+int run_mn(const char* name) {
+    std::vector<float> A(R * M), B(R * N), D(M * N);
+    srand(2);
+    for (auto& x : A) x = (rand() / (float)RAND_MAX - 0.5f) * 4.f;
+    for (auto& x : B) x = (rand() / (float)RAND_MAX - 0.5f) * 2.f;
+    float *dA, *dB, *dD; int* dS;
+    cudaMalloc(&dA, A.size() * 4); cudaMalloc(&dB, B.size() * 4); cudaMalloc(&dD, D.size() * 4); cudaMalloc(&dS, 4);
+    cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice); cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemset(dS, 0, 4); cudaMemset(dD, 0, D.size() * 4);
+    const size_t smem = (size_t)(M + N) * R * 4 * 2;
+    cudaFuncSetAttribute(probe_mn<M, N, R, kSwap, kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    probe_mn<M, N, R, kSwap, kMode><<<1, 128, smem>>>(dA, dB, dD, dS);
+    cudaError_t le = cudaGetLastError();
+    if (le != cudaSuccess) printf("  launch error: %s\n", cudaGetErrorString(le));
+    cudaError_t e = cudaDeviceSynchronize();
+    int st = 0;
+    cudaMemcpy(&st, dS, 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost);
+    double maxerr = 0, maxref = 0;
+    for (int m = 0; m < M; ++m)
+        for (int n = 0; n < N; ++n) {
+            double r = 0;
+            for (int k = 0; k < R; ++k) r += (double)A[k * M + m] * B[k * N + n];
+            maxerr = fmax(maxerr, fabs(r - D[m * N + n]));
+            maxref = fmax(maxref, fabs(r));
+        }
+    {
+        int nz = 0;
+        for (auto v : D) nz += v != 0.0f;
+        double r00 = 0, r01 = 0, r10 = 0;
+        for (int k = 0; k < R; ++k) { r00 += (double)A[k * M] * B[k * N]; r01 += (double)A[k * M] * B[k * N + 1]; r10 += (double)A[k * M + 1] * B[k * N]; }
+        printf("  nonzero %d of %d; D[0][0..1], D[1][0] = %.4f %.4f %.4f  ref %.4f %.4f %.4f\n", nz, M * N, D[0], D[1], D[N], r00, r01, r10);
+    }
+    printf("%s mode=%d M=%d N=%d R=%d swap=%d: cuda=%s timeout=%d max_abs_err=%.3e (max |ref| %.2f) rel=%.2e\n", name, kMode, M, N, R, (int)kSwap,
+           cudaGetErrorString(e), st, maxerr, maxref, maxerr / maxref);
+    return e != cudaSuccess;
+}
+
 int main() {
     if (run<128, 64, false>("gemm1")) return 1;
     if (run<128, 64, true>("gemm1")) return 1;
@@ -241,5 +375,9 @@ int main() {
     if (run<64, 64, true>("node")) return 1;
     if (run<128, 64, true, true>("gemm1-ts")) return 1;
     if (run<64, 128, true, true>("gemm2-ts")) return 1;
+    if (run_mn<128, 64, 128, false>("outer-mn")) return 1;
+    if (run_mn<128, 64, 128, true>("outer-mn")) return 1;
+    if (run_mn<128, 64, 128, false, 1>("outer-mn")) return 1;
+    if (run_mn<128, 64, 128, true, 1>("outer-mn")) return 1;
     return 0;
 }
