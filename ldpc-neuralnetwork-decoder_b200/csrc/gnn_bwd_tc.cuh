@@ -373,11 +373,13 @@ __global__ void __launch_bounds__(kOuterThreads, 1) gnn_outer_tc_kernel(
     const uint32_t tmem = tmem_base_s;
     // a_major = b_major = MN (bits 15, 16), D = F32, A = B = TF32, N = 64, M = 128
     constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    // loader mapping: lane = (chunk_sub, row_sub): one warp instruction reads 64 contiguous bytes of 8 rows, and the 8
-    // lanes of a quarter warp write 8 consecutive rows of one chunk
-    const int row_sub = lane & 7, chunk_sub = lane >> 3;
-    const int qa = (warp & 7) * 4 + chunk_sub, ra0 = (warp >> 3) * 64 + row_sub;        // A: 32 chunks x 128 rows, 8 per thread
-    const int qb = (warp & 3) * 4 + chunk_sub, rb0 = (warp >> 2) * 32 + row_sub;        // B: 16 chunks x 128 rows, 4 per thread
+    // loader mapping: one warp instruction moves 4 rows x 128 contiguous bytes (8 chunks = one group of 32 MN elements);
+    // lane = (chunk pair, row % 4, chunk parity), so that the 8 lanes of a quarter warp (2 chunks x 4 rows) hit the 8
+    // distinct 16-byte slots ((chunk/2 ^ row%4) * 2 + chunk%2) of the swizzled 128-byte line: conflict-free stores
+    // (ncu on the first mapping, 8 rows x 1 chunk per quarter warp: 2-way conflicts, L1 83 % busy)
+    const int r3 = (lane >> 1) & 3, cq = (lane >> 3) * 2 + (lane & 1);
+    const int qa = (warp & 3) * 8 + cq, ra0 = (warp >> 2) * 32 + r3;                    // A: 4 octets x 32 row quads, 8 per thread
+    const int qb = (warp & 1) * 8 + cq, rb0 = (warp >> 1) * 16 + r3;                    // B: 2 octets x 32 row quads, 4 per thread
     const long long tiles = (rows + 127) / 128;
     float4 av[8], bv[4];
     float4 sa = make_float4(0.f, 0.f, 0.f, 0.f), sb = sa;
@@ -385,12 +387,12 @@ __global__ void __launch_bounds__(kOuterThreads, 1) gnn_outer_tc_kernel(
         const long long row0 = tile * 128;
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
-            const long long row = row0 + ra0 + it * 8;
+            const long long row = row0 + ra0 + it * 4;
             av[it] = (tile < tiles && row < rows) ? reinterpret_cast<const float4*>(A + (size_t)row * 2 * kH)[qa] : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
-            const long long row = row0 + rb0 + it * 8;
+            const long long row = row0 + rb0 + it * 4;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (tile < tiles && row < rows) {
                 v = reinterpret_cast<const float4*>(Bm + (size_t)row * kH)[qb];
@@ -412,7 +414,7 @@ __global__ void __launch_bounds__(kOuterThreads, 1) gnn_outer_tc_kernel(
         for (int it = 0; it < 8; ++it) {
             const float4 v = av[it];
             const float4 h = make_float4(tf32_trunc(v.x), tf32_trunc(v.y), tf32_trunc(v.z), tf32_trunc(v.w));
-            const uint32_t o = outer_off(qa, ra0 + it * 8);
+            const uint32_t o = outer_off(qa, ra0 + it * 4);
             *reinterpret_cast<float4*>(Ahi + o) = h;
             *reinterpret_cast<float4*>(Alo + o) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
             sa.x += v.x; sa.y += v.y; sa.z += v.z; sa.w += v.w;
@@ -421,7 +423,7 @@ __global__ void __launch_bounds__(kOuterThreads, 1) gnn_outer_tc_kernel(
         for (int it = 0; it < 4; ++it) {
             const float4 v = bv[it];
             const float4 h = make_float4(tf32_trunc(v.x), tf32_trunc(v.y), tf32_trunc(v.z), tf32_trunc(v.w));
-            const uint32_t o = outer_off(qb, rb0 + it * 8);
+            const uint32_t o = outer_off(qb, rb0 + it * 4);
             *reinterpret_cast<float4*>(Bhi + o) = h;
             *reinterpret_cast<float4*>(Blo + o) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
             sb.x += v.x; sb.y += v.y; sb.z += v.z; sb.w += v.w;
@@ -459,15 +461,15 @@ __global__ void __launch_bounds__(kOuterThreads, 1) gnn_outer_tc_kernel(
             for (int j = 0; j < 16; ++j) atomicAdd(dW + (size_t)m * stride_m + (size_t)(c0 + j) * stride_n, o[j]);
         }
     }
-    // column sums: lanes with the same chunk (row_sub = 0..7) first, then one atomic per chunk and warp
+    // column sums: the 4 lanes with the same chunk (row % 4 = 0..3) first, then one atomic per chunk and warp
 #pragma unroll
-    for (int s = 1; s < 8; s <<= 1) {
+    for (int s = 2; s < 8; s <<= 1) {
         sa.x += __shfl_xor_sync(0xffffffffu, sa.x, s); sa.y += __shfl_xor_sync(0xffffffffu, sa.y, s);
         sa.z += __shfl_xor_sync(0xffffffffu, sa.z, s); sa.w += __shfl_xor_sync(0xffffffffu, sa.w, s);
         sb.x += __shfl_xor_sync(0xffffffffu, sb.x, s); sb.y += __shfl_xor_sync(0xffffffffu, sb.y, s);
         sb.z += __shfl_xor_sync(0xffffffffu, sb.z, s); sb.w += __shfl_xor_sync(0xffffffffu, sb.w, s);
     }
-    if (row_sub == 0) {
+    if (r3 == 0) {
         if (csumA) red_add_v4(csumA + qa * 4, sa);
         if (csumB) red_add_v4(csumB + qb * 4, sb);
     }
