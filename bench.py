@@ -90,6 +90,9 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+ALL_CPUS = os.sched_getaffinity(0)          # before any rank-local binding (bind_to_gpu_numa_node)
+
+
 def cpu_baseline(workload, seconds=12.0):
     """The oracle port (faithful O(d^2) restatement of the reference loops, OpenMP over
     codewords) on a bounded sample of the same workload."""
@@ -113,7 +116,7 @@ def cpu_baseline(workload, seconds=12.0):
     return {"value": sample * K_INFO / dt / 1e9, "unit": "Gbit/s", "cores": threads, "kind": "port",
             "sample": f"{sample} codewords of the same workload (BG2 Z=32, {ITERS} it, snr_db {SNR_DB}), "
                       f"oracle/ldpc_oracle.c with {threads} OpenMP threads, {dt:.1f} s",
-            "codewords_per_s": sample / dt}
+            "codewords_per_s": sample / dt, "sample_codewords": sample}
 
 
 def run_reference(args):
@@ -124,18 +127,22 @@ def run_reference(args):
     from oracle import oracle
     oracle.build()
     per_step = max(4.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
-    vals = []
+    vals, step_ms = [], []
     base = None
     for i in range(args.warmup + args.steps):
         base = cpu_baseline(args.workload, seconds=per_step)
         if i >= args.warmup:
             vals.append(base["value"])
+            cw = base["value"] * 1e9 / K_INFO                          # codewords/s of this step's sample
+            step_ms.append(base["sample_codewords"] / cw * 1e3)
     v = sum(vals) / len(vals)
     base["value"] = v
     out = {"impl": "reference", "metric": "decoded info Gbit/s, 5G BG2 Z=32 10 iters", "value": v, "unit": "Gbit/s",
-           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": None,
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sum(step_ms) / len(step_ms),
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": workload_config(args, None), "cpu_baseline": base,
+           "config": dict(workload_config(args, base["sample_codewords"]),
+                          note="each step is a bounded sample of the workload on the host cores (rank 0 only)"),
+           "cpu_baseline": base,
            "e2e": {"value": v, "unit": "Gbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
 

@@ -146,3 +146,22 @@ def test_oracle_qpsk_generator_statistics():
     assert np.allclose(z - b, 2 * amp2 / np.float32(nv), rtol=1e-5)
     t = oracle.qpsk_llr(None, 4, 208, snr_db, seed=3, true_llr=True)
     assert np.allclose(t, z * np.sqrt(2), rtol=1e-6)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver times beside the GPU arm): one JSON line on rank 0 with the
+    contract's keys, runs without a GPU, and the other ranks print nothing."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads(out.stdout.strip().splitlines()[-1])
+    assert d["impl"] == "reference" and d["unit"] == "Gbit/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["ms_per_step"] > 0 and d["config"]["workload"].startswith("minsum_bg2_z32_it10")
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "sample" in d["cpu_baseline"]
+    assert d["e2e"] == {"value": d["value"], "unit": "Gbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    other = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                            "--warmup", "0"], capture_output=True, text=True, timeout=120, cwd=root, env=env)
+    assert other.returncode == 0 and other.stdout.strip() == ""
