@@ -189,6 +189,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1 << 20)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="size of the cpu_baseline sample")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -369,7 +370,7 @@ def main():
                                  "peak_source": peak_src}},
         }
         if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline(args.workload)
+            out["cpu_baseline"] = cpu_baseline(args.workload, seconds=args.cpu_seconds)
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -329,3 +329,20 @@ def test_bp_fast_path_inf_nan_and_frames():
         assert not hard[np.isnan(soft)].any()
         assert (hard.sum(axis=1) > 0).sum() == (o["hard"].sum(axis=1) > 0).sum()
         assert abs(int(hard.sum()) - int(o["hard"].sum())) <= 2
+
+
+def test_bench_line_contract_small_run():
+    """bench.py end to end on a small batch: the JSON line carries every key of the contract (the driver's run uses
+    the default 2^20-codeword batch; this guards the plumbing: events, e2e legs, clocks sampler, roofline, CPU arm)."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "3", "--warmup", "3", "--batch", "65536",
+                          "--e2e-steps", "1", "--cpu-seconds", "2"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-3000:]
+    d = json.loads(out.stdout.strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert k in d, k
+    assert d["value"] > 1.0 and d["gpu_launches"] >= 3 and d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0
+    assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(d["roofline"]) and 0 < d["roofline"]["frac"] <= 1.0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0 and d["fer"]["frames"] == 3 * 65536
