@@ -145,3 +145,49 @@ def test_training_step_gradients_match_reference_autograd(name, Z):
     opt.step()
     _, loss2 = dec(llr, conv.message_var_index, types, None, None, ground_truth=torch.zeros_like(llr))
     assert float(loss2.detach()) < float(loss.detach())
+
+
+_PATH_SCRIPT = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, sys.argv[1])
+import ldpc_b200
+from ldpc_b200 import _native
+from ldpc_b200.models import create_message_gnn_decoder
+from ldpc_b200.utils import QCCode
+code = QCCode.nr_2_0(32)
+torch.manual_seed(3)
+dec, _ = create_message_gnn_decoder(code, 3, 64, base_graph=code.base_matrix(), Z=32)
+dec = dec.cuda()
+B = 37                                              # 37 * 6304 messages: ragged last 128-row tile
+llr = torch.empty((B, code.N), dtype=torch.float32, device="cuda")
+_native.check(_native.lib().ldpc_awgn_llr(None, B, code.N, -1.0, 11, 0, _native.ptr(llr), None))
+gt = (torch.rand(B, code.N, device="cuda") > 0.5).float()
+probs, loss = dec(llr, None, None, None, None, ground_truth=gt)
+loss.backward()
+grad = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in dec.parameters()])
+np.savez(sys.argv[2], probs=probs.detach().cpu().numpy(), loss=float(loss), grad=grad.cpu().numpy())
+"""
+
+
+@pytest.mark.gpu
+def test_tensor_core_and_ffma_paths_agree(tmp_path):
+    """The tcgen05 kernels (forward pipeline, node kernel, data and weight gradients) against the fp32 FFMA kernels
+    (LDPC_GNN_FFMA=1, read once per process -> two subprocesses) on a ragged batch with random targets: probabilities
+    to 2e-5, loss to 1e-6 relative, every gradient entry to 2e-4 of the gradient's scale."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "run.py"
+    script.write_text(_PATH_SCRIPT)
+    res = {}
+    for tag, env in (("tc", {}), ("ffma", {"LDPC_GNN_FFMA": "1"})):
+        out = tmp_path / f"{tag}.npz"
+        p = subprocess.run([sys.executable, str(script), root, str(out)], capture_output=True, text=True, timeout=600,
+                           env=dict(os.environ, **env))
+        assert p.returncode == 0, p.stderr[-3000:]
+        res[tag] = np.load(out)
+    a, b = res["tc"], res["ffma"]
+    assert np.max(np.abs(a["probs"] - b["probs"])) <= 2e-5
+    assert abs(float(a["loss"]) - float(b["loss"])) <= 1e-6 * abs(float(b["loss"]))
+    scale = np.max(np.abs(b["grad"]))
+    assert scale > 0 and np.max(np.abs(a["grad"] - b["grad"])) <= 2e-4 * scale
+    assert np.array_equal(a["grad"] == 0, b["grad"] == 0)           # same parameters without gradient
