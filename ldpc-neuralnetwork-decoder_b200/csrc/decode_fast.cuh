@@ -27,8 +27,12 @@ inline int detect_fast_kind(const ldpc_code* c) {
     return 0;
 }
 
-inline bool fast_path_supports(const ldpc_code* c, int algo, int stop_mode, bool want_mask) {
-    return c->fast_kind != 0 && (algo == LDPC_ALGO_MINSUM || algo == LDPC_ALGO_BP) && stop_mode == LDPC_STOP_FIXED && !want_mask;
+// fixed iteration count: both compiled tables; per-codeword early exit: the Z = 32 table (one codeword per warp), hard
+// decisions / syndrome / iteration counts only (no soft output, no validity masks -- those stay on the exact kernel)
+inline bool fast_path_supports(const ldpc_code* c, int algo, int stop_mode, bool want_mask, bool want_soft) {
+    if (c->fast_kind == 0 || (algo != LDPC_ALGO_MINSUM && algo != LDPC_ALGO_BP) || want_mask) return false;
+    if (stop_mode == LDPC_STOP_FIXED) return true;
+    return stop_mode == LDPC_STOP_PER_CODEWORD && c->fast_kind == 1 && !want_soft;
 }
 
 // defined in fast_kernels.cu

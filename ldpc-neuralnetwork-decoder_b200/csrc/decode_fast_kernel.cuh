@@ -119,8 +119,13 @@ constexpr size_t fast_smem_bytes(int warps) {
     return (size_t)warps * ((LDPC_FAST_TMEM ? 0 : (BG::kCoreEdges + 3) / 4) + (BG::kCoreCols + 3) / 4) * 32 * sizeof(float4);
 }
 
-template <class BG, int kWarps, int kAlgo>
+// kEarly: per-codeword early exit (LDPC_STOP_PER_CODEWORD; one codeword per warp, i.e. Z = 32).  Every iteration then also
+// forms the hard decisions of the degree-1 columns and the syndrome of the new posteriors; a codeword stops after its
+// first valid iteration (traditional_decoders.py:102-106 / 255-258 applied per codeword, as the exact kernel does).
+// Outputs in this mode: hard decisions, syndrome_ok, iters_out (soft_out is served by the exact kernel).
+template <class BG, int kWarps, int kAlgo, bool kEarly = false>
 __global__ void __launch_bounds__(kWarps * 32, 1) decode_fast_kernel(const DecodeParams p) {
+    static_assert(!kEarly || BG::kZ == 32, "early exit needs one codeword per warp");
     constexpr int Z = BG::kZ, G = 32 / Z, NC = BG::kCoreCols, NX = BG::kExtCols, EC = BG::kCoreEdges;
     constexpr int EQ = (EC + 3) / 4;                      // message quads per lane
     constexpr int N = BG::kCols * Z, NW = (N + 31) / 32, NWR = (NW + Z - 1) / Z;
@@ -257,8 +262,12 @@ __global__ void __launch_bounds__(kWarps * 32, 1) decode_fast_kernel(const Decod
         };
         issue_group(IC<0>{});
 #endif
+        unsigned long long xneg_it = 0;        // kEarly: hard decisions of the degree-1 columns after this iteration
         auto iteration = [&](auto lastc) {
-            constexpr bool kLast = decltype(lastc)::value != 0;
+            // mode 0: plain; 1: last (posteriors of the degree-1 columns replace their LLR registers);
+            // 2: checked (kEarly): degree-1 hard decisions into xneg_it, LLR registers untouched
+            constexpr int kMode = decltype(lastc)::value;
+            constexpr bool kLast = kMode != 0;          // "compute the messages towards the degree-1 columns as well"
             float Tn[NC];
             int Kn[NC];
             float nv[EQ * 4];
@@ -392,9 +401,12 @@ __global__ void __launch_bounds__(kWarps * 32, 1) decode_fast_kernel(const Decod
                             Tn[c] = __fadd_rn(Tn[c], code ? 0.0f : t);
                             Kn[c] += code;
                         }
-                    } else if constexpr (kLast) {
+                    } else if constexpr (kMode == 1) {
                         constexpr int x = BG::slot[e];
                         Lx[x] = __fadd_rn(Lx[x], cn[k]);
+                    } else if constexpr (kMode == 2) {
+                        constexpr int x = BG::slot[e];
+                        xneg_it |= __fadd_rn(Lx[x], cn[k]) < 0.0f ? (1ull << x) : 0ull;
                     }
                 });
             });
@@ -406,11 +418,53 @@ __global__ void __launch_bounds__(kWarps * 32, 1) decode_fast_kernel(const Decod
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 #endif
 #if LDPC_FAST_TMEM == 2
-            if constexpr (!kLast) issue_group(IC<0>{});      // first row group of the next iteration
+            if constexpr (kMode != 1) issue_group(IC<0>{});  // first row group of the next iteration
 #endif
         };
-        for (int it = 1; it < p.iters; ++it) iteration(IC<0>{});
-        iteration(IC<1>{});
+        // parity checks of the current posteriors: core columns from Tc (BP: resolved), degree-1 columns from `xneg`
+        auto all_checks_ok = [&](unsigned long long xneg) -> bool {
+            unsigned hb[NC];
+            static_for<0, NC>([&](auto kc) {
+                constexpr int c = decltype(kc)::value;
+                if constexpr (kAlgo == LDPC_ALGO_BP && kEarly) hb[c] = bp_resolve(Tc[c], Kc[c]) < 0.0f ? 1u : 0u;
+                else hb[c] = Tc[c] < 0.0f ? 1u : 0u;
+            });
+            unsigned bad = 0;
+            static_for<0, BG::kRows>([&](auto ic) {
+                constexpr int i = decltype(ic)::value;
+                unsigned par = 0;
+                static_for<BG::row_ptr[i], BG::row_ptr[i + 1]>([&](auto ec) {
+                    constexpr int e = decltype(ec)::value;
+                    if constexpr (BG::kind[e] == 0) {
+                        constexpr int s = BG::shift[e], c = BG::slot[e];
+                        par ^= (s == 0) ? hb[c] : __shfl_sync(kFull, hb[c], lp[s], Z);
+                    } else {
+                        constexpr int x = BG::slot[e];
+                        par ^= (unsigned)(xneg >> x) & 1u;
+                    }
+                });
+                bad |= par;
+            });
+            const unsigned m = __ballot_sync(kFull, bad != 0);
+            const unsigned gmask = (Z == 32) ? kFull : (((1u << (Z & 31)) - 1u) << (cwi * Z));
+            return (m & gmask) == 0;
+        };
+        int iters_done = p.iters;
+        bool early_ok = false;
+        if constexpr (kEarly) {
+            for (iters_done = 1;; ++iters_done) {
+                xneg_it = 0;
+                iteration(IC<2>{});
+                early_ok = all_checks_ok(xneg_it);
+                if (early_ok || iters_done >= p.iters) break;
+            }
+#if LDPC_FAST_TMEM == 2
+            settle_group(IC<0>{});                             // the loads issued for an iteration that does not run
+#endif
+        } else {
+            for (int it = 1; it < p.iters; ++it) iteration(IC<0>{});
+            iteration(IC<1>{});
+        }
         if constexpr (kAlgo == LDPC_ALGO_BP)
             static_for<0, NC>([&](auto kc) { Tc[decltype(kc)::value] = bp_resolve(Tc[decltype(kc)::value], Kc[decltype(kc)::value]); });
 
@@ -421,7 +475,13 @@ __global__ void __launch_bounds__(kWarps * 32, 1) decode_fast_kernel(const Decod
             if constexpr (BG::col_kind[j] == 0) return Tc[sl];
             else return Lx[sl];
         };
-        if (p.soft_out && live) {
+        auto neg_of = [&](auto jc) -> bool {                  // hard decision of column block j at this lane
+            constexpr int j = decltype(jc)::value, sl = BG::col_slot[j];
+            if constexpr (BG::col_kind[j] == 0) return Tc[sl] < 0.0f;
+            else if constexpr (kEarly) return ((xneg_it >> sl) & 1ull) != 0;
+            else return Lx[sl] < 0.0f;
+        };
+        if (!kEarly && p.soft_out && live) {
             float* o = p.soft_out + cw * N + r;
             static_for<0, BG::kCols>([&](auto jc) { o[decltype(jc)::value * Z] = belief_of(jc); });
         }
@@ -432,7 +492,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) decode_fast_kernel(const Decod
                 for (int q = 0; q < NWR; ++q) hw[q] = 0;
                 static_for<0, BG::kCols>([&](auto jc) {
                     constexpr int j = decltype(jc)::value;
-                    const unsigned b = __ballot_sync(kFull, belief_of(jc) < 0.0f);
+                    const unsigned b = __ballot_sync(kFull, neg_of(jc));
                     constexpr int wj = (j * Z) >> 5, off = (j * Z) & 31;
                     const unsigned mine = (Z == 32) ? b : ((b >> (cwi * Z)) & ((1u << (Z & 31)) - 1u));
                     if (r == wj % Z) hw[wj / Z] |= mine << off;
@@ -445,39 +505,26 @@ __global__ void __launch_bounds__(kWarps * 32, 1) decode_fast_kernel(const Decod
             } else if (p.hard_dtype == LDPC_HARD_F32) {
                 if (live) {
                     float* o = (float*)p.hard_out + cw * N + r;
-                    static_for<0, BG::kCols>([&](auto jc) { o[decltype(jc)::value * Z] = belief_of(jc) < 0.0f ? 1.0f : 0.0f; });
+                    static_for<0, BG::kCols>([&](auto jc) { o[decltype(jc)::value * Z] = neg_of(jc) ? 1.0f : 0.0f; });
                 }
             } else {
                 if (live) {
                     uint8_t* o = (uint8_t*)p.hard_out + cw * N + r;
-                    static_for<0, BG::kCols>([&](auto jc) { o[decltype(jc)::value * Z] = belief_of(jc) < 0.0f ? 1 : 0; });
+                    static_for<0, BG::kCols>([&](auto jc) { o[decltype(jc)::value * Z] = neg_of(jc) ? 1 : 0; });
                 }
             }
         }
-        if (p.iters_out && live && r == 0) p.iters_out[cw] = p.iters;
+        if (p.iters_out && live && r == 0) p.iters_out[cw] = iters_done;
         if (p.syndrome_ok || p.counters) {
             unsigned long long xneg = 0;      // hard decisions of the degree-1 columns
-            static_for<0, NX>([&](auto xc) { xneg |= Lx[decltype(xc)::value] < 0.0f ? (1ull << decltype(xc)::value) : 0ull; });
-            unsigned bad = 0;
-            static_for<0, BG::kRows>([&](auto ic) {
-                constexpr int i = decltype(ic)::value;
-                unsigned par = 0;
-                static_for<BG::row_ptr[i], BG::row_ptr[i + 1]>([&](auto ec) {
-                    constexpr int e = decltype(ec)::value;
-                    if constexpr (BG::kind[e] == 0) {
-                        constexpr int s = BG::shift[e], c = BG::slot[e];
-                        const unsigned b = Tc[c] < 0.0f ? 1u : 0u;
-                        par ^= (s == 0) ? b : __shfl_sync(kFull, b, lp[s], Z);
-                    } else {
-                        constexpr int x = BG::slot[e];
-                        par ^= (unsigned)(xneg >> x) & 1u;
-                    }
-                });
-                bad |= par;
-            });
-            const unsigned m = __ballot_sync(kFull, bad != 0);
-            const unsigned gmask = (Z == 32) ? kFull : (((1u << (Z & 31)) - 1u) << (cwi * Z));
-            const bool ok = (m & gmask) == 0;
+            bool ok;
+            if constexpr (kEarly) {
+                xneg = xneg_it;
+                ok = early_ok;
+            } else {
+                static_for<0, NX>([&](auto xc) { xneg |= Lx[decltype(xc)::value] < 0.0f ? (1ull << decltype(xc)::value) : 0ull; });
+                ok = all_checks_ok(xneg);
+            }
             if (p.syndrome_ok && live && r == 0) p.syndrome_ok[cw] = ok ? 1 : 0;
             if (p.counters) {
                 // all-zero codeword was sent: every negative posterior is a bit error

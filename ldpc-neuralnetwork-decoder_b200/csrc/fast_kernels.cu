@@ -11,12 +11,12 @@ namespace ldpc {
 #endif
 constexpr int kFastWarps = LDPC_FAST_WARPS;
 
-template <class BG, int kAlgo>
+template <class BG, int kAlgo, bool kEarly = false>
 inline int launch_fast_inst(DecodeParams p, cudaStream_t st) {
     constexpr int G = 32 / BG::kZ;
     constexpr size_t smem = fast_smem_bytes<BG>(kFastWarps);
     static_assert(smem <= (size_t)kMaxSmemPerBlock, "fast kernel shared memory");
-    auto kern = decode_fast_kernel<BG, kFastWarps, kAlgo>;
+    auto kern = decode_fast_kernel<BG, kFastWarps, kAlgo, kEarly>;
     LDPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     p.ngroups = (p.B + G - 1) / G;
     long long blocks = (p.ngroups + kFastWarps - 1) / kFastWarps;
@@ -35,6 +35,11 @@ inline int launch_fast_inst(DecodeParams p, cudaStream_t st) {
 }
 
 int launch_fast(const ldpc_code* c, int algo, const DecodeParams& p, cudaStream_t st) {
+    if (p.stop_mode == LDPC_STOP_PER_CODEWORD) {
+        if (c->fast_kind == 1 && algo == LDPC_ALGO_MINSUM) return launch_fast_inst<BG2Z32, LDPC_ALGO_MINSUM, true>(p, st);
+        if (c->fast_kind == 1 && algo == LDPC_ALGO_BP) return launch_fast_inst<BG2Z32, LDPC_ALGO_BP, true>(p, st);
+        return fail(LDPC_ERR_UNSUPPORTED, "fast path: per-codeword early exit is compiled for the Z = 32 table only");
+    }
     if (algo == LDPC_ALGO_MINSUM) {
         if (c->fast_kind == 1) return launch_fast_inst<BG2Z32, LDPC_ALGO_MINSUM>(p, st);
         if (c->fast_kind == 2) return launch_fast_inst<BG2Z4, LDPC_ALGO_MINSUM>(p, st);

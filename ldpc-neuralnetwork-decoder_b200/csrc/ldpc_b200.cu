@@ -64,7 +64,7 @@ int decode_common(const ldpc_code_t* code, int algo, const float* llr, int64_t B
     p.llr = llr; p.B = B; p.iters = iters; p.alpha = alpha; p.stop_mode = stop_mode;
     p.soft_out = soft_out; p.hard_out = hard_out; p.hard_dtype = hard_dtype; p.syndrome_ok = syndrome_ok;
     p.iters_out = iters_out; p.valid_mask = (unsigned long long*)valid_mask; p.mask_words = mask_words;
-    const bool fast_ok = fast_path_supports(code, algo, stop_mode, valid_mask != nullptr);
+    const bool fast_ok = fast_path_supports(code, algo, stop_mode, valid_mask != nullptr, soft_out != nullptr);
     if (path == LDPC_PATH_FAST && !fast_ok)
         return fail(LDPC_ERR_UNSUPPORTED, "decode: no specialised kernel for this code/algorithm/stop mode");
     // AUTO: min-sum takes the specialised kernel (hard decisions identical to the reference on every fixture);
@@ -138,7 +138,7 @@ int ldpc_code_info(const ldpc_code_t* c, int32_t info[8]) {
 
 int ldpc_code_has_fast_path(const ldpc_code_t* code, int algo) {
     if (!code) return 0;
-    return fast_path_supports(code, algo, LDPC_STOP_FIXED, false) ? 1 : 0;
+    return fast_path_supports(code, algo, LDPC_STOP_FIXED, false, false) ? 1 : 0;
 }
 
 int ldpc_minsum_decode(const ldpc_code_t* code, const float* llr, int64_t B, int iters, float alpha, int stop_mode,
@@ -331,7 +331,7 @@ int ldpc_sim_fer(const ldpc_code_t* code, int algo, int iters, float alpha, floa
     p.B = (long long)n_frames; p.iters = iters; p.alpha = alpha; p.stop_mode = LDPC_STOP_FIXED;
     p.counters = (unsigned long long*)counters;
     make_gen(snr_db, seed, first_frame, &p.gen);
-    if (fast_path_supports(code, algo, LDPC_STOP_FIXED, false)) return launch_fast(code, algo, p, (cudaStream_t)stream);
+    if (fast_path_supports(code, algo, LDPC_STOP_FIXED, false, false)) return launch_fast(code, algo, p, (cudaStream_t)stream);
     return launch_exact(code, algo, p, (cudaStream_t)stream);
 }
 

@@ -92,25 +92,51 @@ class _FloodingDecoder:
         idx = torch.nonzero(ok)
         return int(idx[0]) if idx.numel() else None
 
-    def _decode_full(self, llr):
+    def _fast_early_allowed(self):
+        """The specialised early-exit kernel may replace the exact validity-mask pass: path "auto" for min-sum,
+        "fast" for either algorithm (the same policy as for fixed iteration counts); never for path "exact"."""
+        if self.path == "exact":
+            return False
+        return self.path == "fast" or self._ALGO == _native.ALGO_MINSUM
+
+    def _decode_full(self, llr, soft=True):
+        """Batch-global early stopping of the reference (:102-106 / :255-258): stop after the first iteration T at
+        which EVERY codeword of the batch is valid; return the state after T iterations (T = max_iterations if none).
+
+        Fast route (Z = 32 tables): (A) per-codeword early exit on the specialised kernel gives each codeword's first
+        valid iteration; T0 = their maximum is a lower bound of T, and T = max_iterations if a codeword never
+        converges.  (B) T0 iterations for the whole batch; if every codeword is valid then, T = T0 exactly.  Only if
+        a codeword has left the code again in between (not observed) the exact validity-mask pass decides."""
         llr_d, dev = self._prepare(llr)
         iters = self.max_iterations
         if self.early_stopping and llr_d.shape[0] > 0:
-            soft, hard, _, _, mask = self._launch(llr_d, dev, iters, mask=True)
+            if self._fast_early_allowed():
+                try:
+                    _, _, syn, its, _ = self._launch(llr_d, dev, iters, stop_mode=_native.STOP_PER_CODEWORD, soft=False,
+                                                     hard_dtype=_native.HARD_PACKED, syndrome=True, iters_out=True, path="fast")
+                except _native.LdpcError as e:
+                    if e.code != _native.ERR_UNSUPPORTED:
+                        raise
+                else:
+                    t0 = int(torch.where(syn.bool().all(), its.max(), torch.tensor(iters, dtype=its.dtype, device=dev)))
+                    soft_t, hard, syn2, _, _ = self._launch(llr_d, dev, t0, soft=soft, syndrome=True, path="fast")
+                    if t0 == iters or bool(syn2.all()):
+                        return (soft_t.to(llr.device) if soft else None), hard.to(llr.device), t0
+            soft_t, hard, _, _, mask = self._launch(llr_d, dev, iters, mask=True)
             t = self._first_all_valid(mask, iters)
             if t is not None and t + 1 < iters:
                 iters = t + 1
-                soft, hard, _, _, _ = self._launch(llr_d, dev, iters)
+                soft_t, hard, _, _, _ = self._launch(llr_d, dev, iters)
             elif t is not None:
                 iters = t + 1
         else:
-            soft, hard, _, _, _ = self._launch(llr_d, dev, iters)
-        return soft.to(llr.device), hard.to(llr.device), iters
+            soft_t, hard, _, _, _ = self._launch(llr_d, dev, iters, soft=soft)
+        return (soft_t.to(llr.device) if soft_t is not None else None), hard.to(llr.device), iters
 
     # ---- reference API -------------------------------------------------------------------
     def decode(self, llr):
         """(decoded_bits float32 (B,N), num_iterations int), as the reference."""
-        _, hard, iters = self._decode_full(llr)
+        _, hard, iters = self._decode_full(llr, soft=False)
         return hard, iters
 
     # ---- added API -----------------------------------------------------------------------

@@ -346,3 +346,53 @@ def test_bench_line_contract_small_run():
     assert d["value"] > 1.0 and d["gpu_launches"] >= 3 and d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0
     assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(d["roofline"]) and 0 < d["roofline"]["frac"] <= 1.0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0 and d["fer"]["frames"] == 3 * 65536
+
+
+@pytest.mark.parametrize("algo", ["minsum", "bp"])
+def test_fast_kernel_per_codeword_early_exit(algo):
+    """The specialised kernel's early-exit variant (Z = 32): every codeword stops after its first valid iteration.
+    Hard decisions, iteration counts and the syndrome flag equal the oracle run with the same stopping rule (min-sum:
+    in the fast kernel's operation order), on a batch that mixes early, late and never-converging codewords."""
+    code = QCCode.nr_2_0(32)
+    B, iters = 301, 20
+    llr = np.concatenate([oracle.awgn_llr(None, 150, code.N, -3.6, seed=41), oracle.awgn_llr(None, 151, code.N, -1.0, seed=42)])
+    if algo == "minsum":
+        dec = MinSumScaledDecoder(code, iters, 0.75, early_stopping=True)                  # auto -> specialised kernel
+        o = oracle.decode(code.shifts, 32, llr, iters, "minsum", 0.75, order="fast", stop_when_valid=True)
+    else:
+        dec = BeliefPropagationDecoder(code, iters, early_stopping=True, path="fast")
+        o = oracle.decode(code.shifts, 32, llr, iters, "bp", 1.0, stop_when_valid=True)
+    bits, its, ok = dec.decode_with_iterations(torch.from_numpy(llr).to(dev()))
+    assert np.array_equal(its.cpu().numpy(), o["iters"])
+    assert np.array_equal(bits.cpu().numpy().astype(np.uint8), o["hard"])
+    valid = np.asarray(dec._check_valid_codeword(bits).cpu().numpy())
+    assert np.array_equal(ok.cpu().numpy(), valid)
+    assert 0 < int((its.cpu().numpy() < iters).sum()) and int((~valid).sum()) > 0          # the batch really is mixed
+    # the exact kernel (reference operation order) under the same rule: every codeword that converges does so at the same
+    # iteration with the same decisions; frames that never converge are chaotic (see fast_order_tolerance_ok) and their
+    # decisions after 20 iterations may differ between the two operation orders
+    ex = type(dec)(code, iters, early_stopping=True, path="exact", **({"scaling_factor": 0.75} if algo == "minsum" else {}))
+    bits_x, its_x, ok_x = ex.decode_with_iterations(torch.from_numpy(llr).to(dev()))
+    assert torch.equal(ok_x, ok)
+    assert torch.equal(its_x[ok_x], its[ok_x]) and torch.equal(bits_x[ok_x], bits[ok_x])
+
+
+def test_batch_global_early_stopping_fast_route():
+    """decode() with the reference's batch-global rule on the specialised kernels (two passes) == the exact
+    validity-mask route, for a batch that converges (stop = slowest codeword) and one that does not (stop = max)."""
+    code = QCCode.nr_2_0(32)
+    for snr, seed in ((0.0, 7), (-3.6, 8)):
+        llr = torch.from_numpy(oracle.awgn_llr(None, 96, code.N, snr, seed=seed)).to(dev())
+        fast = MinSumScaledDecoder(code, 30, 0.75, early_stopping=True)
+        exact = MinSumScaledDecoder(code, 30, 0.75, early_stopping=True, path="exact")
+        bf, tf = fast.decode(llr)
+        bx, tx = exact.decode(llr)
+        conv_t = exact._check_valid_codeword(bx)
+        assert tf == tx and torch.equal(bf[conv_t], bx[conv_t])              # never-converging frames: chaotic, see above
+        assert (tf < 30) == (snr == 0.0) and (snr != 0.0 or bool(conv_t.all()))
+        sf, hf = fast.forward(llr)
+        sx, hx = exact.forward(llr)
+        conv = np.asarray(conv_t.cpu().numpy())
+        assert torch.equal(hf[conv_t], hx[conv_t])
+        if snr == 0.0:       # quick convergence: the two operation orders stay within the fast path's soft tolerance
+            assert fast_order_tolerance_ok(sf.cpu().numpy(), sx.cpu().numpy(), conv)
