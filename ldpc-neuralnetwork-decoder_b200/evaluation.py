@@ -26,9 +26,11 @@ from .utils.channel import QPSKChannel, compute_ber_fer, count_errors
 
 class ComparativeEvaluator:
     def __init__(self, H=None, neural_decoder=None, device="cuda", base_graph=None, Z=None, seed=0, channel=None,
-                 max_iterations=50, scaling_factor=0.75):
+                 max_iterations=50, scaling_factor=0.75, path="auto"):
         """`H` (dense parity-check matrix, factored into QC shifts) or `(base_graph, Z)`.  `channel`: any object with
-        `transmit(bits, snr_db) -> llrs`; default `QPSKChannel(seed)` with the reference's LLR scaling."""
+        `transmit(bits, snr_db) -> llrs`; default `QPSKChannel(seed)` with the reference's LLR scaling.  `path`: kernel
+        policy of both classic decoders ("auto": specialised kernels for min-sum, exact kernel for BP; "fast": specialised
+        kernels for both -- BP then uses CUDA's tanhf/atanhf instead of once-rounded double evaluation; "exact")."""
         if not torch.cuda.is_available() and channel is None:
             raise RuntimeError("the LDPC engine needs a CUDA device (no CPU fallback)")
         self.device = torch.device(device)
@@ -38,9 +40,9 @@ class ComparativeEvaluator:
             neural_decoder.to(self.device)
             neural_decoder.eval()
         self.bp_decoder = BeliefPropagationDecoder(H, max_iterations=max_iterations, early_stopping=True,
-                                                   base_graph=base_graph, Z=Z)
+                                                   base_graph=base_graph, Z=Z, path=path)
         self.ms_decoder = MinSumScaledDecoder(H, max_iterations=max_iterations, scaling_factor=scaling_factor,
-                                              early_stopping=True, base_graph=base_graph, Z=Z)
+                                              early_stopping=True, base_graph=base_graph, Z=Z, path=path)
         self.channel = channel if channel is not None else QPSKChannel(seed=seed)
         self.results = {}
 
