@@ -93,11 +93,17 @@ __device__ __forceinline__ void umma_gemm3_ts(uint32_t d_tmem, uint32_t a_hi, ui
 // hi = x with the 13 low mantissa bits cleared (a TF32 value), lo = x - hi (exact; the tensor core reads its top 19
 // bits).  Truncation instead of cvt.rna costs 2 instructions per element instead of 8 (cvt.rna.tf32.f32 expands to
 // FSETP + VIADD + SEL + LOP3 on sm_100) and keeps the 3xTF32 product error at ~2^-20 relative.
+#ifndef GNN_LO_ROUND
+#define GNN_LO_ROUND 1
+#endif
+// the tensor core reads only the top 19 bits of lo: scaling lo by (1 + 2^-11) first turns that truncation into
+// round-to-nearest (removes the systematic towards-zero bias of the lo term) for one FMUL
+constexpr float kLoRound = GNN_LO_ROUND ? 1.00048828125f : 1.0f;
 __device__ __forceinline__ void split16(const float (&v)[16], uint32_t (&hi)[16], uint32_t (&lo)[16]) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         hi[i] = __float_as_uint(v[i]) & 0xffffe000u;
-        lo[i] = __float_as_uint(v[i] - __uint_as_float(hi[i]));
+        lo[i] = __float_as_uint((v[i] - __uint_as_float(hi[i])) * kLoRound);
     }
 }
 
@@ -218,7 +224,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) gnn_edge_pipe_kernel(
                             for (int i = 0; i < 4; ++i) {
                                 const float v = fmaxf(__uint_as_float(hh[q * 4 + i]) + add[i], 0.f);
                                 hh[q * 4 + i] = __float_as_uint(v) & 0xffffe000u;
-                                lo[q * 4 + i] = __float_as_uint(v - __uint_as_float(hh[q * 4 + i]));
+                                lo[q * 4 + i] = __float_as_uint((v - __uint_as_float(hh[q * 4 + i])) * kLoRound);
                             }
                         }
                         tmem_st16(tmem + lane_base + kTmHHi + col + cofs, hh);
