@@ -110,18 +110,21 @@ class _FloodingDecoder:
         llr_d, dev = self._prepare(llr)
         iters = self.max_iterations
         if self.early_stopping and llr_d.shape[0] > 0:
-            if self._fast_early_allowed():
+            # two exact passes (docstring), on the specialised kernels where they exist and the policy allows them,
+            # otherwise on the exact kernel -- either way far fewer iterations than a max_iterations-long mask pass
+            for route in (["fast"] if self._fast_early_allowed() else []) + [self.path]:
                 try:
                     _, _, syn, its, _ = self._launch(llr_d, dev, iters, stop_mode=_native.STOP_PER_CODEWORD, soft=False,
-                                                     hard_dtype=_native.HARD_PACKED, syndrome=True, iters_out=True, path="fast")
+                                                     hard_dtype=_native.HARD_PACKED, syndrome=True, iters_out=True, path=route)
                 except _native.LdpcError as e:
                     if e.code != _native.ERR_UNSUPPORTED:
                         raise
-                else:
-                    t0 = int(torch.where(syn.bool().all(), its.max(), torch.tensor(iters, dtype=its.dtype, device=dev)))
-                    soft_t, hard, syn2, _, _ = self._launch(llr_d, dev, t0, soft=soft, syndrome=True, path="fast")
-                    if t0 == iters or bool(syn2.all()):
-                        return (soft_t.to(llr.device) if soft else None), hard.to(llr.device), t0
+                    continue
+                t0 = int(torch.where(syn.bool().all(), its.max(), torch.tensor(iters, dtype=its.dtype, device=dev)))
+                soft_t, hard, syn2, _, _ = self._launch(llr_d, dev, t0, soft=soft, syndrome=True, path=route)
+                if t0 == iters or bool(syn2.all()):
+                    return (soft_t.to(llr.device) if soft else None), hard.to(llr.device), t0
+                break
             soft_t, hard, _, _, mask = self._launch(llr_d, dev, iters, mask=True)
             t = self._first_all_valid(mask, iters)
             if t is not None and t + 1 < iters:
