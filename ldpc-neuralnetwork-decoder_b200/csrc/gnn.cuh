@@ -304,6 +304,26 @@ __global__ void __launch_bounds__(256) gnn_readout_kernel(const float* __restric
     }
 }
 
+// Readout from per-message projections dec[b][e] = <x_L[e], w_out> (written by the last edge kernel, gnn_tc_pipe.cuh):
+// soft[b][v] = llr + sum_{e in v} (dec[e] + b_out)   (message_gnn_decoder.py:289-301)
+__global__ void __launch_bounds__(256) gnn_readout_sum_kernel(const float* __restrict__ dec, const float* __restrict__ params,
+                                                               GnnLayout lay, int last_layer, const float* __restrict__ llr,
+                                                               const int* __restrict__ var_ptr, const int* __restrict__ var_edge,
+                                                               long long B, int E, int N, float* __restrict__ soft_out,
+                                                               float* __restrict__ prob_out) {
+    const float bias = params[lay.out_b(last_layer)];
+    const long long total = B * N;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int v = (int)(t % N);
+        const long long b = t / N;
+        float s = 0.0f;
+        for (int q = var_ptr[v]; q < var_ptr[v + 1]; ++q) s += dec[(size_t)b * E + var_edge[q]] + bias;
+        s += llr[t];
+        if (soft_out) soft_out[t] = s;
+        if (prob_out) prob_out[t] = 1.0f / (1.0f + expf(-s));
+    }
+}
+
 inline int gnn_grid(long long items, int threads) {
     long long g = (items + threads - 1) / threads;
     const long long cap = (long long)kNumSMs * 16;

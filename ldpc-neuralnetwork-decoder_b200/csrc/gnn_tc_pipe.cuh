@@ -125,7 +125,10 @@ __global__ void __launch_bounds__(kPipeThreads, 1) gnn_edge_pipe_kernel(
     const float* __restrict__ x, const float* __restrict__ emb_l, const float* __restrict__ packed_l, const float* __restrict__ tc_l,
     const int* __restrict__ edge_var, const int* __restrict__ edge_chk, const int* __restrict__ edge_type,
     const float* __restrict__ Pv, const float* __restrict__ Pc, long long B, int E, int N, int M, float* __restrict__ y,
-    int* __restrict__ status) {
+    const float* __restrict__ w_out, float* __restrict__ dec_out, int* __restrict__ status) {
+    // dec_out != nullptr (last layer, inference): the output projection of the readout (MessageGNNDecoder.decode_messages,
+    // message_gnn_decoder.py:46-47) is applied to the finished rows here -- dec_out[row] = <y_row, w_out> -- and y itself is
+    // not written: saves the 256-byte row store and its re-read by the readout kernel.
     extern __shared__ __align__(1024) uint8_t tc_smem[];
     uint8_t* W1Ahi = tc_smem;                               // [128 x 64]
     uint8_t* W1Alo = W1Ahi + 128 * 64 * 4;
@@ -174,6 +177,9 @@ __global__ void __launch_bounds__(kPipeThreads, 1) gnn_edge_pipe_kernel(
         const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
         const int cc = tid & 15, cr0 = tid >> 4;                             // cooperative mapping of the y store
         const float4 bias = *reinterpret_cast<const float4*>(b2s + cc * 4);  // b2 of the 4 output columns this thread stores
+        // (scalar loads: the flat parameter vector gives w_out no 16-byte alignment)
+        const float4 wo = dec_out ? make_float4(__ldg(w_out + cc * 4), __ldg(w_out + cc * 4 + 1), __ldg(w_out + cc * 4 + 2), __ldg(w_out + cc * 4 + 3))
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
         auto convert = [&]() {                                               // C: Sx -> comb hi/lo in TMEM, my 32 columns
 #pragma unroll
             for (int c0 = 0; c0 < kPipeCw; c0 += 16) {
@@ -288,7 +294,14 @@ __global__ void __launch_bounds__(kPipeThreads, 1) gnn_edge_pipe_kernel(
                 float4 r = *stage_ptr(Sx, rr, cc);
                 r.x += bias.x; r.y += bias.y; r.z += bias.z; r.w += bias.w;
                 if constexpr (kResidual) { r.x += xv[it].x; r.y += xv[it].y; r.z += xv[it].z; r.w += xv[it].w; }
-                if (row0 + rr < rows) reinterpret_cast<float4*>(y + (size_t)(row0 + rr) * kH)[cc] = r;
+                if (dec_out) {                                           // warp-uniform
+                    float d = __fmaf_rn(r.w, wo.w, __fmaf_rn(r.z, wo.z, __fmaf_rn(r.y, wo.y, r.x * wo.x)));
+#pragma unroll
+                    for (int sft = 8; sft > 0; sft >>= 1) d += __shfl_xor_sync(0xffffffffu, d, sft);   // the 16 lanes of this row
+                    if (cc == 0 && row0 + rr < rows) dec_out[row0 + rr] = d;
+                } else if (row0 + rr < rows) {
+                    reinterpret_cast<float4*>(y + (size_t)(row0 + rr) * kH)[cc] = r;
+                }
             }
             warp_arrive(kBarFreeY);
             PIPE_TRACE(6);

@@ -585,6 +585,7 @@ int ldpc_gnn_forward(const ldpc_gnn_t* g, const float* params, const float* llr,
         float* pv = training ? base + tw.PV : xb + (size_t)bc * E * kH;
         float* pc = training ? base + tw.PC : pv + (size_t)bc * N * kH;
         const float* llr_c = llr + (size_t)b0 * N;
+        bool fused_readout = false;
         gnn_embed_kernel<<<gnn_grid(bc * E * (kH / 4), 256), 256, 0, st>>>(params, lay, llr_c, g->d_edge_var, bc, E, N, xa);
         LDPC_CHECK_LAUNCH("gnn_embed_kernel");
         for (int l = 0; l < g->layers; ++l) {
@@ -598,12 +599,16 @@ int ldpc_gnn_forward(const ldpc_gnn_t* g, const float* params, const float* llr,
                 gnn_node_tc_kernel<<<tc_grid(bc * M, 2), kNodeThreads, kNodeTcSmem, st>>>(
                     xa, em, pk, tcw, 1, g->d_chk_ptr, nullptr, g->d_edge_type, bc, E, M, pc, g->d_status);
                 LDPC_CHECK_LAUNCH("gnn_node_tc_kernel(chk)");
+                // inference: the last layer applies the readout projection itself and writes one float per message into xb
+                fused_readout = use_pipe && !training && l == g->layers - 1;
+                const float* wo = fused_readout ? params + lay.out_w(l) : nullptr;
+                float* dec = fused_readout ? xb : nullptr;
                 if (use_pipe && l == 0)
                     gnn_edge_pipe_kernel<false><<<tc_grid(bc * E, 1), kPipeThreads, kPipeSmem, st>>>(
-                        xa, em, pk, tcw, g->d_edge_var, g->d_edge_chk, g->d_edge_type, pv, pc, bc, E, N, M, xb, g->d_status);
+                        xa, em, pk, tcw, g->d_edge_var, g->d_edge_chk, g->d_edge_type, pv, pc, bc, E, N, M, xb, wo, dec, g->d_status);
                 else if (use_pipe)
                     gnn_edge_pipe_kernel<true><<<tc_grid(bc * E, 1), kPipeThreads, kPipeSmem, st>>>(
-                        xa, em, pk, tcw, g->d_edge_var, g->d_edge_chk, g->d_edge_type, pv, pc, bc, E, N, M, xb, g->d_status);
+                        xa, em, pk, tcw, g->d_edge_var, g->d_edge_chk, g->d_edge_type, pv, pc, bc, E, N, M, xb, wo, dec, g->d_status);
                 else if (l == 0)
                     gnn_edge_tc_kernel<false><<<tc_grid(bc * E, 1), kEdgeThreads, kEdgeTcSmem, st>>>(
                         xa, em, pk, tcw, g->d_edge_var, g->d_edge_chk, g->d_edge_type, pv, pc, bc, E, N, M, xb, g->d_status);
@@ -630,10 +635,17 @@ int ldpc_gnn_forward(const ldpc_gnn_t* g, const float* params, const float* llr,
             else { float* tmp = xa; xa = xb; xb = tmp; }
         }
         float* soft_dst = training ? base + tw.SOFT : (soft_out ? soft_out + (size_t)b0 * N : nullptr);
-        gnn_readout_kernel<<<gnn_grid(bc * N, 256), 256, 0, st>>>(
-            xa, params, lay, g->layers - 1, llr_c, g->d_var_ptr, g->d_var_edge, bc, E, N, soft_dst,
-            prob_out ? prob_out + (size_t)b0 * N : nullptr);
-        LDPC_CHECK_LAUNCH("gnn_readout_kernel");
+        if (fused_readout) {
+            gnn_readout_sum_kernel<<<gnn_grid(bc * N, 256), 256, 0, st>>>(
+                xa, params, lay, g->layers - 1, llr_c, g->d_var_ptr, g->d_var_edge, bc, E, N, soft_dst,
+                prob_out ? prob_out + (size_t)b0 * N : nullptr);
+            LDPC_CHECK_LAUNCH("gnn_readout_sum_kernel");
+        } else {
+            gnn_readout_kernel<<<gnn_grid(bc * N, 256), 256, 0, st>>>(
+                xa, params, lay, g->layers - 1, llr_c, g->d_var_ptr, g->d_var_edge, bc, E, N, soft_dst,
+                prob_out ? prob_out + (size_t)b0 * N : nullptr);
+            LDPC_CHECK_LAUNCH("gnn_readout_kernel");
+        }
         if (training && soft_out)
             LDPC_CUDA(cudaMemcpyAsync(soft_out, soft_dst, sizeof(float) * (size_t)B * N, cudaMemcpyDeviceToDevice, st));
     }
