@@ -478,4 +478,105 @@ __global__ void __launch_bounds__(kOuterThreads, 1) gnn_outer_tc_kernel(
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" :: "r"(tmem) : "memory");
 }
 
+// ---- node backward on the tensor cores: dm[row][:] = (dP[row][:] . W1B) / deg(node) -------------------------------
+// (the node means themselves were saved by the training forward, gnn_node_tc_kernel's Msave, so no gather is repeated)
+__global__ void __launch_bounds__(kNodeThreads, 2) gnn_node_dm_tc_kernel(const float* __restrict__ dP, const float* __restrict__ tc_l,
+                                                                        int kind, const int* __restrict__ ptr, long long rows,
+                                                                        int nodes, float* __restrict__ DMout, int* __restrict__ status) {
+    extern __shared__ __align__(1024) uint8_t tc_smem[];
+    uint8_t* Whi = tc_smem;                                 // W1B transposed [64 x 64]
+    uint8_t* Wlo = Whi + 64 * 64 * 4;
+    uint8_t* S = Wlo + 64 * 64 * 4;
+    __shared__ uint64_t mbar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int rowi = tid & 127, part = tid >> 7;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" :: "r"(smem_u32(&tmem_base_s)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&mbar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    {
+        const float4* src = reinterpret_cast<const float4*>(tc_l + (kind == 0 ? kTcW1BVT : kTcW1BCT));
+        float4* dst = reinterpret_cast<float4*>(tc_smem);
+        for (int t = tid; t < 2 * 64 * 64 / 4; t += kNodeThreads) dst[t] = src[t];
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base_s;
+    const uint32_t my_lane = ((uint32_t)((warp & 3) * 32)) << 16;
+    constexpr uint32_t kIdesc64 = umma_idesc_tf32(64);
+    uint32_t phase = 0;
+    bool ok = true;
+    const long long tiles = (rows + 127) / 128;
+    const int cc = tid & 15, cr0 = tid >> 4;
+    constexpr int kCoop = 128 * 16 / kNodeThreads, kStep = kNodeThreads / 16;
+    for (long long tile = blockIdx.x; tile < tiles && ok; tile += gridDim.x) {
+        const long long row0 = tile * 128;
+        {
+            float4 v[kCoop];
+#pragma unroll
+            for (int it = 0; it < kCoop; ++it) {
+                const long long row = row0 + it * kStep + cr0;
+                v[it] = row < rows ? reinterpret_cast<const float4*>(dP + (size_t)row * kH)[cc] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int it = 0; it < kCoop; ++it) *stage_ptr(S, it * kStep + cr0, cc) = v[it];
+        }
+        __syncthreads();
+        {
+            float v[16];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 t = *stage_ptr(S, rowi, part * 4 + q);
+                v[q * 4] = t.x; v[q * 4 + 1] = t.y; v[q * 4 + 2] = t.z; v[q * 4 + 3] = t.w;
+            }
+            uint32_t hi[16], lo[16];
+            split16(v, hi, lo);
+            tmem_st16(tmem + my_lane + kTmNodeAHi + part * 16, hi);
+            tmem_st16(tmem + my_lane + kTmNodeALo + part * 16, lo);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            umma_gemm3_ts(tmem + kTmNodeD, tmem + kTmNodeAHi, tmem + kTmNodeALo, smem_u32(Whi), smem_u32(Wlo), 64, 2048, kIdesc64);
+            umma_commit(&mbar);
+        }
+        ok = mbar_wait(&mbar, phase); phase ^= 1;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (ok) {
+            const long long row = row0 + rowi;
+            float inv = 0.0f;
+            if (row < rows) { const int node = (int)(row % nodes); inv = 1.0f / (float)(ptr[node + 1] - ptr[node]); }
+            float o[16];
+            tmem_ld16(tmem + my_lane + kTmNodeD + part * 16, o);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                *stage_ptr(S, rowi, part * 4 + q) = make_float4(o[q * 4] * inv, o[q * 4 + 1] * inv, o[q * 4 + 2] * inv, o[q * 4 + 3] * inv);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (ok) {
+#pragma unroll
+            for (int it = 0; it < kCoop; ++it) {
+                const int rr = it * kStep + cr0;
+                if (row0 + rr < rows) reinterpret_cast<float4*>(DMout + (size_t)(row0 + rr) * kH)[cc] = *stage_ptr(S, rr, cc);
+            }
+        }
+        __syncthreads();
+    }
+    if (!ok) { if (tid == 0) atomicExch(status, 1); asm volatile("trap;"); }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" :: "r"(tmem) : "memory");
+}
+
 }  // namespace ldpc

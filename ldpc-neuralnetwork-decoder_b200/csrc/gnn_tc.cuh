@@ -111,7 +111,8 @@ __device__ __forceinline__ void put_chunk(uint8_t* hi, uint8_t* lo, int r, int c
 //            | W2T [128 x 64] hi, lo (W2 transposed: B operand of dH = G . W2) | W1AT [64 x 128] hi, lo (B operand of
 //              dcomb = dH . W1A) -- the two backward images (gnn_bwd_tc.cuh)
 constexpr int kTcW1A = 0, kTcW2 = kTcW1A + 2 * 128 * 64, kTcW1BV = kTcW2 + 2 * 64 * 128, kTcW1BC = kTcW1BV + 2 * 64 * 64,
-              kTcW2T = kTcW1BC + 2 * 64 * 64, kTcW1AT = kTcW2T + 2 * 128 * 64, kTcPerLayer = kTcW1AT + 2 * 64 * 128;
+              kTcW2T = kTcW1BC + 2 * 64 * 64, kTcW1AT = kTcW2T + 2 * 128 * 64, kTcW1BVT = kTcW1AT + 2 * 64 * 128,
+              kTcW1BCT = kTcW1BVT + 2 * 64 * 64, kTcPerLayer = kTcW1BCT + 2 * 64 * 64;      // + W1B transposed (dm = dP . W1B)
 __global__ void gnn_pack_tc_kernel(const float* __restrict__ packed, float* __restrict__ tc) {
     const int l = blockIdx.y;
     const float* pk = packed + (size_t)l * kPackedPerLayer;
@@ -129,6 +130,8 @@ __global__ void gnn_pack_tc_kernel(const float* __restrict__ packed, float* __re
         if (t < 64 * 64) {
             put(o + kTcW1BV, 64, 64, t / 64, t % 64, pk[kPkW1BV + t]);
             put(o + kTcW1BC, 64, 64, t / 64, t % 64, pk[kPkW1BC + t]);
+            put(o + kTcW1BVT, 64, 64, t % 64, t / 64, pk[kPkW1BV + t]);
+            put(o + kTcW1BCT, 64, 64, t % 64, t / 64, pk[kPkW1BC + t]);
         }
     }
 }

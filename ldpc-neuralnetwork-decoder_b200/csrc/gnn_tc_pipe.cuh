@@ -449,7 +449,8 @@ constexpr uint32_t kTmNodeAHi = 0, kTmNodeALo = 64, kTmNodeD = 128;
 __global__ void __launch_bounds__(kNodeThreads, 2) gnn_node_tc_kernel(
     const float* __restrict__ x, const float* __restrict__ emb_l, const float* __restrict__ packed_l, const float* __restrict__ tc_l,
     int kind, const int* __restrict__ ptr, const int* __restrict__ list, const int* __restrict__ edge_type, long long B, int E,
-    int nodes, float* __restrict__ P, int* __restrict__ status) {
+    int nodes, float* __restrict__ P, float* __restrict__ Msave, int* __restrict__ status) {
+    // Msave != nullptr (training forward): the node means are kept for the backward pass (weight gradient of W1B)
     extern __shared__ __align__(1024) uint8_t tc_smem[];
     uint8_t* Whi = tc_smem;                                 // W1B [64 x 64]
     uint8_t* Wlo = Whi + 64 * 64 * 4;
@@ -519,6 +520,7 @@ __global__ void __launch_bounds__(kNodeThreads, 2) gnn_node_tc_kernel(
                 }
                 const float inv = 1.0f / (float)(k1 - k0);
                 m.x *= inv; m.y *= inv; m.z *= inv; m.w *= inv;
+                if (Msave) reinterpret_cast<float4*>(Msave + (size_t)row * kH)[cc] = m;
             }
             *stage_ptr(S, rr, cc) = m;
         }

@@ -512,7 +512,7 @@ size_t ldpc_gnn_param_count(const ldpc_gnn_t* g) { return g ? g->params : 0; }
 //   G[B][E][h] DC[B][E][h] HR[B][E][2h] DH[B][E][2h]
 //   DPV,MV,DMV [B][N][h]   DPC,MC,DMC [B][M][h]   PG[L][kPackedPerLayer + types*h]
 struct GnnTrainWs {
-    size_t X, PV, PC, SOFT, DSOFT, G, DC, HR, DH, DPV, MV, DMV, DPC, MC, DMC, PG, total;
+    size_t X, PV, PC, SOFT, DSOFT, G, DC, HR, DH, DPV, MV, DMV, DPC, MC, DMC, PG, MVS, MCS, total;   // MVS/MCS: node means of every layer
     size_t xs, pvs, pcs, pg_layer;
 };
 static GnnTrainWs gnn_train_layout(const ldpc_gnn_t* g, int64_t B) {
@@ -527,6 +527,7 @@ static GnnTrainWs gnn_train_layout(const ldpc_gnn_t* g, int64_t B) {
     w.DPV = take(w.pvs); w.MV = take(w.pvs); w.DMV = take(w.pvs);
     w.DPC = take(w.pcs); w.MC = take(w.pcs); w.DMC = take(w.pcs);
     w.PG = take(L * w.pg_layer);
+    w.MVS = take(L * w.pvs); w.MCS = take(L * w.pcs);
     w.total = o;
     return w;
 }
@@ -594,10 +595,12 @@ int ldpc_gnn_forward(const ldpc_gnn_t* g, const float* params, const float* llr,
             if (use_tc) {
                 const float* tcw = g->d_tc + (size_t)l * kTcPerLayer;
                 gnn_node_tc_kernel<<<tc_grid(bc * N, 2), kNodeThreads, kNodeTcSmem, st>>>(
-                    xa, em, pk, tcw, 0, g->d_var_ptr, g->d_var_edge, g->d_edge_type, bc, E, N, pv, g->d_status);
+                    xa, em, pk, tcw, 0, g->d_var_ptr, g->d_var_edge, g->d_edge_type, bc, E, N, pv,
+                    training ? base + tw.MVS + (size_t)l * tw.pvs : nullptr, g->d_status);
                 LDPC_CHECK_LAUNCH("gnn_node_tc_kernel(var)");
                 gnn_node_tc_kernel<<<tc_grid(bc * M, 2), kNodeThreads, kNodeTcSmem, st>>>(
-                    xa, em, pk, tcw, 1, g->d_chk_ptr, nullptr, g->d_edge_type, bc, E, M, pc, g->d_status);
+                    xa, em, pk, tcw, 1, g->d_chk_ptr, nullptr, g->d_edge_type, bc, E, M, pc,
+                    training ? base + tw.MCS + (size_t)l * tw.pcs : nullptr, g->d_status);
                 LDPC_CHECK_LAUNCH("gnn_node_tc_kernel(chk)");
                 // inference: the last layer applies the readout projection itself and writes one float per message into xb
                 fused_readout = use_pipe && !training && l == g->layers - 1;
@@ -691,6 +694,7 @@ int ldpc_gnn_backward(const ldpc_gnn_t* g, const float* params, const float* llr
         LDPC_CUDA(cudaFuncSetAttribute(gnn_dcomb_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDcombTcSmem));
         LDPC_CUDA(cudaFuncSetAttribute(gnn_outer_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kOuterTcSmem));
         LDPC_CUDA(cudaFuncSetAttribute(gnn_outer_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kOuterTcSmem));
+        LDPC_CUDA(cudaFuncSetAttribute(gnn_node_dm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNodeTcSmem));
     }
     for (int l = L - 1; l >= 0; --l) {
         const float* x = base + tw.X + (size_t)l * tw.xs;
@@ -736,12 +740,23 @@ int ldpc_gnn_backward(const ldpc_gnn_t* g, const float* params, const float* llr
         gnn_outer_kernel<2 * kH, kH, 2><<<outer_grid, 256, 0, st>>>(DH, x, (long long)B * E, em, g->d_edge_type, E, pg + kPkW1A, pg + kPkB1V);
         LDPC_CHECK_LAUNCH("gnn_outer_kernel(dW1A)");
         }
+        if (bwd_tc) {       // the means were saved by the training forward; dm = dP . W1B / deg on the tensor cores
+            const float* tcw = g->d_tc + (size_t)l * kTcPerLayer;
+            MV = base + tw.MVS + (size_t)l * tw.pvs;
+            MC = base + tw.MCS + (size_t)l * tw.pcs;
+            auto ngrid = [](long long rows) { const long long t = (rows + 127) / 128; return (int)(t < 2 * kNumSMs ? t : 2 * kNumSMs); };
+            gnn_node_dm_tc_kernel<<<ngrid((long long)B * N), kNodeThreads, kNodeTcSmem, st>>>(DPV, tcw, 0, g->d_var_ptr, (long long)B * N, N, DMV, g->d_status);
+            LDPC_CHECK_LAUNCH("gnn_node_dm_tc_kernel(var)");
+            gnn_node_dm_tc_kernel<<<ngrid((long long)B * M), kNodeThreads, kNodeTcSmem, st>>>(DPC, tcw, 1, g->d_chk_ptr, (long long)B * M, M, DMC, g->d_status);
+            LDPC_CHECK_LAUNCH("gnn_node_dm_tc_kernel(chk)");
+        } else {
         gnn_node_bwd_kernel<<<gnn_grid(B * N, kGnnThreads), kGnnThreads, 0, st>>>(
             x, em, pk, 0, g->d_var_ptr, g->d_var_edge, g->d_edge_type, DPV, B, E, N, MV, DMV);
         LDPC_CHECK_LAUNCH("gnn_node_bwd_kernel(var)");
         gnn_node_bwd_kernel<<<gnn_grid(B * M, kGnnThreads), kGnnThreads, 0, st>>>(
             x, em, pk, 1, g->d_chk_ptr, nullptr, g->d_edge_type, DPC, B, E, M, MC, DMC);
         LDPC_CHECK_LAUNCH("gnn_node_bwd_kernel(chk)");
+        }
         gnn_outer_kernel<kH, kH, 0><<<outer_grid, 256, 0, st>>>(DPV, MV, (long long)B * N, nullptr, nullptr, E, pg + kPkW1BV, nullptr);
         LDPC_CHECK_LAUNCH("gnn_outer_kernel(dW1Bv)");
         gnn_outer_kernel<kH, kH, 0><<<outer_grid, 256, 0, st>>>(DPC, MC, (long long)B * M, nullptr, nullptr, E, pg + kPkW1BC, nullptr);
