@@ -191,3 +191,36 @@ def test_tensor_core_and_ffma_paths_agree(tmp_path):
     scale = np.max(np.abs(b["grad"]))
     assert scale > 0 and np.max(np.abs(a["grad"] - b["grad"])) <= 2e-4 * scale
     assert np.array_equal(a["grad"] == 0, b["grad"] == 0)           # same parameters without gradient
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B", [1, 3, 40])
+def test_tiny_graph_tiles_span_many_codewords(B):
+    """The notebook's 3x4 toy matrix has 7 messages, so a 128-row tile of the tensor-core kernels covers up to 18
+    codewords and most tiles are ragged: forward against the oracle, and the gradient of one weight against a central
+    finite difference of the loss."""
+    H = torch.tensor([[1, 1, 0, 0], [0, 1, 1, 1], [1, 0, 0, 1]], dtype=torch.float32)
+    torch.manual_seed(5)
+    dec, conv = create_message_gnn_decoder(H, 2, 64)
+    rng = np.random.default_rng(B)
+    llr = rng.normal(1.0, 2.0, size=(B, 4)).astype(np.float32)
+    sd = {k: v.detach().numpy() for k, v in dec.state_dict().items()}
+    soft_ref, _ = oracle.gnn_forward(sd, llr, conv.message_var_index.numpy(), conv.message_check_index.numpy(),
+                                     dec._expanded_types(), 2)
+    dec = dec.cuda()
+    soft, hard = dec(torch.from_numpy(llr).cuda())
+    assert np.all(np.abs(soft.cpu().numpy() - soft_ref) <= 1e-4 * np.maximum(np.abs(soft_ref), 1.0))
+    gt = torch.from_numpy((rng.random((B, 4)) > 0.5).astype(np.float32)).cuda()
+    _, loss = dec(torch.from_numpy(llr).cuda(), None, None, None, None, ground_truth=gt)
+    loss.backward()
+    p = dec.output_projection.weight if hasattr(dec, "output_projection") else next(dec.parameters())
+    g = p.grad.reshape(-1)[0].item()
+    eps = 1e-2
+    with torch.no_grad():
+        p.reshape(-1)[0] += eps
+        _, lp = dec(torch.from_numpy(llr).cuda(), None, None, None, None, ground_truth=gt)
+        p.reshape(-1)[0] -= 2 * eps
+        _, lm = dec(torch.from_numpy(llr).cuda(), None, None, None, None, ground_truth=gt)
+        p.reshape(-1)[0] += eps
+    fd = (lp.item() - lm.item()) / (2 * eps)
+    assert abs(fd - g) <= 2e-3 * max(1.0, abs(g)) + 2e-4
