@@ -28,6 +28,7 @@
 //     iteration; the posterior itself is accumulated in the reference's ascending-check
 //     order).  LDPC_PATH_EXACT keeps the reference order bit for bit.
 #pragma once
+#include "math_ref.cuh"
 #include <math_constants.h>
 
 #include "bg2_tables.h"
@@ -63,7 +64,14 @@ __device__ __forceinline__ float bp_resolve(float finite_sum, int k) {
 #ifndef LDPC_BP_NOINLINE
 #define LDPC_BP_NOINLINE 1
 #endif
-#if LDPC_BP_NOINLINE
+// LDPC_BP_REF_FN=1: the exact kernel's once-rounded double evaluation (math_ref.cuh) instead of tanhf/atanhf
+#ifndef LDPC_BP_REF_FN
+#define LDPC_BP_REF_FN 0
+#endif
+#if LDPC_BP_REF_FN
+__device__ __noinline__ float bp_tanh_half(float v) { return tanh_ref(0.5f * v); }
+__device__ __noinline__ float bp_two_atanh(float p) { return 2.0f * atanh_ref(p); }
+#elif LDPC_BP_NOINLINE
 __device__ __noinline__ float bp_tanh_half(float v) { return tanhf(0.5f * v); }
 __device__ __noinline__ float bp_two_atanh(float p) { return 2.0f * atanhf(p); }
 #else
