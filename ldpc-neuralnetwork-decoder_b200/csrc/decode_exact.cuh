@@ -120,7 +120,10 @@ __global__ void __launch_bounds__(256) decode_exact_kernel(const DecodeParams p)
                 } else {
                     float t[kMaxDc];
 #pragma unroll
-                    for (int k = 0; k < kMaxDc; ++k) t[k] = (k < d) ? tanh_ref(v[k] * 0.5f) : 1.0f;
+                    for (int k = 0; k < kMaxDc; ++k) {
+                        t[k] = 1.0f;
+                        if (k < d) t[k] = tanh_half_ref(v[k]);        // warp-uniform branch: degree-3..5 rows skip the rest
+                    }
                     float pre = 1.0f;
 #pragma unroll
                     for (int k = 0; k < kMaxDc; ++k)
@@ -129,7 +132,7 @@ __global__ void __launch_bounds__(256) decode_exact_kernel(const DecodeParams p)
 #pragma unroll
                             for (int k2 = k + 1; k2 < kMaxDc; ++k2)
                                 if (k2 < d) pr = __fmul_rn(pr, t[k2]);
-                            v[k] = 2.0f * atanh_ref(pr);
+                            v[k] = two_atanh_ref(pr);
                             pre = __fmul_rn(pre, t[k]);
                         }
                 }
