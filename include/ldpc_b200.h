@@ -105,6 +105,14 @@ int ldpc_bp_decode(const ldpc_code_t* code, const float* llr, int64_t B, int ite
 int ldpc_syndrome_check(const ldpc_code_t* code, const void* hard, int hard_dtype, int64_t B, uint8_t* syndrome_ok,
                         void* stream);
 
+/* ldpc_encode: systematic encoder, absent from the reference (every loop there sends the all-zero codeword,
+ * trainer.py:86, comparative_evaluation.py:132).  info: [B, K] uint8 0/1 (device), codeword:
+ * [B, N] uint8 0/1 with codeword[:, :K] == info and every parity check of the code satisfied.  plan / binv: the device
+ * tables built by utils/encoder.py for a code of the shape H = [A B 0; C D I] (plan = [g, kb, words, core_rows[g],
+ * core_cols[g], ext_of_row[rows]] int32, binv = B^-1 packed by rows, [g*Z][words] uint32).                          */
+int ldpc_encode(const ldpc_code_t* code, const uint8_t* info, int64_t B, const int32_t* plan, int64_t plan_len,
+                const uint32_t* binv, uint8_t* codeword, void* stream);
+
 /* Host-buffer variant (the `e2e` path of bench.py): llr_host / hard_host are HOST pointers
  * (pinned memory recommended).  The call chunks the batch, overlaps H2D, decode and D2H on
  * internal streams and returns when hard_host (and soft_host if given) are complete.     */

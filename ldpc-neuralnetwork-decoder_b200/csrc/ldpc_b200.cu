@@ -10,6 +10,7 @@
 #include "gnn.cuh"
 #include "gnn_bwd.cuh"
 #include <cuda_fp16.h>
+#include "encode.cuh"
 #include "gnn_tc.cuh"
 #include "gnn_tc_pipe.cuh"
 #include "gnn_bwd_tc.cuh"
@@ -165,6 +166,25 @@ int ldpc_syndrome_check(const ldpc_code_t* code, const void* hard, int hard_dtyp
     DeviceGuard g(code->device);
     if (!g.ok) return fail(LDPC_ERR_CUDA, "syndrome_check: cannot select device %d", code->device);
     return launch_syndrome(code, hard, hard_dtype, B, syndrome_ok, (cudaStream_t)stream);
+}
+
+int ldpc_encode(const ldpc_code_t* code, const uint8_t* info, int64_t B, const int32_t* plan, int64_t plan_len,
+                const uint32_t* binv, uint8_t* codeword, void* stream) {
+    if (!code || !plan || !binv) return fail(LDPC_ERR_INVALID, "encode: null code handle or encoder tables");
+    if (B < 0) return fail(LDPC_ERR_INVALID, "encode: negative batch");
+    if (B == 0) return LDPC_OK;
+    if (!info || !codeword) return fail(LDPC_ERR_INVALID, "encode: null buffer");
+    if (plan_len < 3 + code->rows) return fail(LDPC_ERR_INVALID, "encode: plan of %lld words is too short", (long long)plan_len);
+    DeviceGuard g(code->device);
+    if (!g.ok) return fail(LDPC_ERR_CUDA, "encode: cannot select device %d", code->device);
+    // words per row of B^-1: the plan carries it at [2]; it is needed on the host for the shared-memory size
+    int hdr[3];
+    LDPC_CUDA(cudaMemcpyAsync(hdr, plan, sizeof(hdr), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    LDPC_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    if (hdr[0] <= 0 || hdr[1] <= 0 || hdr[2] != (hdr[0] * code->Z + 31) / 32 || plan_len != 3 + 2 * hdr[0] + code->rows)
+        return fail(LDPC_ERR_INVALID, "encode: inconsistent plan (g %d, kb %d, words %d, length %lld)", hdr[0], hdr[1], hdr[2],
+                    (long long)plan_len);
+    return launch_encode(code, info, B, plan, hdr[2], binv, codeword, (cudaStream_t)stream);
 }
 
 int ldpc_decode_host_q(const ldpc_code_t* code, int algo, const void* llr_host, int llr_format, float llr_scale,

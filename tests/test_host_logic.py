@@ -165,3 +165,36 @@ def test_bench_reference_arm_prints_the_contract_line():
     other = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                             "--warmup", "0"], capture_output=True, text=True, timeout=120, cwd=root, env=env)
     assert other.returncode == 0 and other.stdout.strip() == ""
+
+
+@pytest.mark.parametrize("Z", [4, 32])
+def test_encoder_plan_and_oracle_encoder(Z):
+    """Host side of the systematic encoder: the structure discovered from the BG2 table (10 information
+    blocks, 4 core parity blocks, 38 extension rows), B^-1 really inverts the core block, and the oracle's dense
+    GF(2) solve yields systematic codewords in the null space of H."""
+    from oracle import oracle
+    from ldpc_b200.utils import QCCode, SystematicEncoder
+    code = QCCode.nr_2_0(Z)
+    enc = SystematicEncoder(code)
+    assert (enc.g, enc.kb) == (4, 10) and enc.plan[2] == (4 * Z + 31) // 32
+    core_rows, core_cols, ext = enc.plan[3:7], enc.plan[7:11], enc.plan[11:]
+    assert list(core_rows) == [0, 1, 2, 3] and list(core_cols) == [10, 11, 12, 13]
+    assert list(ext[:4]) == [-1] * 4 and list(ext[4:]) == list(range(14, 52))
+    # B * B^-1 = I over GF(2)
+    n = 4 * Z
+    binv = ((enc.binv_packed[:, np.arange(n) >> 5] >> (np.arange(n) & 31).astype(np.uint32)) & 1).astype(np.int64)
+    Bm = np.zeros((n, n), dtype=np.int64)
+    r = np.arange(Z)
+    for a in range(4):
+        for b in range(4):
+            s = int(code.shifts[a, 10 + b])
+            if s >= 0:
+                Bm[a * Z + r, b * Z + (r + s) % Z] = 1
+    assert np.array_equal((Bm @ binv) & 1, np.eye(n, dtype=np.int64))
+    rng = np.random.default_rng(Z)
+    info = rng.integers(0, 2, size=(5, code.K), dtype=np.uint8)
+    cw = oracle.encode_dense(code.shifts, Z, info)                     # asserts H c = 0 itself
+    assert cw.shape == (5, code.N) and np.array_equal(cw[:, :code.K], info)
+    assert not oracle.encode_dense(code.shifts, Z, np.zeros((1, code.K), dtype=np.uint8)).any()
+    with pytest.raises(ValueError):
+        SystematicEncoder(QCCode(np.array([[0, 0, -1], [0, -1, 0]]), 2))      # every row owns a degree-1 column: no core block
