@@ -175,6 +175,24 @@ int ldpc_variable_layer_bwd(const int64_t* idx, const float* grad_out, int64_t B
  * prev: array of L device pointers (host array of pointers), each [B,E].                 */
 int ldpc_residual_layer_fwd(const float* llr, const float* c2v, const float* w_ch, const float* w_res,
                             const float* const* prev, int L, int64_t B, int64_t E, float* out, void* stream);
+/* Variable + residual update of the unrolled neural min-sum decoder (LDPCNeuralDecoder; the
+ * reference's models/decoder.py is missing, prototype: EE4002R_2025.ipynb cell 11
+ * `variable_layer_update`): out = w_ch*llr + sum_k c2v[idx] + sum_{i<L} w_res[i]*prev[i],
+ * bit-identical to VariableLayer (layers.py:78-125, zero llr) then ResidualLayer (:143-168). */
+int ldpc_neural_variable_layer_fwd(const float* llr, const float* c2v, const int64_t* idx, const float* w_ch,
+                                   const float* w_res, const float* const* prev, int L, int64_t B, int64_t E, int K,
+                                   float* out, void* stream);
+/* Whole LDPCNeuralDecoder forward (inference / validation) in one kernel: `iters` unrolled
+ * iterations of CheckLayer (layers.py:14-66) -> VariableLayer (:78-125) -> ResidualLayer
+ * (:143-168), the last check messages summed per variable into OutputLayer (:180-210); the
+ * composition of the reference's missing models/decoder.py (notebook cell 11 `forward`).
+ * Messages stay in shared memory across iterations; bit-identical to the per-layer entry
+ * points.  cidx/vidx are the [E,K] int64 neighbour tables packed ONCE per code by
+ * ldpc_neural_pack_index to [K,E] uint16 (0xFFFF = -1).  gt_e / max_loss optional.       */
+int ldpc_neural_pack_index(const int64_t* idx, int64_t E, int K, uint16_t* out, void* stream);
+int ldpc_neural_decode(const float* llr_e, const uint16_t* cidx, int Kc, const uint16_t* vidx, int Kv, const float* w_ch,
+                       const float* w_res, int L, int iters, int64_t B, int64_t E, const float* gt_e, float* soft,
+                       float* max_loss, void* stream);
 /* OutputLayer.forward, layers.py:180-210: soft = sigmoid(final+llr); if gt: per-row max of
  * BCE(soft, gt) -> max_loss [B], argmax [B] int32 (for the backward).                    */
 int ldpc_output_layer_fwd(const float* final_llr, const float* llr, const float* gt, int64_t B, int64_t E,

@@ -159,6 +159,53 @@ __global__ void __launch_bounds__(kLayerThreads) residual_layer_fwd_kernel(const
     }
 }
 
+// Variable + residual update of the unrolled neural min-sum decoder in one pass
+// (notebook cell 11 `variable_layer_update`; the composing models/decoder.py is missing from the
+// reference): out = (w_ch*llr + sum_k c2v[idx[e,k]]) + sum_{i<L} w_res[i]*prev[i], same operation
+// order as VariableLayer(0, c2v) followed by ResidualLayer, so the result is bit-identical to the
+// two-kernel composition while the gathered sum never makes a round trip through HBM.
+template <int kRows, bool kStage>
+__global__ void __launch_bounds__(kLayerThreads) neural_variable_fwd_kernel(
+    const float* __restrict__ llr, const float* __restrict__ c2v, const long long* __restrict__ idx,
+    const float* __restrict__ w_ch, const float* __restrict__ w_res, ResidualPtrs prev, int L, long long B,
+    long long E, int K, float* __restrict__ out) {
+    extern __shared__ float xs[];
+    float wr[kMaxResidual];
+#pragma unroll
+    for (int i = 0; i < kMaxResidual; ++i) wr[i] = i < L ? w_res[i] : 0.0f;
+    for (long long b0 = (long long)blockIdx.x * kRows; b0 < B; b0 += (long long)gridDim.x * kRows) {
+        const int nb = (int)((B - b0) < kRows ? (B - b0) : kRows);
+        if constexpr (kStage) {
+            __syncthreads();
+            for (long long t = threadIdx.x; t < (long long)nb * E; t += kLayerThreads) xs[t] = c2v[b0 * E + t];
+            __syncthreads();
+        }
+        for (long long e = threadIdx.x; e < E; e += kLayerThreads) {
+            float acc[kRows];
+#pragma unroll
+            for (int q = 0; q < kRows; ++q) acc[q] = 0.0f;
+            for (int k = 0; k < K; ++k) {
+                const long long n = idx[e * K + k];
+                if (n < 0) continue;
+#pragma unroll
+                for (int q = 0; q < kRows; ++q)
+                    if (q < nb) acc[q] += kStage ? xs[(long long)q * E + n] : c2v[(b0 + q) * E + n];
+            }
+            const float w = w_ch[e];
+#pragma unroll
+            for (int q = 0; q < kRows; ++q)
+                if (q < nb) {
+                    const long long t = (b0 + q) * E + e;
+                    float r = __fadd_rn(__fmul_rn(llr[t], w), acc[q]);
+#pragma unroll
+                    for (int i = 0; i < kMaxResidual; ++i)
+                        if (i < L) r = __fadd_rn(r, __fmul_rn(wr[i], prev.prev[i][t]));
+                    out[t] = r;
+                }
+        }
+    }
+}
+
 // soft = sigmoid(final + llr); per-row max of BCE(soft, gt) with torch's log clamp at -100.
 // One warp per row.
 __global__ void __launch_bounds__(kLayerThreads) output_layer_fwd_kernel(const float* __restrict__ final_llr,

@@ -7,6 +7,7 @@
 #include "decode_fast.cuh"
 #include "channel_kernels.cuh"
 #include "layers.cuh"
+#include "neural.cuh"
 #include "gnn.cuh"
 #include "gnn_bwd.cuh"
 #include <cuda_fp16.h>
@@ -439,6 +440,74 @@ int ldpc_residual_layer_fwd(const float* llr, const float* c2v, const float* w_c
         llr, c2v, w_ch, w_res, rp, L, (long long)B, (long long)E, out);
     LDPC_CHECK_LAUNCH("residual_layer_fwd_kernel");
     return LDPC_OK;
+}
+
+int ldpc_neural_variable_layer_fwd(const float* llr, const float* c2v, const int64_t* idx, const float* w_ch,
+                                   const float* w_res, const float* const* prev, int L, int64_t B, int64_t E, int K,
+                                   float* out, void* stream) {
+    if (!llr || !c2v || !idx || !w_ch || !out || (L > 0 && (!prev || !w_res)))
+        return fail(LDPC_ERR_INVALID, "neural_variable_layer_fwd: null argument");
+    if (L < 0 || L > kMaxResidual) return fail(LDPC_ERR_UNSUPPORTED, "neural_variable_layer_fwd: depth %d outside 0..%d", L, kMaxResidual);
+    if (B < 0 || E <= 0 || K <= 0) return fail(LDPC_ERR_INVALID, "neural_variable_layer_fwd: bad shape");
+    if (B == 0) return LDPC_OK;
+    ResidualPtrs rp{};
+    for (int i = 0; i < L; ++i) {
+        if (!prev[i]) return fail(LDPC_ERR_INVALID, "neural_variable_layer_fwd: prev[%d] is null", i);
+        rp.prev[i] = prev[i];
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    LDPC_LAYER_DISPATCH(neural_variable_fwd_kernel, llr, c2v, (const long long*)idx, w_ch, w_res, rp, L, (long long)B,
+                        (long long)E, K, out);
+    LDPC_CHECK_LAUNCH("neural_variable_fwd_kernel");
+    return LDPC_OK;
+}
+
+int ldpc_neural_pack_index(const int64_t* idx, int64_t E, int K, uint16_t* out, void* stream) {
+    if (!idx || !out) return fail(LDPC_ERR_INVALID, "neural_pack_index: null argument");
+    if (E <= 0 || K <= 0) return fail(LDPC_ERR_INVALID, "neural_pack_index: bad shape");
+    if (E >= 0xFFFF) return fail(LDPC_ERR_UNSUPPORTED, "neural_pack_index: %lld edges do not fit 16-bit indices", (long long)E);
+    neural_pack_index_kernel<<<layer_grid(E * K, 256), 256, 0, (cudaStream_t)stream>>>((const long long*)idx, (long long)E, K, out);
+    LDPC_CHECK_LAUNCH("neural_pack_index_kernel");
+    return LDPC_OK;
+}
+
+}  // extern "C"
+
+template <int kRows>
+static int launch_neural(const float* llr, const uint16_t* cidx, int Kc, const uint16_t* vidx, int Kv, const float* w_ch,
+                         const float* w_res, int L, int iters, int64_t B, int E, const float* gt, float* soft,
+                         float* max_loss, size_t smem, cudaStream_t st) {
+    LDPC_CUDA(cudaFuncSetAttribute(neural_decode_kernel<kRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int ctas_per_sm = smem * 2 + 8192 <= (size_t)227 * 1024 ? 2 : 1;
+    long long grid = (B + kRows - 1) / kRows;
+    if (grid > (long long)kNumSMs * ctas_per_sm) grid = (long long)kNumSMs * ctas_per_sm;
+    neural_decode_kernel<kRows><<<(int)grid, kNeuralThreads, smem, st>>>(llr, cidx, Kc, vidx, Kv, w_ch, w_res, L, iters,
+                                                                       (long long)B, E, gt, soft, max_loss);
+    LDPC_CHECK_LAUNCH("neural_decode_kernel");
+    return LDPC_OK;
+}
+
+extern "C" {
+
+int ldpc_neural_decode(const float* llr_e, const uint16_t* cidx, int Kc, const uint16_t* vidx, int Kv, const float* w_ch,
+                       const float* w_res, int L, int iters, int64_t B, int64_t E, const float* gt_e, float* soft,
+                       float* max_loss, void* stream) {
+    if (!llr_e || !cidx || !vidx || !w_ch || !soft || (L > 0 && !w_res)) return fail(LDPC_ERR_INVALID, "neural_decode: null argument");
+    if (gt_e && !max_loss) return fail(LDPC_ERR_INVALID, "neural_decode: ground truth given without max_loss buffer");
+    if (L < 0 || L > kMaxResidual) return fail(LDPC_ERR_UNSUPPORTED, "neural_decode: depth %d outside 0..%d", L, kMaxResidual);
+    if (iters < 1 || B < 0 || E <= 0 || Kc <= 0 || Kv <= 0) return fail(LDPC_ERR_INVALID, "neural_decode: bad shape");
+    if (E >= 0xFFFF) return fail(LDPC_ERR_UNSUPPORTED, "neural_decode: %lld edges do not fit 16-bit indices", (long long)E);
+    if (B == 0) return LDPC_OK;
+    const size_t per_row = (size_t)((L > 0 ? L : 1) + 1) * E * sizeof(float);
+    const size_t cap = (size_t)220 * 1024;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (4 * per_row <= cap && B >= 4 * 2 * kNumSMs)
+        return launch_neural<4>(llr_e, cidx, Kc, vidx, Kv, w_ch, w_res, L, iters, B, (int)E, gt_e, soft, max_loss, 4 * per_row, st);
+    if (2 * per_row <= cap && B >= 2 * kNumSMs)
+        return launch_neural<2>(llr_e, cidx, Kc, vidx, Kv, w_ch, w_res, L, iters, B, (int)E, gt_e, soft, max_loss, 2 * per_row, st);
+    if (per_row <= cap)
+        return launch_neural<1>(llr_e, cidx, Kc, vidx, Kv, w_ch, w_res, L, iters, B, (int)E, gt_e, soft, max_loss, per_row, st);
+    return fail(LDPC_ERR_UNSUPPORTED, "neural_decode: %zu bytes of resident state per codeword exceed shared memory", per_row);
 }
 
 int ldpc_output_layer_fwd(const float* final_llr, const float* llr, const float* gt, int64_t B, int64_t E, float* soft,

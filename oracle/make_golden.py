@@ -242,6 +242,52 @@ def qpsk():
     np.savez_compressed(os.path.join(OUT, "qpsk.npz"), **out)
 
 
+def neural_decoder(Z=4, B=6, iters=4, depth_L=2):
+    """The composition LDPCNeuralDecoder stands for (models/decoder.py is missing from the
+    reference; notebook cell 11 is its prototype), run with the REFERENCE's own layer
+    classes: forward, per-frame max loss, and autograd gradients of loss.mean()
+    (training/trainer.py:102-107)."""
+    base = load_base_matrix(TABLES[Z])
+    H = expand_base_matrix(base, Z)
+    _, c, v, o = create_LLR_mapping(H.T)
+    E = c.shape[0]
+    torch.manual_seed(11)
+    bits = torch.zeros(B, H.shape[1])
+    # scaled-down LLRs at low SNR keep sigmoid/BCE out of saturation, so the per-frame max loss has a gradient
+    llr = AWGNChannel().transmit(bits, snr_db=-3.0) * 0.125
+    llr[0, :3] = 0.0                                       # exact zeros: the "ignored" rule of CheckLayer
+    llr_e = llr[:, o[0]].clone()
+    # sigmoid(LLR > 0) -> 1 is the reference's output convention (layers.py:198), so the all-zero codeword's
+    # target in that convention is all ones; a few flipped targets exercise both BCE branches
+    gt_e = (torch.rand(B, H.shape[1]) > 0.05).float()[:, o[0]]
+    cl, vl, ol = CheckLayer(), VariableLayer(), OutputLayer()
+    res = ResidualLayer(E, depth_L=depth_L)
+    with torch.no_grad():
+        res.w_ch.copy_(torch.rand(E) * 0.5 + 0.75)
+        res.w_res.copy_(torch.tensor([0.25, -0.125, 0.0625][:depth_L]))
+    queue, x, c2v, xs = [], llr_e, None, []
+    for l in range(iters):
+        c2v = cl(x, c)
+        if l == iters - 1:
+            break
+        s = vl(torch.zeros_like(c2v), c2v, v)
+        x = res(llr_e, s, queue[:depth_L])
+        queue.insert(0, x)
+        xs.append(x.detach().numpy())
+    final = vl(c2v, c2v, v)
+    soft, max_loss = ol(final, llr_e, gt_e)
+    max_loss.mean().backward()
+    np.savez_compressed(
+        os.path.join(OUT, f"neural_decoder_z{Z}.npz"),
+        Z=Z, iters=iters, depth_L=depth_L, check=c.numpy().astype(np.int32), var=v.numpy().astype(np.int32),
+        out_index=o.numpy().astype(np.int32), llr=llr.numpy(), llr_e=llr_e.numpy(), gt_e=gt_e.numpy(),
+        w_ch=res.w_ch.detach().numpy(), w_res=res.w_res.detach().numpy(), x=np.stack(xs),
+        c2v=c2v.detach().numpy(), final=final.detach().numpy(), soft=soft.detach().numpy(),
+        max_loss=max_loss.detach().numpy(), grad_wch=res.w_ch.grad.numpy(), grad_wres=res.w_res.grad.numpy())
+    print("neural_decoder: E", E, "max_loss", max_loss.detach().numpy(), "grad_wres", res.w_res.grad.numpy(),
+          "nonzero grad_wch", int((res.w_ch.grad != 0).sum()))
+
+
 JOBS = {
     "mapping_layers": mapping_and_layers,
     # BASELINE.json config 1 (plumbing): Z=4, B=1024, 5 iters, alpha 0.75, snr_db 2.0, seed 1234
@@ -255,6 +301,7 @@ JOBS = {
     "gnn_z4": lambda: gnn(4, 4, 1.0, "z4_b4", True),
     "gnn_z32": lambda: gnn(32, 2, -2.0, "z32_b2", True),
     "qpsk": qpsk,
+    "neural_decoder": neural_decoder,
 }
 
 if __name__ == "__main__":

@@ -1,0 +1,140 @@
+"""LDPCNeuralDecoder (unrolled neural min-sum decoder) on the GPU against the
+composition of the reference's own layer classes (golden) and against the oracle at Z=32.
+Needs a B200 (-m gpu)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import oracle
+import ldpc_b200  # noqa: F401
+from ldpc_b200.models import LDPCNeuralDecoder
+from ldpc_b200.utils import QCCode, create_LLR_mapping
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _decoder(g, fused, out_index=None):
+    E = g["llr_e"].shape[1]
+    dec = LDPCNeuralDecoder(num_nodes=E, num_iterations=int(g["iters"]), depth_L=int(g["depth_L"]),
+                            output_index_tensor=out_index, fused=fused).to(DEV)
+    with torch.no_grad():
+        dec.residual_layer.w_ch.copy_(torch.from_numpy(g["w_ch"]))
+        dec.residual_layer.w_res.copy_(torch.from_numpy(g["w_res"]))
+    return dec
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_forward_and_gradients_match_reference_layers(fused):
+    g = load_golden("neural_decoder_z4")
+    t = lambda k, dt=torch.float32: torch.from_numpy(g[k]).to(DEV).to(dt)
+    dec = _decoder(g, fused)
+    cidx, vidx = t("check", torch.int64), t("var", torch.int64)
+    soft, ml = dec(t("llr_e"), cidx, vidx, t("gt_e"))
+    np.testing.assert_allclose(soft.detach().cpu().numpy(), g["soft"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(ml.detach().cpu().numpy(), g["max_loss"], rtol=1e-5)
+    ml.mean().backward()                                             # trainer.py:105-107
+    np.testing.assert_allclose(dec.residual_layer.w_ch.grad.cpu().numpy(), g["grad_wch"], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(dec.residual_layer.w_res.grad.cpu().numpy(), g["grad_wres"], rtol=1e-4, atol=1e-5)
+    # state_dict carries exactly the reference layer's parameter names
+    assert set(dec.state_dict()) == {"residual_layer.w_ch", "residual_layer.w_res"}
+
+
+def test_fused_variable_residual_kernel_is_bit_identical_to_the_composition():
+    g = load_golden("neural_decoder_z4")
+    t = lambda k, dt=torch.float32: torch.from_numpy(g[k]).to(DEV).to(dt)
+    cidx, vidx = t("check", torch.int64), t("var", torch.int64)
+    a = _decoder(g, True)._messages(t("llr_e"), cidx, vidx)
+    b = _decoder(g, False)._messages(t("llr_e"), cidx, vidx)
+    assert torch.equal(a, b)
+    np.testing.assert_allclose(a.detach().cpu().numpy(), g["c2v"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("depth_L,iters", [(2, 4), (1, 3), (0, 2), (3, 6), (2, 1)])
+def test_one_kernel_decoder_is_bit_identical_to_the_layer_chain(depth_L, iters):
+    """ldpc_neural_decode (messages resident in shared memory) vs the per-layer kernels: same
+    bits for soft outputs and per-frame max loss, for every queue depth / iteration count,
+    on a ragged batch; and both equal the oracle."""
+    g = load_golden("neural_decoder_z4")
+    cidx = torch.from_numpy(g["check"]).to(DEV).long()
+    vidx = torch.from_numpy(g["var"]).to(DEV).long()
+    E = g["llr_e"].shape[1]
+    rng = np.random.default_rng(depth_L * 10 + iters)
+    B = 1201                                                         # > 4 * 2 * 148: the 4-row tiles, ragged tail
+    llr_e = (rng.normal(size=(B, E)) * 0.6 + 0.3).astype(np.float32)
+    llr_e[5, ::3] = 0.0
+    gt_e = (rng.random((B, E)) > 0.1).astype(np.float32)
+    w_ch = (rng.random(E) * 0.5 + 0.75).astype(np.float32)
+    w_res = np.array([0.25, -0.125, 0.0625][:depth_L], np.float32)
+    decs = []
+    for fused in (True, False):
+        d = LDPCNeuralDecoder(E, iters, depth_L, fused=fused).to(DEV)
+        with torch.no_grad():
+            d.residual_layer.w_ch.copy_(torch.from_numpy(w_ch))
+            d.residual_layer.w_res.copy_(torch.from_numpy(w_res))
+        decs.append(d)
+    x, y = torch.from_numpy(llr_e).to(DEV), torch.from_numpy(gt_e).to(DEV)
+    with torch.no_grad():
+        for nb in (B, 300, 7):                                       # 4-, 2- and 1-row tiles
+            s1, m1 = decs[0](x[:nb], cidx, vidx, y[:nb])             # one kernel
+            s2, m2 = decs[1](x[:nb], cidx, vidx, y[:nb])             # four layers per iteration
+            assert torch.equal(s1, s2) and torch.equal(m1, m2)
+        s3, none = decs[0](x, cidx, vidx)
+        assert none is None and torch.equal(s3, s1 if nb == B else decs[1](x, cidx, vidx)[0])
+    ref = oracle.neural_minsum_forward(llr_e[:64], g["check"].astype(np.int64), g["var"].astype(np.int64),
+                                       w_ch, w_res, iters, gt_e[:64])
+    with torch.no_grad():
+        s64, m64 = decs[0](x[:64], cidx, vidx, y[:64])
+    np.testing.assert_allclose(s64.cpu().numpy(), ref["soft"], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(m64.cpu().numpy(), ref["max_loss"], rtol=1e-4, atol=1e-6)
+
+
+def test_variable_space_io_and_decode():
+    g = load_golden("neural_decoder_z4")
+    t = lambda k, dt=torch.float32: torch.from_numpy(g[k]).to(DEV).to(dt)
+    cidx, vidx = t("check", torch.int64), t("var", torch.int64)
+    dec = _decoder(g, True, out_index=torch.from_numpy(g["out_index"]))
+    soft_v, none = dec(t("llr"), cidx, vidx)                         # (B, N) in -> (B, N) out
+    assert none is None and soft_v.shape == g["llr"].shape
+    first = np.full(g["llr"].shape[1], -1)
+    for e, v in reversed(list(enumerate(g["out_index"][0]))):
+        first[v] = e
+    np.testing.assert_allclose(soft_v.detach().cpu().numpy(), g["soft"][:, first], rtol=1e-5, atol=1e-6)
+    hard = dec.decode(t("llr"), cidx, vidx)
+    assert torch.equal(hard, (soft_v > 0.5).float())
+    with pytest.raises(ValueError):
+        dec(t("llr")[:, :-1], cidx, vidx)
+    with pytest.raises(RuntimeError):
+        dec(torch.from_numpy(g["llr"]), cidx, vidx)                  # CPU tensor: no fallback
+
+
+def test_z32_against_oracle_ragged_batch():
+    code = QCCode.nr_2_0(32)
+    _, cidx, vidx, oidx = create_LLR_mapping(code.dense().T)
+    rng = np.random.default_rng(5)
+    B, iters, L = 11, 5, 2
+    llr = (rng.normal(size=(B, code.N)) * 0.5 + 0.4).astype(np.float32)
+    llr[2, ::9] = 0.0
+    llr_e = llr[:, oidx.numpy()[0]]
+    w_ch = (rng.random(code.E) * 0.5 + 0.75).astype(np.float32)
+    w_res = np.array([0.2, -0.1], np.float32)
+    gt_e = np.ones_like(llr_e)
+    dec = LDPCNeuralDecoder(code.E, iters, L).to(DEV)
+    with torch.no_grad():
+        dec.residual_layer.w_ch.copy_(torch.from_numpy(w_ch))
+        dec.residual_layer.w_res.copy_(torch.from_numpy(w_res))
+    soft, ml = dec(torch.from_numpy(llr_e).to(DEV), cidx.to(DEV), vidx.to(DEV), torch.from_numpy(gt_e).to(DEV))
+    ref = oracle.neural_minsum_forward(llr_e, cidx.numpy(), vidx.numpy(), w_ch, w_res, iters, gt_e)
+    np.testing.assert_allclose(soft.detach().cpu().numpy(), ref["soft"], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(ml.detach().cpu().numpy(), ref["max_loss"], rtol=1e-4, atol=1e-6)
+    with torch.no_grad():                                            # one-kernel path, 2-row tiles at E = 6304
+        big = torch.from_numpy(np.tile(llr_e, (30, 1))).to(DEV)
+        sk, mk = dec(big, cidx.to(DEV), vidx.to(DEV), torch.ones_like(big))
+        s1, m1 = dec(torch.from_numpy(llr_e).to(DEV), cidx.to(DEV), vidx.to(DEV), torch.from_numpy(gt_e).to(DEV))
+    assert torch.equal(sk[:B], soft.detach()) and torch.equal(mk[-B:], ml.detach())
+    assert torch.equal(s1, soft.detach()) and torch.equal(m1, ml.detach())
+    plain = LDPCNeuralDecoder(code.E, iters, L, fused=False).to(DEV)
+    plain.load_state_dict(dec.state_dict())
+    args = (torch.from_numpy(llr_e).to(DEV), cidx.to(DEV), vidx.to(DEV))
+    assert torch.equal(dec._messages(*args), plain._messages(*args))

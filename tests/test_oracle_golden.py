@@ -93,6 +93,19 @@ def test_layer_oracle_matches_reference():
     np.testing.assert_allclose(ml, g["lay_maxloss"], rtol=1e-5)
 
 
+def test_neural_decoder_oracle_matches_reference_layers():
+    """oracle.neural_minsum_forward against the composition run with the reference's own layer
+    classes (oracle/make_golden.py:neural_decoder)."""
+    g = load_golden("neural_decoder_z4")
+    r = oracle.neural_minsum_forward(g["llr_e"], g["check"].astype(np.int64), g["var"].astype(np.int64),
+                                     g["w_ch"], g["w_res"], int(g["iters"]), g["gt_e"])
+    np.testing.assert_allclose(r["c2v"], g["c2v"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(r["final"], g["final"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(r["soft"], g["soft"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(r["max_loss"], g["max_loss"], rtol=1e-5)
+    assert np.array_equal(g["llr_e"], g["llr"][:, g["out_index"][0]])
+
+
 @pytest.mark.parametrize("name,layers", [("gnn_z4_b4", 5), ("gnn_z32_b2", 5)])
 def test_gnn_oracle_matches_reference(name, layers):
     g = load_golden(name)

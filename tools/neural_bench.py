@@ -1,0 +1,67 @@
+#!/usr/bin/env python
+"""Throughput of LDPCNeuralDecoder (unrolled neural min-sum, edge space) on one GPU:
+fused variable+residual kernel vs the literal two-layer composition, inference and one
+training step (forward + loss.mean().backward()).  BG2 Z=32, E = 6304.
+Usage: python tools/neural_bench.py [--batch 4096] [--iters 5] [--reps 5]"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import ldpc_b200  # noqa: E402,F401
+from ldpc_b200.models import LDPCNeuralDecoder  # noqa: E402
+from ldpc_b200.utils import QCCode, create_LLR_mapping  # noqa: E402
+
+
+def timed(fn, reps):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=4096)
+    ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--reps", type=int, default=5)
+    args = ap.parse_args()
+    dev = "cuda:0"
+    code = QCCode.nr_2_0(32)
+    _, cidx, vidx, oidx = create_LLR_mapping(code.dense().T)
+    cidx, vidx = cidx.to(dev), vidx.to(dev)
+    g = torch.Generator(device=dev).manual_seed(1)
+    llr = (torch.randn(args.batch, code.N, device=dev, generator=g) * 0.5 + 0.4)
+    llr_e = llr[:, oidx[0].to(dev)].contiguous()
+    gt = torch.ones_like(llr_e)
+    out = {"batch": args.batch, "iters": args.iters, "E": code.E}
+    for fused in (True, False):
+        dec = LDPCNeuralDecoder(code.E, args.iters, 2, fused=fused).to(dev)
+
+        def infer():
+            with torch.no_grad():
+                dec(llr_e, cidx, vidx)
+
+        def train():
+            dec.zero_grad(set_to_none=True)
+            _, ml = dec(llr_e, cidx, vidx, gt)
+            ml.mean().backward()
+
+        ms_i, ms_t = timed(infer, args.reps), timed(train, args.reps)
+        tag = "fused" if fused else "composed"
+        out[tag] = {"infer_ms": ms_i, "infer_cw_per_s": args.batch / ms_i * 1e3,
+                    "train_ms": ms_t, "train_cw_per_s": args.batch / ms_t * 1e3}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
