@@ -193,6 +193,16 @@ int ldpc_neural_pack_index(const int64_t* idx, int64_t E, int K, uint16_t* out, 
 int ldpc_neural_decode(const float* llr_e, const uint16_t* cidx, int Kc, const uint16_t* vidx, int Kv, const float* w_ch,
                        const float* w_res, int L, int iters, int64_t B, int64_t E, const float* gt_e, float* soft,
                        float* max_loss, void* stream);
+/* The three gather-type forwards with the neighbour table packed by ldpc_neural_pack_index
+ * ([K,E] uint16, 0xFFFF = -1): same arithmetic and results as the int64 entry points above
+ * (layers.py:14-66, :78-125, notebook cell 11), coalesced index loads.                    */
+int ldpc_check_layer_fwd_packed(const float* x, const uint16_t* idx16, int64_t B, int64_t E, int K, float* out,
+                                int32_t* argmin_out, void* stream);
+int ldpc_variable_layer_fwd_packed(const float* llr, const float* c2v, const uint16_t* idx16, int64_t B, int64_t E, int K,
+                                   float* out, void* stream);
+int ldpc_neural_variable_layer_fwd_packed(const float* llr, const float* c2v, const uint16_t* idx16, const float* w_ch,
+                                          const float* w_res, const float* const* prev, int L, int64_t B, int64_t E,
+                                          int K, float* out, void* stream);
 /* OutputLayer.forward, layers.py:180-210: soft = sigmoid(final+llr); if gt: per-row max of
  * BCE(soft, gt) -> max_loss [B], argmax [B] int32 (for the backward).                    */
 int ldpc_output_layer_fwd(const float* final_llr, const float* llr, const float* gt, int64_t B, int64_t E,

@@ -12,9 +12,13 @@
 
 #include "common.cuh"
 
+#ifndef LDPC_LAYER_THREADS
+#define LDPC_LAYER_THREADS 1024
+#endif
+
 namespace ldpc {
 
-constexpr int kLayerThreads = 256;
+constexpr int kLayerThreads = LDPC_LAYER_THREADS;
 
 // rows of x staged per CTA: as many as fit 200 KB, at most 8
 inline int layer_rows_per_cta(long long E) {
@@ -22,9 +26,25 @@ inline int layer_rows_per_cta(long long E) {
     return r < 1 ? 0 : (r > 8 ? 8 : (int)r);
 }
 
-template <int kRows, bool kStage>
+// Neighbour-table accessors.  IdxI64 reads the reference layout directly ([E,K] int64, -1 padded): a warp's load
+// of slot k touches 32 rows K*8 bytes apart = 32 L1 wavefronts, which is what bounds the layer kernels (ncu launch
+// list r1: variable layer 606 us per 4096 x 6304 pass).  IdxU16 reads the table packed once per code by
+// ldpc_neural_pack_index ([K,E] uint16, 0xFFFF padded): one 64-byte wavefront per warp and slot.
+struct IdxI64 {
+    const long long* p;
+    __device__ __forceinline__ long long operator()(long long e, int k, long long, int K) const { return p[e * K + k]; }
+};
+struct IdxU16 {
+    const unsigned short* p;
+    __device__ __forceinline__ long long operator()(long long e, int k, long long E, int) const {
+        const unsigned short n = p[(long long)k * E + e];
+        return n == 0xFFFFu ? -1ll : (long long)n;
+    }
+};
+
+template <int kRows, bool kStage, class Idx = IdxI64>
 __global__ void __launch_bounds__(kLayerThreads) check_layer_fwd_kernel(const float* __restrict__ x,
-                                                                        const long long* __restrict__ idx, long long B,
+                                                                        const Idx idx, long long B,
                                                                         long long E, int K, float* __restrict__ out,
                                                                         int* __restrict__ argmin_out) {
     extern __shared__ float xs[];   // [kRows][E] when staged
@@ -41,7 +61,7 @@ __global__ void __launch_bounds__(kLayerThreads) check_layer_fwd_kernel(const fl
 #pragma unroll
             for (int q = 0; q < kRows; ++q) { sp[q] = 1.0f; mn[q] = CUDART_INF_F; am[q] = -1; }
             for (int k = 0; k < K; ++k) {
-                const long long n = idx[e * K + k];
+                const long long n = idx(e, k, E, K);
 #pragma unroll
                 for (int q = 0; q < kRows; ++q)
                     if (q < nb) {
@@ -91,10 +111,10 @@ __global__ void __launch_bounds__(kLayerThreads) check_layer_bwd_kernel(const fl
     }
 }
 
-template <int kRows, bool kStage>
+template <int kRows, bool kStage, class Idx = IdxI64>
 __global__ void __launch_bounds__(kLayerThreads) variable_layer_fwd_kernel(const float* __restrict__ llr,
                                                                            const float* __restrict__ c2v,
-                                                                           const long long* __restrict__ idx,
+                                                                           const Idx idx,
                                                                            long long B, long long E, int K,
                                                                            float* __restrict__ out) {
     extern __shared__ float xs[];
@@ -110,7 +130,7 @@ __global__ void __launch_bounds__(kLayerThreads) variable_layer_fwd_kernel(const
 #pragma unroll
             for (int q = 0; q < kRows; ++q) acc[q] = 0.0f;
             for (int k = 0; k < K; ++k) {
-                const long long n = idx[e * K + k];
+                const long long n = idx(e, k, E, K);
                 if (n < 0) continue;
 #pragma unroll
                 for (int q = 0; q < kRows; ++q)
@@ -164,9 +184,9 @@ __global__ void __launch_bounds__(kLayerThreads) residual_layer_fwd_kernel(const
 // reference): out = (w_ch*llr + sum_k c2v[idx[e,k]]) + sum_{i<L} w_res[i]*prev[i], same operation
 // order as VariableLayer(0, c2v) followed by ResidualLayer, so the result is bit-identical to the
 // two-kernel composition while the gathered sum never makes a round trip through HBM.
-template <int kRows, bool kStage>
+template <int kRows, bool kStage, class Idx = IdxI64>
 __global__ void __launch_bounds__(kLayerThreads) neural_variable_fwd_kernel(
-    const float* __restrict__ llr, const float* __restrict__ c2v, const long long* __restrict__ idx,
+    const float* __restrict__ llr, const float* __restrict__ c2v, const Idx idx,
     const float* __restrict__ w_ch, const float* __restrict__ w_res, ResidualPtrs prev, int L, long long B,
     long long E, int K, float* __restrict__ out) {
     extern __shared__ float xs[];
@@ -185,7 +205,7 @@ __global__ void __launch_bounds__(kLayerThreads) neural_variable_fwd_kernel(
 #pragma unroll
             for (int q = 0; q < kRows; ++q) acc[q] = 0.0f;
             for (int k = 0; k < K; ++k) {
-                const long long n = idx[e * K + k];
+                const long long n = idx(e, k, E, K);
                 if (n < 0) continue;
 #pragma unroll
                 for (int q = 0; q < kRows; ++q)

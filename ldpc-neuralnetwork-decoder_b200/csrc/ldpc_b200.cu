@@ -357,23 +357,23 @@ int ldpc_sim_fer(const ldpc_code_t* code, int algo, int iters, float alpha, floa
 }
 
 // ---- edge-space layers ---------------------------------------------------------------------
-#define LDPC_LAYER_DISPATCH(KERNEL, ...)                                                            \
+#define LDPC_LAYER_DISPATCH(KERNEL, IDX, ...)                                                            \
     do {                                                                                            \
         const int rows = layer_rows_per_cta(E);                                                     \
         const int grid = layer_grid(rows ? (B + rows - 1) / rows : B, 1);                           \
         const size_t smem = (size_t)rows * E * sizeof(float);                                       \
         switch (rows) {                                                                             \
-            case 0: KERNEL<1, false><<<grid, kLayerThreads, 0, st>>>(__VA_ARGS__); break;           \
-            case 1: LDPC_CUDA(cudaFuncSetAttribute(KERNEL<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-                    KERNEL<1, true><<<grid, kLayerThreads, smem, st>>>(__VA_ARGS__); break;         \
+            case 0: KERNEL<1, false, IDX><<<grid, kLayerThreads, 0, st>>>(__VA_ARGS__); break;           \
+            case 1: LDPC_CUDA(cudaFuncSetAttribute(KERNEL<1, true, IDX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+                    KERNEL<1, true, IDX><<<grid, kLayerThreads, smem, st>>>(__VA_ARGS__); break;         \
             case 2: case 3: { const size_t sm2 = (size_t)2 * E * sizeof(float);                     \
-                    LDPC_CUDA(cudaFuncSetAttribute(KERNEL<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2)); \
-                    KERNEL<2, true><<<layer_grid((B + 1) / 2, 1), kLayerThreads, sm2, st>>>(__VA_ARGS__); break; } \
+                    LDPC_CUDA(cudaFuncSetAttribute(KERNEL<2, true, IDX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2)); \
+                    KERNEL<2, true, IDX><<<layer_grid((B + 1) / 2, 1), kLayerThreads, sm2, st>>>(__VA_ARGS__); break; } \
             case 4: case 5: case 6: case 7: { const size_t sm4 = (size_t)4 * E * sizeof(float);     \
-                    LDPC_CUDA(cudaFuncSetAttribute(KERNEL<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4)); \
-                    KERNEL<4, true><<<layer_grid((B + 3) / 4, 1), kLayerThreads, sm4, st>>>(__VA_ARGS__); break; } \
-            default: LDPC_CUDA(cudaFuncSetAttribute(KERNEL<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-                    KERNEL<8, true><<<grid, kLayerThreads, smem, st>>>(__VA_ARGS__); break;         \
+                    LDPC_CUDA(cudaFuncSetAttribute(KERNEL<4, true, IDX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4)); \
+                    KERNEL<4, true, IDX><<<layer_grid((B + 3) / 4, 1), kLayerThreads, sm4, st>>>(__VA_ARGS__); break; } \
+            default: LDPC_CUDA(cudaFuncSetAttribute(KERNEL<8, true, IDX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+                    KERNEL<8, true, IDX><<<grid, kLayerThreads, smem, st>>>(__VA_ARGS__); break;         \
         }                                                                                           \
     } while (0)
 
@@ -383,7 +383,7 @@ int ldpc_check_layer_fwd(const float* x, const int64_t* idx, int64_t B, int64_t 
     if (B < 0 || E <= 0 || K <= 0) return fail(LDPC_ERR_INVALID, "check_layer_fwd: bad shape");
     if (B == 0) return LDPC_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    LDPC_LAYER_DISPATCH(check_layer_fwd_kernel, x, (const long long*)idx, (long long)B, (long long)E, K, out, argmin_out);
+    LDPC_LAYER_DISPATCH(check_layer_fwd_kernel, IdxI64, x, IdxI64{(const long long*)idx}, (long long)B, (long long)E, K, out, argmin_out);
     LDPC_CHECK_LAUNCH("check_layer_fwd_kernel");
     return LDPC_OK;
 }
@@ -407,7 +407,7 @@ int ldpc_variable_layer_fwd(const float* llr, const float* c2v, const int64_t* i
     if (B < 0 || E <= 0 || K <= 0) return fail(LDPC_ERR_INVALID, "variable_layer_fwd: bad shape");
     if (B == 0) return LDPC_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    LDPC_LAYER_DISPATCH(variable_layer_fwd_kernel, llr, c2v, (const long long*)idx, (long long)B, (long long)E, K, out);
+    LDPC_LAYER_DISPATCH(variable_layer_fwd_kernel, IdxI64, llr, c2v, IdxI64{(const long long*)idx}, (long long)B, (long long)E, K, out);
     LDPC_CHECK_LAUNCH("variable_layer_fwd_kernel");
     return LDPC_OK;
 }
@@ -456,9 +456,52 @@ int ldpc_neural_variable_layer_fwd(const float* llr, const float* c2v, const int
         rp.prev[i] = prev[i];
     }
     cudaStream_t st = (cudaStream_t)stream;
-    LDPC_LAYER_DISPATCH(neural_variable_fwd_kernel, llr, c2v, (const long long*)idx, w_ch, w_res, rp, L, (long long)B,
-                        (long long)E, K, out);
+    LDPC_LAYER_DISPATCH(neural_variable_fwd_kernel, IdxI64, llr, c2v, IdxI64{(const long long*)idx}, w_ch, w_res, rp, L,
+                        (long long)B, (long long)E, K, out);
     LDPC_CHECK_LAUNCH("neural_variable_fwd_kernel");
+    return LDPC_OK;
+}
+
+// Packed-table variants: idx16 = [K,E] uint16 from ldpc_neural_pack_index (coalesced index loads).
+int ldpc_check_layer_fwd_packed(const float* x, const uint16_t* idx16, int64_t B, int64_t E, int K, float* out,
+                                int32_t* argmin_out, void* stream) {
+    if (!x || !idx16 || !out) return fail(LDPC_ERR_INVALID, "check_layer_fwd_packed: null argument");
+    if (B < 0 || E <= 0 || K <= 0 || E >= 0xFFFF) return fail(LDPC_ERR_INVALID, "check_layer_fwd_packed: bad shape");
+    if (B == 0) return LDPC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    LDPC_LAYER_DISPATCH(check_layer_fwd_kernel, IdxU16, x, IdxU16{idx16}, (long long)B, (long long)E, K, out, argmin_out);
+    LDPC_CHECK_LAUNCH("check_layer_fwd_kernel(packed)");
+    return LDPC_OK;
+}
+
+int ldpc_variable_layer_fwd_packed(const float* llr, const float* c2v, const uint16_t* idx16, int64_t B, int64_t E, int K,
+                                   float* out, void* stream) {
+    if (!llr || !c2v || !idx16 || !out) return fail(LDPC_ERR_INVALID, "variable_layer_fwd_packed: null argument");
+    if (B < 0 || E <= 0 || K <= 0 || E >= 0xFFFF) return fail(LDPC_ERR_INVALID, "variable_layer_fwd_packed: bad shape");
+    if (B == 0) return LDPC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    LDPC_LAYER_DISPATCH(variable_layer_fwd_kernel, IdxU16, llr, c2v, IdxU16{idx16}, (long long)B, (long long)E, K, out);
+    LDPC_CHECK_LAUNCH("variable_layer_fwd_kernel(packed)");
+    return LDPC_OK;
+}
+
+int ldpc_neural_variable_layer_fwd_packed(const float* llr, const float* c2v, const uint16_t* idx16, const float* w_ch,
+                                          const float* w_res, const float* const* prev, int L, int64_t B, int64_t E,
+                                          int K, float* out, void* stream) {
+    if (!llr || !c2v || !idx16 || !w_ch || !out || (L > 0 && (!prev || !w_res)))
+        return fail(LDPC_ERR_INVALID, "neural_variable_layer_fwd_packed: null argument");
+    if (L < 0 || L > kMaxResidual) return fail(LDPC_ERR_UNSUPPORTED, "neural_variable_layer_fwd_packed: depth %d outside 0..%d", L, kMaxResidual);
+    if (B < 0 || E <= 0 || K <= 0 || E >= 0xFFFF) return fail(LDPC_ERR_INVALID, "neural_variable_layer_fwd_packed: bad shape");
+    if (B == 0) return LDPC_OK;
+    ResidualPtrs rp{};
+    for (int i = 0; i < L; ++i) {
+        if (!prev[i]) return fail(LDPC_ERR_INVALID, "neural_variable_layer_fwd_packed: prev[%d] is null", i);
+        rp.prev[i] = prev[i];
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    LDPC_LAYER_DISPATCH(neural_variable_fwd_kernel, IdxU16, llr, c2v, IdxU16{idx16}, w_ch, w_res, rp, L, (long long)B,
+                        (long long)E, K, out);
+    LDPC_CHECK_LAUNCH("neural_variable_fwd_kernel(packed)");
     return LDPC_OK;
 }
 
@@ -473,18 +516,27 @@ int ldpc_neural_pack_index(const int64_t* idx, int64_t E, int K, uint16_t* out, 
 
 }  // extern "C"
 
+template <int kRows, int KC, int KV>
+static int launch_neural_k(const float* llr, const uint16_t* cidx, int Kc, const uint16_t* vidx, int Kv, const float* w_ch,
+                           const float* w_res, int L, int iters, int64_t B, int E, const float* gt, float* soft,
+                           float* max_loss, size_t smem, cudaStream_t st) {
+    LDPC_CUDA(cudaFuncSetAttribute(neural_decode_kernel<kRows, KC, KV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int ctas_per_sm = smem * 2 + 8192 <= (size_t)227 * 1024 ? 2 : 1;
+    long long grid = (B + kRows - 1) / kRows;
+    if (grid > (long long)kNumSMs * ctas_per_sm) grid = (long long)kNumSMs * ctas_per_sm;
+    neural_decode_kernel<kRows, KC, KV><<<(int)grid, kNeuralThreads, smem, st>>>(
+        llr, cidx, Kc, vidx, Kv, w_ch, w_res, L, iters, (long long)B, E, gt, soft, max_loss);
+    LDPC_CHECK_LAUNCH("neural_decode_kernel");
+    return LDPC_OK;
+}
+
 template <int kRows>
 static int launch_neural(const float* llr, const uint16_t* cidx, int Kc, const uint16_t* vidx, int Kv, const float* w_ch,
                          const float* w_res, int L, int iters, int64_t B, int E, const float* gt, float* soft,
                          float* max_loss, size_t smem, cudaStream_t st) {
-    LDPC_CUDA(cudaFuncSetAttribute(neural_decode_kernel<kRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int ctas_per_sm = smem * 2 + 8192 <= (size_t)227 * 1024 ? 2 : 1;
-    long long grid = (B + kRows - 1) / kRows;
-    if (grid > (long long)kNumSMs * ctas_per_sm) grid = (long long)kNumSMs * ctas_per_sm;
-    neural_decode_kernel<kRows><<<(int)grid, kNeuralThreads, smem, st>>>(llr, cidx, Kc, vidx, Kv, w_ch, w_res, L, iters,
-                                                                       (long long)B, E, gt, soft, max_loss);
-    LDPC_CHECK_LAUNCH("neural_decode_kernel");
-    return LDPC_OK;
+    if (Kc == 9 && Kv == 22)      // create_LLR_mapping on the 5G BG2 graphs (max degrees 10 / 23)
+        return launch_neural_k<kRows, 9, 22>(llr, cidx, Kc, vidx, Kv, w_ch, w_res, L, iters, B, E, gt, soft, max_loss, smem, st);
+    return launch_neural_k<kRows, 0, 0>(llr, cidx, Kc, vidx, Kv, w_ch, w_res, L, iters, B, E, gt, soft, max_loss, smem, st);
 }
 
 extern "C" {

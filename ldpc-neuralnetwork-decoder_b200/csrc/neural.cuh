@@ -41,13 +41,17 @@ __global__ void neural_pack_index_kernel(const long long* __restrict__ idx, long
     }
 }
 
-template <int kRows>
+// KC / KV: compile-time neighbour-table widths (0 = use the run-time Kc / Kv).  With the widths of
+// the 5G BG2 tables (9 / 22) known, the k loops unroll completely and a thread has all its index
+// loads in flight before the first shared-memory gather -- the kernel is latency-, not bandwidth-bound.
+template <int kRows, int KC, int KV>
 __global__ void __launch_bounds__(kNeuralThreads) neural_decode_kernel(
-    const float* __restrict__ llr, const unsigned short* __restrict__ cidx, int Kc,
-    const unsigned short* __restrict__ vidx, int Kv, const float* __restrict__ w_ch,
+    const float* __restrict__ llr, const unsigned short* __restrict__ cidx, int Kc_rt,
+    const unsigned short* __restrict__ vidx, int Kv_rt, const float* __restrict__ w_ch,
     const float* __restrict__ w_res, int L, int iters, long long B, int E, const float* __restrict__ gt,
     float* __restrict__ soft, float* __restrict__ max_loss) {
     extern __shared__ float sm[];
+    const int Kc = KC ? KC : Kc_rt, Kv = KV ? KV : Kv_rt;
     const int Lb = L > 0 ? L : 1;
     float* c2v = sm;                                  // [kRows][E]
     float* ring = sm + (size_t)kRows * E;             // [Lb][kRows][E]
@@ -68,7 +72,7 @@ __global__ void __launch_bounds__(kNeuralThreads) neural_decode_kernel(
                 float sp[kRows], mn[kRows];
 #pragma unroll
                 for (int q = 0; q < kRows; ++q) { sp[q] = 1.0f; mn[q] = CUDART_INF_F; }
-#pragma unroll 3
+#pragma unroll
                 for (int k = 0; k < Kc; ++k) {
                     const unsigned short n = cidx[(size_t)k * E + e];
 #pragma unroll
@@ -92,7 +96,7 @@ __global__ void __launch_bounds__(kNeuralThreads) neural_decode_kernel(
                 float acc[kRows];
 #pragma unroll
                 for (int q = 0; q < kRows; ++q) acc[q] = 0.0f;
-#pragma unroll 4
+#pragma unroll
                 for (int k = 0; k < Kv; ++k) {
                     const unsigned short n = vidx[(size_t)k * E + e];
                     if (n == kNeuralPad) continue;
@@ -123,7 +127,7 @@ __global__ void __launch_bounds__(kNeuralThreads) neural_decode_kernel(
             float acc[kRows];
 #pragma unroll
             for (int q = 0; q < kRows; ++q) acc[q] = 0.0f;
-#pragma unroll 4
+#pragma unroll
             for (int k = 0; k < Kv; ++k) {
                 const unsigned short n = vidx[(size_t)k * E + e];
                 if (n == kNeuralPad) continue;

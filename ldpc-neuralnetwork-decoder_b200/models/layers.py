@@ -23,22 +23,100 @@ def _need_cuda(*ts):
             raise RuntimeError("the LDPC engine layers need CUDA tensors (no CPU fallback)")
 
 
+# ---- neighbour tables, packed once per tensor -----------------------------------------------
+# The reference hands every layer call the [E,K] int64 table (utils/ldpc_utils.py:48-58).  The
+# kernels read it far faster as k-major uint16 (csrc/layers.cuh IdxU16), so the first call with
+# a given tensor packs it on the device (ldpc_neural_pack_index) and later calls reuse the copy;
+# the key holds the tensor's address and version counter, the entry keeps the tensor alive.
+_PACK_CACHE = {}
+_PACK_LIMIT = 16
+
+
+class _Packed:
+    __slots__ = ("src", "table", "symmetric")
+
+
+def packed_index(idx):
+    """-> _Packed(table [K,E] int16 view of the uint16 words, symmetric flag) or None when the
+    table cannot be packed (E >= 65535)."""
+    E, K = idx.shape
+    if E >= 0xFFFF:
+        return None
+    key = (idx.data_ptr(), idx._version, E, K, idx.dtype, str(idx.device))
+    hit = _PACK_CACHE.get(key)
+    if hit is None:
+        src = idx.to(torch.int64).contiguous()
+        out = torch.empty((K, E), dtype=torch.int16, device=src.device)
+        with torch.cuda.device(src.device):
+            _native.check(_native.lib().ldpc_neural_pack_index(
+                _native.ptr(src), E, K, _native.ptr(out), _native.stream_ptr(src.device)))
+        # "n is listed by e  <=>  e is listed by n" (true for the reference's tables: the OTHER edges of the same
+        # node).  Then the transpose of the gather is the same gather and backward needs no atomics.
+        e_of = torch.arange(E, device=src.device).unsqueeze(1).expand(E, K)[src >= 0]
+        n_of = src[src >= 0]
+        hit = _Packed()
+        hit.src, hit.table = idx, out
+        hit.symmetric = bool(torch.equal(torch.sort(e_of * E + n_of).values, torch.sort(n_of * E + e_of).values))
+        if len(_PACK_CACHE) >= _PACK_LIMIT:
+            _PACK_CACHE.clear()
+        _PACK_CACHE[key] = hit
+    return hit
+
+
+def _gather_sum(llr, c2v, idx):
+    """llr + sum_k c2v[:, idx[:, k]] on the engine (VariableLayer arithmetic, layers.py:78-125)."""
+    B, E = c2v.shape
+    out = torch.empty_like(c2v)
+    pk = packed_index(idx)
+    with torch.cuda.device(c2v.device):
+        if pk is not None:
+            _native.check(_native.lib().ldpc_variable_layer_fwd_packed(
+                _native.ptr(llr), _native.ptr(c2v), _native.ptr(pk.table), B, E, idx.shape[1], _native.ptr(out),
+                _native.stream_ptr(c2v.device)))
+        else:
+            idx = idx.to(torch.int64).contiguous()
+            _native.check(_native.lib().ldpc_variable_layer_fwd(
+                _native.ptr(llr), _native.ptr(c2v), _native.ptr(idx), B, E, idx.shape[1], _native.ptr(out),
+                _native.stream_ptr(c2v.device)))
+    return out
+
+
+def _gather_sum_transposed(idx, g):
+    """grad_c2v[b, n] = sum over (e, k) with idx[e, k] == n of g[b, e]."""
+    B, E = g.shape
+    pk = packed_index(idx)
+    if pk is not None and pk.symmetric:
+        return _gather_sum(torch.zeros_like(g), g, idx)            # same gather, deterministic, no atomics
+    idx = idx.to(torch.int64).contiguous()
+    gc = torch.empty_like(g)
+    with torch.cuda.device(g.device):
+        _native.check(_native.lib().ldpc_variable_layer_bwd(
+            _native.ptr(idx), _native.ptr(g), B, E, idx.shape[1], _native.ptr(gc), _native.stream_ptr(g.device)))
+    return gc
+
+
 class _CheckFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, idx):
         _need_cuda(x, idx)
         x = x.detach().to(torch.float32).contiguous()
-        idx = idx.to(torch.int64).contiguous()
         B, E = x.shape
         Em, K = idx.shape
         if Em != E:
             raise ValueError("check_index_tensor must have one row per edge")
         out = torch.empty_like(x)
         am = torch.empty((B, E), dtype=torch.int32, device=x.device)
+        pk = packed_index(idx)
+        idx = idx.to(torch.int64).contiguous()
         with torch.cuda.device(x.device):
-            _native.check(_native.lib().ldpc_check_layer_fwd(
-                _native.ptr(x), _native.ptr(idx), B, E, K, _native.ptr(out), _native.ptr(am),
-                _native.stream_ptr(x.device)))
+            if pk is not None:
+                _native.check(_native.lib().ldpc_check_layer_fwd_packed(
+                    _native.ptr(x), _native.ptr(pk.table), B, E, K, _native.ptr(out), _native.ptr(am),
+                    _native.stream_ptr(x.device)))
+            else:
+                _native.check(_native.lib().ldpc_check_layer_fwd(
+                    _native.ptr(x), _native.ptr(idx), B, E, K, _native.ptr(out), _native.ptr(am),
+                    _native.stream_ptr(x.device)))
         ctx.save_for_backward(x, idx, am)
         return out
 
@@ -61,13 +139,9 @@ class _VariableFn(torch.autograd.Function):
         _need_cuda(llr, c2v, idx)
         llr = llr.detach().to(torch.float32).contiguous()
         c2v = c2v.detach().to(torch.float32).contiguous()
-        idx = idx.to(torch.int64).contiguous()
-        B, E = c2v.shape
-        out = torch.empty_like(c2v)
-        with torch.cuda.device(c2v.device):
-            _native.check(_native.lib().ldpc_variable_layer_fwd(
-                _native.ptr(llr), _native.ptr(c2v), _native.ptr(idx), B, E, idx.shape[1], _native.ptr(out),
-                _native.stream_ptr(c2v.device)))
+        if idx.shape[0] != c2v.shape[1]:
+            raise ValueError("var_index_tensor must have one row per edge")
+        out = _gather_sum(llr, c2v, idx)
         ctx.save_for_backward(idx)
         return out
 
@@ -75,13 +149,7 @@ class _VariableFn(torch.autograd.Function):
     def backward(ctx, g):
         (idx,) = ctx.saved_tensors
         g = g.to(torch.float32).contiguous()
-        B, E = g.shape
-        gc = torch.empty_like(g)
-        with torch.cuda.device(g.device):
-            _native.check(_native.lib().ldpc_variable_layer_bwd(
-                _native.ptr(idx), _native.ptr(g), B, E, idx.shape[1], _native.ptr(gc),
-                _native.stream_ptr(g.device)))
-        return g, gc, None
+        return g, _gather_sum_transposed(idx, g), None
 
 
 class _ResidualFn(torch.autograd.Function):
