@@ -516,49 +516,49 @@ int ldpc_neural_pack_index(const int64_t* idx, int64_t E, int K, uint16_t* out, 
 
 }  // extern "C"
 
+struct NeuralArgs {
+    const float* llr; const uint16_t* cidx; int Kc; const uint16_t* cperm; const uint16_t* vidx; int Kv; const uint16_t* vperm;
+    const float* w_ch; const float* w_res; int L; int iters; int64_t B; int E; const float* gt; float* soft; float* max_loss;
+};
+
 template <int kRows, int KC, int KV>
-static int launch_neural_k(const float* llr, const uint16_t* cidx, int Kc, const uint16_t* vidx, int Kv, const float* w_ch,
-                           const float* w_res, int L, int iters, int64_t B, int E, const float* gt, float* soft,
-                           float* max_loss, size_t smem, cudaStream_t st) {
+static int launch_neural_k(const NeuralArgs& a, size_t smem, cudaStream_t st) {
     LDPC_CUDA(cudaFuncSetAttribute(neural_decode_kernel<kRows, KC, KV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int ctas_per_sm = smem * 2 + 8192 <= (size_t)227 * 1024 ? 2 : 1;
-    long long grid = (B + kRows - 1) / kRows;
+    long long grid = (a.B + kRows - 1) / kRows;
     if (grid > (long long)kNumSMs * ctas_per_sm) grid = (long long)kNumSMs * ctas_per_sm;
     neural_decode_kernel<kRows, KC, KV><<<(int)grid, kNeuralThreads, smem, st>>>(
-        llr, cidx, Kc, vidx, Kv, w_ch, w_res, L, iters, (long long)B, E, gt, soft, max_loss);
+        a.llr, a.cidx, a.Kc, a.cperm, a.vidx, a.Kv, a.vperm, a.w_ch, a.w_res, a.L, a.iters, (long long)a.B, a.E, a.gt,
+        a.soft, a.max_loss);
     LDPC_CHECK_LAUNCH("neural_decode_kernel");
     return LDPC_OK;
 }
 
 template <int kRows>
-static int launch_neural(const float* llr, const uint16_t* cidx, int Kc, const uint16_t* vidx, int Kv, const float* w_ch,
-                         const float* w_res, int L, int iters, int64_t B, int E, const float* gt, float* soft,
-                         float* max_loss, size_t smem, cudaStream_t st) {
-    if (Kc == 9 && Kv == 22)      // create_LLR_mapping on the 5G BG2 graphs (max degrees 10 / 23)
-        return launch_neural_k<kRows, 9, 22>(llr, cidx, Kc, vidx, Kv, w_ch, w_res, L, iters, B, E, gt, soft, max_loss, smem, st);
-    return launch_neural_k<kRows, 0, 0>(llr, cidx, Kc, vidx, Kv, w_ch, w_res, L, iters, B, E, gt, soft, max_loss, smem, st);
+static int launch_neural(const NeuralArgs& a, size_t smem, cudaStream_t st) {
+    if (a.Kc == 9 && a.Kv == 22)      // create_LLR_mapping on the 5G BG2 graphs (max degrees 10 / 23)
+        return launch_neural_k<kRows, 9, 22>(a, smem, st);
+    return launch_neural_k<kRows, 0, 0>(a, smem, st);
 }
 
 extern "C" {
 
-int ldpc_neural_decode(const float* llr_e, const uint16_t* cidx, int Kc, const uint16_t* vidx, int Kv, const float* w_ch,
-                       const float* w_res, int L, int iters, int64_t B, int64_t E, const float* gt_e, float* soft,
-                       float* max_loss, void* stream) {
+int ldpc_neural_decode(const float* llr_e, const uint16_t* cidx, int Kc, const uint16_t* cperm, const uint16_t* vidx, int Kv,
+                       const uint16_t* vperm, const float* w_ch, const float* w_res, int L, int iters, int64_t B, int64_t E,
+                       const float* gt_e, float* soft, float* max_loss, void* stream) {
     if (!llr_e || !cidx || !vidx || !w_ch || !soft || (L > 0 && !w_res)) return fail(LDPC_ERR_INVALID, "neural_decode: null argument");
     if (gt_e && !max_loss) return fail(LDPC_ERR_INVALID, "neural_decode: ground truth given without max_loss buffer");
     if (L < 0 || L > kMaxResidual) return fail(LDPC_ERR_UNSUPPORTED, "neural_decode: depth %d outside 0..%d", L, kMaxResidual);
     if (iters < 1 || B < 0 || E <= 0 || Kc <= 0 || Kv <= 0) return fail(LDPC_ERR_INVALID, "neural_decode: bad shape");
     if (E >= 0xFFFF) return fail(LDPC_ERR_UNSUPPORTED, "neural_decode: %lld edges do not fit 16-bit indices", (long long)E);
     if (B == 0) return LDPC_OK;
-    const size_t per_row = (size_t)((L > 0 ? L : 1) + 1) * E * sizeof(float);
+    const NeuralArgs a{llr_e, cidx, Kc, cperm, vidx, Kv, vperm, w_ch, w_res, L, iters, B, (int)E, gt_e, soft, max_loss};
+    const size_t per_row = (size_t)((L > 0 ? L : 1) + 2) * E * sizeof(float);   // c2v + llr + ring
     const size_t cap = (size_t)220 * 1024;
     cudaStream_t st = (cudaStream_t)stream;
-    if (4 * per_row <= cap && B >= 4 * 2 * kNumSMs)
-        return launch_neural<4>(llr_e, cidx, Kc, vidx, Kv, w_ch, w_res, L, iters, B, (int)E, gt_e, soft, max_loss, 4 * per_row, st);
-    if (2 * per_row <= cap && B >= 2 * kNumSMs)
-        return launch_neural<2>(llr_e, cidx, Kc, vidx, Kv, w_ch, w_res, L, iters, B, (int)E, gt_e, soft, max_loss, 2 * per_row, st);
-    if (per_row <= cap)
-        return launch_neural<1>(llr_e, cidx, Kc, vidx, Kv, w_ch, w_res, L, iters, B, (int)E, gt_e, soft, max_loss, per_row, st);
+    if (4 * per_row <= cap && B >= 4 * 2 * kNumSMs) return launch_neural<4>(a, 4 * per_row, st);
+    if (2 * per_row <= cap && B >= 2 * kNumSMs) return launch_neural<2>(a, 2 * per_row, st);
+    if (per_row <= cap) return launch_neural<1>(a, per_row, st);
     return fail(LDPC_ERR_UNSUPPORTED, "neural_decode: %zu bytes of resident state per codeword exceed shared memory", per_row);
 }
 

@@ -33,7 +33,29 @@ _PACK_LIMIT = 16
 
 
 class _Packed:
-    __slots__ = ("src", "table", "symmetric")
+    __slots__ = ("src", "table", "symmetric", "_i64", "_sorted")
+
+    def sorted(self):
+        """(table [K,E], perm [E]) for the one-kernel decoder: edges ordered by descending neighbour count, the
+        padding of each row compacted to its end (valid neighbours keep the caller's order), column t = edge perm[t]."""
+        if self._sorted is None:
+            src = self._i64
+            E, K = src.shape
+            valid = src >= 0
+            order = torch.argsort((~valid).to(torch.int8), dim=1, stable=True)
+            compact = torch.gather(src, 1, order)
+            perm = torch.argsort(valid.sum(dim=1), descending=True, stable=True)
+            self._sorted = (_pack(compact[perm].contiguous()), perm.to(torch.int32).to(torch.int16).contiguous())
+        return self._sorted
+
+
+def _pack(src):
+    E, K = src.shape
+    out = torch.empty((K, E), dtype=torch.int16, device=src.device)
+    with torch.cuda.device(src.device):
+        _native.check(_native.lib().ldpc_neural_pack_index(
+            _native.ptr(src), E, K, _native.ptr(out), _native.stream_ptr(src.device)))
+    return out
 
 
 def packed_index(idx):
@@ -46,16 +68,13 @@ def packed_index(idx):
     hit = _PACK_CACHE.get(key)
     if hit is None:
         src = idx.to(torch.int64).contiguous()
-        out = torch.empty((K, E), dtype=torch.int16, device=src.device)
-        with torch.cuda.device(src.device):
-            _native.check(_native.lib().ldpc_neural_pack_index(
-                _native.ptr(src), E, K, _native.ptr(out), _native.stream_ptr(src.device)))
+        out = _pack(src)
         # "n is listed by e  <=>  e is listed by n" (true for the reference's tables: the OTHER edges of the same
         # node).  Then the transpose of the gather is the same gather and backward needs no atomics.
         e_of = torch.arange(E, device=src.device).unsqueeze(1).expand(E, K)[src >= 0]
         n_of = src[src >= 0]
         hit = _Packed()
-        hit.src, hit.table = idx, out
+        hit.src, hit.table, hit._i64, hit._sorted = idx, out, src, None
         hit.symmetric = bool(torch.equal(torch.sort(e_of * E + n_of).values, torch.sort(n_of * E + e_of).values))
         if len(_PACK_CACHE) >= _PACK_LIMIT:
             _PACK_CACHE.clear()

@@ -97,3 +97,22 @@ def test_neural_decoder_slot_takes_the_gnn():
     ev = ComparativeEvaluator(base_graph=code.shifts, Z=Z, device=DEV, neural_decoder=dec, seed=1, max_iterations=5)
     res = ev.evaluate_all([2.0], batch_size=16, num_trials=2)
     assert set(res["neural_decoder"]) == {"ber", "fer"} and 0.0 <= res["neural_decoder"]["ber"][0] <= 1.0
+
+
+def test_neural_decoder_slot_takes_the_unrolled_min_sum_decoder():
+    """run_comparison.py:85-110 call shape: LDPCNeuralDecoder(num_nodes, num_iterations, depth_L) in the evaluator's
+    neural slot, index tensors passed to evaluate_all; (B, N) LLRs in, (B, N) bits out through output_index_tensor."""
+    from ldpc_b200.models import LDPCNeuralDecoder
+    from ldpc_b200.utils import create_LLR_mapping
+    Z = 4
+    code = QCCode.nr_2_0(Z)
+    _, cidx, vidx, oidx = create_LLR_mapping(code.dense().T)
+    dec = LDPCNeuralDecoder(num_nodes=code.E, num_iterations=5, depth_L=2, output_index_tensor=oidx)
+    ev = ComparativeEvaluator(base_graph=code.shifts, Z=Z, device=DEV, neural_decoder=dec, seed=1, max_iterations=5)
+    res = ev.evaluate_all([4.0], batch_size=64, num_trials=1, variable_bit_length=code.N,
+                          check_index_tensor=cidx, var_index_tensor=vidx)
+    nd = res["neural_decoder"]
+    assert set(nd) == {"ber", "fer"} and 0.0 <= nd["ber"][0] <= 1.0
+    # at 4 dB the unit-weight network is plain min-sum and decodes the all-zero codeword: with the reference's
+    # `soft > 0.5` rule (trainer.py:186) on sigmoid(LLR) that reads as all ones, i.e. BER = 1 against zeros
+    assert nd["ber"][0] > 0.95

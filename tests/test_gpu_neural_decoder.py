@@ -138,3 +138,35 @@ def test_z32_against_oracle_ragged_batch():
     plain.load_state_dict(dec.state_dict())
     args = (torch.from_numpy(llr_e).to(DEV), cidx.to(DEV), vidx.to(DEV))
     assert torch.equal(dec._messages(*args), plain._messages(*args))
+
+
+def test_c_abi_identity_order_equals_sorted_order():
+    """ldpc_neural_decode with cperm = vperm = NULL on the plainly packed tables (padding wherever the caller put
+    it) gives the same bits as the degree-sorted tables the Python class passes."""
+    from ldpc_b200 import _native
+    from ldpc_b200.models.layers import packed_index
+    g = load_golden("neural_decoder_z4")
+    cidx = torch.from_numpy(g["check"]).to(DEV).long()
+    vidx = torch.from_numpy(g["var"]).to(DEV).long()
+    # move some padding to the FRONT of the rows: the kernel must not rely on compacted tables
+    cidx = torch.flip(cidx, dims=[1]).contiguous()
+    E = g["llr_e"].shape[1]
+    B, iters, L = 77, 4, 2
+    rng = np.random.default_rng(3)
+    llr_e = torch.from_numpy((rng.normal(size=(B, E)) * 0.6 + 0.3).astype(np.float32)).to(DEV)
+    w_ch = torch.from_numpy((rng.random(E) * 0.5 + 0.75).astype(np.float32)).to(DEV)
+    w_res = torch.tensor([0.25, -0.125], device=DEV)
+    pc, pv = packed_index(cidx), packed_index(vidx)
+    outs = []
+    for (ct, cp), (vt, vp) in (((pc.table, None), (pv.table, None)), (pc.sorted(), pv.sorted())):
+        soft = torch.empty_like(llr_e)
+        _native.check(_native.lib().ldpc_neural_decode(
+            _native.ptr(llr_e), _native.ptr(ct), ct.shape[0], _native.ptr(cp), _native.ptr(vt), vt.shape[0],
+            _native.ptr(vp), _native.ptr(w_ch), _native.ptr(w_res), L, iters, B, E, None, _native.ptr(soft), None,
+            _native.stream_ptr(llr_e.device)))
+        outs.append(soft)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1])
+    ref = oracle.neural_minsum_forward(llr_e.cpu().numpy(), cidx.cpu().numpy(), vidx.cpu().numpy(), w_ch.cpu().numpy(),
+                                       w_res.cpu().numpy(), iters)
+    np.testing.assert_allclose(outs[0].cpu().numpy(), ref["soft"], rtol=1e-4, atol=1e-6)
