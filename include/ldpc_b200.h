@@ -188,14 +188,16 @@ int ldpc_neural_variable_layer_fwd(const float* llr, const float* c2v, const int
  * composition of the reference's missing models/decoder.py (notebook cell 11 `forward`).
  * Messages stay in shared memory across iterations; bit-identical to the per-layer entry
  * points.  cidx/vidx are the [E,K] int64 neighbour tables packed ONCE per code by
- * ldpc_neural_pack_index to [K,E] uint16 (0xFFFF = -1).  cperm / vperm (optional, [E]
- * uint16): column t of the packed table belongs to edge perm[t] -- the host sorts edges by
- * neighbour count so that warps skip the padding; NULL = identity.  gt_e / max_loss
- * optional.                                                                              */
+ * ldpc_neural_pack_index to [K,E] uint16, with every row COMPACTED first (valid entries
+ * first, caller's order; unused slots any index < E); ccnt / vcnt [E] uint8 = number of
+ * valid entries per column; cperm / vperm (optional, [E] uint16): column t belongs to edge
+ * perm[t] -- the host sorts columns by descending count so that warps skip the padding;
+ * NULL = identity.  L <= 4.  gt_e / max_loss optional.                                   */
 int ldpc_neural_pack_index(const int64_t* idx, int64_t E, int K, uint16_t* out, void* stream);
-int ldpc_neural_decode(const float* llr_e, const uint16_t* cidx, int Kc, const uint16_t* cperm, const uint16_t* vidx, int Kv,
-                       const uint16_t* vperm, const float* w_ch, const float* w_res, int L, int iters, int64_t B, int64_t E,
-                       const float* gt_e, float* soft, float* max_loss, void* stream);
+int ldpc_neural_decode(const float* llr_e, const uint16_t* cidx, int Kc, const uint8_t* ccnt, const uint16_t* cperm,
+                       const uint16_t* vidx, int Kv, const uint8_t* vcnt, const uint16_t* vperm, const float* w_ch,
+                       const float* w_res, int L, int iters, int64_t B, int64_t E, const float* gt_e, float* soft,
+                       float* max_loss, void* stream);
 /* The three gather-type forwards with the neighbour table packed by ldpc_neural_pack_index
  * ([K,E] uint16, 0xFFFF = -1): same arithmetic and results as the int64 entry points above
  * (layers.py:14-66, :78-125, notebook cell 11), coalesced index loads.                    */

@@ -517,7 +517,8 @@ int ldpc_neural_pack_index(const int64_t* idx, int64_t E, int K, uint16_t* out, 
 }  // extern "C"
 
 struct NeuralArgs {
-    const float* llr; const uint16_t* cidx; int Kc; const uint16_t* cperm; const uint16_t* vidx; int Kv; const uint16_t* vperm;
+    const float* llr; const uint16_t* cidx; int Kc; const uint8_t* ccnt; const uint16_t* cperm;
+    const uint16_t* vidx; int Kv; const uint8_t* vcnt; const uint16_t* vperm;
     const float* w_ch; const float* w_res; int L; int iters; int64_t B; int E; const float* gt; float* soft; float* max_loss;
 };
 
@@ -528,7 +529,7 @@ static int launch_neural_k(const NeuralArgs& a, size_t smem, cudaStream_t st) {
     long long grid = (a.B + kRows - 1) / kRows;
     if (grid > (long long)kNumSMs * ctas_per_sm) grid = (long long)kNumSMs * ctas_per_sm;
     neural_decode_kernel<kRows, KC, KV><<<(int)grid, kNeuralThreads, smem, st>>>(
-        a.llr, a.cidx, a.Kc, a.cperm, a.vidx, a.Kv, a.vperm, a.w_ch, a.w_res, a.L, a.iters, (long long)a.B, a.E, a.gt,
+        a.llr, a.cidx, a.Kc, a.ccnt, a.cperm, a.vidx, a.Kv, a.vcnt, a.vperm, a.w_ch, a.w_res, a.L, a.iters, (long long)a.B, a.E, a.gt,
         a.soft, a.max_loss);
     LDPC_CHECK_LAUNCH("neural_decode_kernel");
     return LDPC_OK;
@@ -543,16 +544,17 @@ static int launch_neural(const NeuralArgs& a, size_t smem, cudaStream_t st) {
 
 extern "C" {
 
-int ldpc_neural_decode(const float* llr_e, const uint16_t* cidx, int Kc, const uint16_t* cperm, const uint16_t* vidx, int Kv,
-                       const uint16_t* vperm, const float* w_ch, const float* w_res, int L, int iters, int64_t B, int64_t E,
+int ldpc_neural_decode(const float* llr_e, const uint16_t* cidx, int Kc, const uint8_t* ccnt, const uint16_t* cperm,
+                       const uint16_t* vidx, int Kv, const uint8_t* vcnt, const uint16_t* vperm, const float* w_ch, const float* w_res, int L, int iters, int64_t B, int64_t E,
                        const float* gt_e, float* soft, float* max_loss, void* stream) {
-    if (!llr_e || !cidx || !vidx || !w_ch || !soft || (L > 0 && !w_res)) return fail(LDPC_ERR_INVALID, "neural_decode: null argument");
+    if (!llr_e || !cidx || !ccnt || !vidx || !vcnt || !w_ch || !soft || (L > 0 && !w_res))
+        return fail(LDPC_ERR_INVALID, "neural_decode: null argument");
     if (gt_e && !max_loss) return fail(LDPC_ERR_INVALID, "neural_decode: ground truth given without max_loss buffer");
-    if (L < 0 || L > kMaxResidual) return fail(LDPC_ERR_UNSUPPORTED, "neural_decode: depth %d outside 0..%d", L, kMaxResidual);
-    if (iters < 1 || B < 0 || E <= 0 || Kc <= 0 || Kv <= 0) return fail(LDPC_ERR_INVALID, "neural_decode: bad shape");
+    if (L < 0 || L > kNeuralMaxL) return fail(LDPC_ERR_UNSUPPORTED, "neural_decode: depth %d outside 0..%d", L, kNeuralMaxL);
+    if (iters < 1 || B < 0 || E <= 0 || Kc <= 0 || Kv <= 0 || Kc > 255 || Kv > 255) return fail(LDPC_ERR_INVALID, "neural_decode: bad shape");
     if (E >= 0xFFFF) return fail(LDPC_ERR_UNSUPPORTED, "neural_decode: %lld edges do not fit 16-bit indices", (long long)E);
     if (B == 0) return LDPC_OK;
-    const NeuralArgs a{llr_e, cidx, Kc, cperm, vidx, Kv, vperm, w_ch, w_res, L, iters, B, (int)E, gt_e, soft, max_loss};
+    const NeuralArgs a{llr_e, cidx, Kc, ccnt, cperm, vidx, Kv, vcnt, vperm, w_ch, w_res, L, iters, B, (int)E, gt_e, soft, max_loss};
     const size_t per_row = (size_t)((L > 0 ? L : 1) + 2) * E * sizeof(float);   // c2v + llr + ring
     const size_t cap = (size_t)220 * 1024;
     cudaStream_t st = (cudaStream_t)stream;

@@ -12,10 +12,9 @@
 //     the new x overwrites the oldest ring slot in place -- each thread reads and writes only its
 //     own element there).  HBM sees one coalesced read of llr_e and one coalesced write of the soft
 //     outputs per codeword (25 KB each at BG2 Z=32) instead of six [B,E] round trips per iteration.
-//   * the neighbour tables are pre-packed once per code to uint16, k-major ([K][E], 0xFFFF = the
-//     reference's -1 padding): a warp's index load is one coalesced 64 B segment instead of 32
-//     strided 8-byte words, 4x fewer bytes, and L2-resident (390 KB at Z=32), shared by the
-//     kRows codewords of the CTA.
+//   * the neighbour tables are pre-packed once per code to uint16, k-major ([K][E]): a warp's
+//     index load is one coalesced 64 B segment instead of 32 strided 8-byte words, 4x fewer
+//     bytes, and L2-resident (390 KB at Z=32), shared by the kRows codewords of the CTA.
 // Algorithmic traffic per codeword: 4E in + 4E soft out (+ 4E ground truth) = 50 KB at Z=32;
 // the kernel is bound by shared-memory gathers (sum_d d(d-1) = 93 376 per codeword-iteration).
 #pragma once
@@ -27,12 +26,21 @@
 
 namespace ldpc {
 
-constexpr int kNeuralThreads = 1024;
+#ifndef LDPC_NEURAL_THREADS
+#define LDPC_NEURAL_THREADS 1024
+#endif
+constexpr int kNeuralThreads = LDPC_NEURAL_THREADS;
 constexpr unsigned short kNeuralPad = 0xFFFFu;
 #ifndef LDPC_NEURAL_GROUP
 #define LDPC_NEURAL_GROUP 4
 #endif
 constexpr int kNeuralGroup = LDPC_NEURAL_GROUP;
+// 1: load a column's whole index list before the first gather.  Measured slower (2.3-2.6 M cw/s at 768 / 1024
+// threads against 2.95 M with group-wise loads), kept for experiments.
+#ifndef LDPC_NEURAL_PRELOAD
+#define LDPC_NEURAL_PRELOAD 0
+#endif
+constexpr bool kNeuralPreload = LDPC_NEURAL_PRELOAD != 0;
 
 // idx [E,K] int64 (-1 padded) -> out [K,E] uint16 (0xFFFF padded)
 __global__ void neural_pack_index_kernel(const long long* __restrict__ idx, long long E, int K,
@@ -45,56 +53,92 @@ __global__ void neural_pack_index_kernel(const long long* __restrict__ idx, long
     }
 }
 
-// KC / KV: compile-time neighbour-table widths (0 = use the run-time Kc / Kv).  With the widths of
-// the 5G BG2 tables (9 / 22) known, the slot loops unroll completely: a thread has all its index
-// loads in flight before the first shared-memory gather, and the loop stops at the warp's last
-// used slot.  cperm / vperm (optional): thread t works on edge perm[t] and reads column t of the
-// table, which the host has sorted by descending neighbour count (padding compacted to the end of
-// each row) -- warps then see uniform list lengths and skip the padded slots, 59 % of the check
-// table and 55 % of the variable table at BG2.  Results do not depend on the permutation: per edge,
-// the valid neighbours are visited in the caller's order.
+// KC / KV: compile-time neighbour-table widths (0 = use the run-time Kc / Kv): with the widths of
+// the 5G BG2 tables (9 / 22) the slot loops unroll completely.
+//
+// Table format ("sorted pack", built by the host once per code, models/layers.py:_Packed.sorted):
+//   idx  [K][E] uint16  column t lists the neighbours of edge perm[t], valid entries first in the
+//                       caller's order, unused slots = 0 (never dereferenced for their value)
+//   cnt  [E]    uint8   number of valid entries of column t
+//   perm [E]    uint16  edge of column t; columns are ordered by descending cnt so that the 32 edges
+//                       of a warp have (nearly) the same list length.  NULL = identity.
+// A warp loads and visits only slots below the largest cnt of its 32 columns: at BG2, 59 % of the
+// check table and 55 % of the variable table is padding.  Per edge the valid neighbours are visited
+// in the caller's order, so results do not depend on the permutation.
+//
+// Shared-memory arrays are row-interleaved, a[e * kRows + q]: the kRows codewords of the CTA share
+// every gather address, so one LDS.64 / LDS.128 fetches the neighbour's value for all of them.
 
-// sum over the valid slots of column t of src[q][idx]; all 32 lanes of the warp must call it
+constexpr int kNeuralMaxL = 4;       // residual depths kept in registers; deeper queues use the per-layer kernels
+
+template <int R>
+__device__ __forceinline__ void neural_ldv(const float* p, float (&v)[R]) {
+    if constexpr (R == 1) {
+        v[0] = p[0];
+    } else if constexpr (R == 2) {
+        const float2 t = *reinterpret_cast<const float2*>(p);
+        v[0] = t.x; v[1] = t.y;
+    } else {
+        static_assert(R == 4, "kRows is 1, 2 or 4");
+        const float4 t = *reinterpret_cast<const float4*>(p);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+}
+template <int R>
+__device__ __forceinline__ void neural_stv(float* p, const float (&v)[R]) {
+    if constexpr (R == 1) {
+        p[0] = v[0];
+    } else if constexpr (R == 2) {
+        *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+    } else {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+// sum over the valid slots of column t of src[idx][q]; all 32 lanes of the warp must call it
 template <int kRows, int KV>
-__device__ __forceinline__ void neural_gather_sum(const float* __restrict__ src, const unsigned short* __restrict__ idx,
-                                                  int Kv, int E, int t, bool live, float (&acc)[kRows]) {
+__device__ __forceinline__ void neural_gather_sum(const float* __restrict__ src, const unsigned short* __restrict__ col,
+                                                  int Kv_rt, int E, int cnt, float (&acc)[kRows]) {
+    const int K = KV ? KV : Kv_rt;
 #pragma unroll
     for (int q = 0; q < kRows; ++q) acc[q] = 0.0f;
-    if constexpr (KV > 0) {
-        unsigned short nn[KV];
-        int last = 0;
+    const int kmax = __reduce_max_sync(0xffffffffu, cnt);
+    if constexpr (KV > 0 && kNeuralPreload) {
+        // the whole column of indices first (one L2 latency per edge instead of one per group) ...
+        unsigned n[KV];
 #pragma unroll
-        for (int k = 0; k < KV; ++k) {
-            nn[k] = live ? idx[k * E + t] : kNeuralPad;
-            last = nn[k] != kNeuralPad ? k + 1 : last;
-        }
-        const int kmax = __reduce_max_sync(0xffffffffu, last);
-        // groups of kNeuralGroup slots between warp-uniform exits: inside a group the gathers are independent and
-        // predicated, so they are in flight together
+        for (int k = 0; k < KV; ++k) n[k] = (k / kNeuralGroup) * kNeuralGroup < kmax ? col[k * E] : 0u;
+        // ... then groups of kNeuralGroup gathers between warp-uniform exits
 #pragma unroll
         for (int k0 = 0; k0 < KV; k0 += kNeuralGroup) {
             if (k0 >= kmax) break;
             float v[kNeuralGroup][kRows];
 #pragma unroll
-            for (int j = 0; j < kNeuralGroup; ++j) {
-                const bool on = k0 + j < KV && nn[k0 + j < KV ? k0 + j : 0] != kNeuralPad;
-                const int n = on ? nn[k0 + j < KV ? k0 + j : 0] : 0;
+            for (int j = 0; j < kNeuralGroup; ++j)
+                if (k0 + j < KV) neural_ldv<kRows>(src + n[k0 + j < KV ? k0 + j : 0] * kRows, v[j]);
 #pragma unroll
-                for (int q = 0; q < kRows; ++q) v[j][q] = on ? src[q * E + n] : 0.0f;
-            }
+            for (int j = 0; j < kNeuralGroup; ++j)
+                if (k0 + j < KV && k0 + j < cnt) {
 #pragma unroll
-            for (int j = 0; j < kNeuralGroup; ++j) {
-                const bool on = k0 + j < KV && nn[k0 + j < KV ? k0 + j : 0] != kNeuralPad;
-#pragma unroll
-                for (int q = 0; q < kRows; ++q) acc[q] = on ? acc[q] + v[j][q] : acc[q];
-            }
+                    for (int q = 0; q < kRows; ++q) acc[q] += v[j][q];
+                }
         }
     } else {
-        for (int k = 0; k < Kv; ++k) {
-            const unsigned short n = live ? idx[k * E + t] : kNeuralPad;
-            if (n == kNeuralPad) continue;
 #pragma unroll
-            for (int q = 0; q < kRows; ++q) acc[q] += src[q * E + n];
+        for (int k0 = 0; k0 < K; k0 += kNeuralGroup) {
+            if (k0 >= kmax) break;                          // warp-uniform
+            unsigned n[kNeuralGroup];
+            float v[kNeuralGroup][kRows];
+#pragma unroll
+            for (int j = 0; j < kNeuralGroup; ++j) n[j] = k0 + j < K ? col[(k0 + j) * E] : 0u;
+#pragma unroll
+            for (int j = 0; j < kNeuralGroup; ++j) neural_ldv<kRows>(src + n[j] * kRows, v[j]);
+#pragma unroll
+            for (int j = 0; j < kNeuralGroup; ++j)
+                if (k0 + j < cnt) {
+#pragma unroll
+                    for (int q = 0; q < kRows; ++q) acc[q] += v[j][q];
+                }
         }
     }
 }
@@ -114,19 +158,23 @@ __device__ __forceinline__ void neural_check_visit(float v, unsigned& negb, bool
 template <int kRows, int KC, int KV>
 __global__ void __launch_bounds__(kNeuralThreads) neural_decode_kernel(
     const float* __restrict__ llr, const unsigned short* __restrict__ cidx, int Kc_rt,
-    const unsigned short* __restrict__ cperm, const unsigned short* __restrict__ vidx, int Kv_rt,
+    const unsigned char* __restrict__ ccnt, const unsigned short* __restrict__ cperm,
+    const unsigned short* __restrict__ vidx, int Kv_rt, const unsigned char* __restrict__ vcnt,
     const unsigned short* __restrict__ vperm, const float* __restrict__ w_ch, const float* __restrict__ w_res, int L,
     int iters, long long B, int E, const float* __restrict__ gt, float* __restrict__ soft,
     float* __restrict__ max_loss) {
-    extern __shared__ float sm[];
-    const int Kc = KC ? KC : Kc_rt, Kv = KV ? KV : Kv_rt;
+    extern __shared__ __align__(16) float sm[];
+    const int Kc = KC ? KC : Kc_rt;
     const int Lb = L > 0 ? L : 1;
     const int RE = kRows * E;
-    float* c2v = sm;                                  // [kRows][E] check-to-variable messages
-    float* lls = sm + RE;                             // [kRows][E] channel LLRs of the resident codewords
-    float* ring = sm + 2 * RE;                        // [Lb][kRows][E] earlier variable outputs
+    float* c2v = sm;                                  // [E][kRows] check-to-variable messages
+    float* lls = sm + RE;                             // [E][kRows] channel LLRs of the resident codewords
+    float* ring = sm + 2 * RE;                        // [Lb][E][kRows] earlier variable outputs
     __shared__ float red[kRows][kNeuralThreads / 32];
     const int lane = threadIdx.x & 31;
+    float wr[kNeuralMaxL];
+#pragma unroll
+    for (int i = 0; i < kNeuralMaxL; ++i) wr[i] = i < L ? w_res[i] : 0.0f;
 
     for (long long b0 = (long long)blockIdx.x * kRows; b0 < B; b0 += (long long)gridDim.x * kRows) {
         const int nb = (int)((B - b0) < kRows ? (B - b0) : kRows);
@@ -138,8 +186,8 @@ __global__ void __launch_bounds__(kNeuralThreads) neural_decode_kernel(
             const long long row = b0 + (q < nb ? q : nb - 1);
             for (int e = threadIdx.x; e < E; e += kNeuralThreads) {
                 const float v = llr[row * E + e];
-                lls[q * E + e] = v;
-                ring[q * E + e] = v;
+                lls[e * kRows + q] = v;
+                ring[e * kRows + q] = v;
             }
         }
         __syncthreads();
@@ -150,83 +198,91 @@ __global__ void __launch_bounds__(kNeuralThreads) neural_decode_kernel(
             for (int t = threadIdx.x; t - lane < E; t += kNeuralThreads) {
                 const bool live = t < E;
                 const int tt = live ? t : 0;
-                const int e = cperm ? cperm[tt] : tt;
+                const int cnt = live ? (int)ccnt[tt] : 0;
+                const unsigned short* col = cidx + tt;
                 float mn[kRows];
                 unsigned negb[kRows];
                 bool zero[kRows];
 #pragma unroll
                 for (int q = 0; q < kRows; ++q) { mn[q] = CUDART_INF_F; negb[q] = 0u; zero[q] = false; }
-                int used = 0;
-                if constexpr (KC > 0) {
-                    unsigned short nn[KC];
-                    int last = 0;
+                const int kmax = __reduce_max_sync(0xffffffffu, cnt);
+                if constexpr (KC > 0 && kNeuralPreload) {
+                    unsigned n[KC];
 #pragma unroll
-                    for (int k = 0; k < KC; ++k) {
-                        nn[k] = live ? cidx[k * E + tt] : kNeuralPad;
-                        last = nn[k] != kNeuralPad ? k + 1 : last;
-                        used += nn[k] != kNeuralPad;
-                    }
-                    const int kmax = __reduce_max_sync(0xffffffffu, last);
+                    for (int k = 0; k < KC; ++k) n[k] = (k / kNeuralGroup) * kNeuralGroup < kmax ? col[k * E] : 0u;
 #pragma unroll
                     for (int k0 = 0; k0 < KC; k0 += kNeuralGroup) {
                         if (k0 >= kmax) break;           // warp-uniform
                         float v[kNeuralGroup][kRows];
 #pragma unroll
-                        for (int j = 0; j < kNeuralGroup; ++j) {
-                            const bool on = k0 + j < KC && nn[k0 + j < KC ? k0 + j : 0] != kNeuralPad;
-                            const int n = on ? nn[k0 + j < KC ? k0 + j : 0] : 0;
+                        for (int j = 0; j < kNeuralGroup; ++j)
+                            if (k0 + j < KC) neural_ldv<kRows>(x + n[k0 + j < KC ? k0 + j : 0] * kRows, v[j]);
 #pragma unroll
-                            for (int q = 0; q < kRows; ++q) v[j][q] = x[q * E + n];
-                        }
-#pragma unroll
-                        for (int j = 0; j < kNeuralGroup; ++j) {
-                            const bool on = k0 + j < KC && nn[k0 + j < KC ? k0 + j : 0] != kNeuralPad;
-                            if (on) {
+                        for (int j = 0; j < kNeuralGroup; ++j)
+                            if (k0 + j < KC && k0 + j < cnt) {
 #pragma unroll
                                 for (int q = 0; q < kRows; ++q) neural_check_visit(v[j][q], negb[q], zero[q], mn[q]);
                             }
-                        }
                     }
                 } else {
-                    for (int k = 0; k < Kc; ++k) {
-                        const unsigned short n = live ? cidx[k * E + tt] : kNeuralPad;
-                        if (n == kNeuralPad) continue;
-                        ++used;
 #pragma unroll
-                        for (int q = 0; q < kRows; ++q) neural_check_visit(x[q * E + n], negb[q], zero[q], mn[q]);
+                    for (int k0 = 0; k0 < Kc; k0 += kNeuralGroup) {
+                        if (k0 >= kmax) break;           // warp-uniform
+                        unsigned n[kNeuralGroup];
+                        float v[kNeuralGroup][kRows];
+#pragma unroll
+                        for (int j = 0; j < kNeuralGroup; ++j) n[j] = k0 + j < Kc ? col[(k0 + j) * E] : 0u;
+#pragma unroll
+                        for (int j = 0; j < kNeuralGroup; ++j) neural_ldv<kRows>(x + n[j] * kRows, v[j]);
+#pragma unroll
+                        for (int j = 0; j < kNeuralGroup; ++j)
+                            if (k0 + j < cnt) {
+#pragma unroll
+                                for (int q = 0; q < kRows; ++q) neural_check_visit(v[j][q], negb[q], zero[q], mn[q]);
+                            }
                     }
                 }
                 if (live) {
+                    const int e = cperm ? cperm[tt] : tt;
+                    float o[kRows];
 #pragma unroll
                     for (int q = 0; q < kRows; ++q) {
                         // a padded slot is a zero input: sign factor +1, magnitude 1e10 (layers.py:48-57)
-                        const float m = (used < Kc && 1e10f < mn[q]) ? 1e10f : mn[q];
+                        const float m = (cnt < Kc && 1e10f < mn[q]) ? 1e10f : mn[q];
                         const float sp = __uint_as_float((negb[q] & 0x80000000u) | (zero[q] ? 0u : 0x3f800000u));
-                        c2v[q * E + e] = sp * m;
+                        o[q] = sp * m;
                     }
+                    neural_stv<kRows>(c2v + e * kRows, o);
                 }
             }
             __syncthreads();
             if (l == iters - 1) break;
             // ---- VariableLayer(0, c2v) + ResidualLayer (layers.cuh neural_variable_fwd_kernel) ----
             const int nxt = nq == 0 ? 0 : (cur + 1) % Lb;   // empty slot, or the oldest entry once the queue is full
+            int slot_off[kNeuralMaxL];
+#pragma unroll
+            for (int i = 0; i < kNeuralMaxL; ++i) slot_off[i] = ((cur - i + 2 * Lb) % Lb) * RE;
             for (int t = threadIdx.x; t - lane < E; t += kNeuralThreads) {
                 const bool live = t < E;
                 const int tt = live ? t : 0;
-                const int e = vperm ? vperm[tt] : tt;
+                const int cnt = live ? (int)vcnt[tt] : 0;
                 float acc[kRows];
-                neural_gather_sum<kRows, KV>(c2v, vidx, Kv, E, tt, live, acc);
+                neural_gather_sum<kRows, KV>(c2v, vidx + tt, Kv_rt, E, cnt, acc);
                 if (live) {
+                    const int e = vperm ? vperm[tt] : tt;
                     const float w = w_ch[e];
+                    float r[kRows], ll[kRows], pv[kRows];
+                    neural_ldv<kRows>(lls + e * kRows, ll);
 #pragma unroll
-                    for (int q = 0; q < kRows; ++q) {
-                        float r = __fadd_rn(__fmul_rn(lls[q * E + e], w), acc[q]);
-                        for (int i = 0; i < nq; ++i) {
-                            const int slot = (cur - i + Lb) % Lb;
-                            r = __fadd_rn(r, __fmul_rn(__ldg(w_res + i), ring[slot * RE + q * E + e]));
+                    for (int q = 0; q < kRows; ++q) r[q] = __fadd_rn(__fmul_rn(ll[q], w), acc[q]);
+#pragma unroll
+                    for (int i = 0; i < kNeuralMaxL; ++i)
+                        if (i < nq) {
+                            neural_ldv<kRows>(ring + slot_off[i] + e * kRows, pv);
+#pragma unroll
+                            for (int q = 0; q < kRows; ++q) r[q] = __fadd_rn(r[q], __fmul_rn(wr[i], pv[q]));
                         }
-                        ring[nxt * RE + q * E + e] = r;
-                    }
+                    neural_stv<kRows>(ring + nxt * RE + e * kRows, r);
                 }
             }
             cur = nxt;
@@ -239,16 +295,20 @@ __global__ void __launch_bounds__(kNeuralThreads) neural_decode_kernel(
         for (int t = threadIdx.x; t - lane < E; t += kNeuralThreads) {
             const bool live = t < E;
             const int tt = live ? t : 0;
-            const int e = vperm ? vperm[tt] : tt;
+            const int cnt = live ? (int)vcnt[tt] : 0;
             float acc[kRows];
-            neural_gather_sum<kRows, KV>(c2v, vidx, Kv, E, tt, live, acc);
+            neural_gather_sum<kRows, KV>(c2v, vidx + tt, Kv_rt, E, cnt, acc);
             if (live) {
+                const int e = vperm ? vperm[tt] : tt;
+                float own[kRows], ll[kRows], s[kRows];
+                neural_ldv<kRows>(c2v + e * kRows, own);
+                neural_ldv<kRows>(lls + e * kRows, ll);
 #pragma unroll
                 for (int q = 0; q < kRows; ++q) {
-                    const float fin = __fadd_rn(c2v[q * E + e], acc[q]);
-                    const float z = __fadd_rn(fin, lls[q * E + e]);
-                    stage[q * E + e] = 1.0f / (1.0f + expf(-z));
+                    const float z = __fadd_rn(__fadd_rn(own[q], acc[q]), ll[q]);
+                    s[q] = 1.0f / (1.0f + expf(-z));
                 }
+                neural_stv<kRows>(stage + e * kRows, s);
             }
         }
         __syncthreads();
@@ -259,7 +319,7 @@ __global__ void __launch_bounds__(kNeuralThreads) neural_decode_kernel(
             if (q < nb) {
                 for (int e = threadIdx.x; e < E; e += kNeuralThreads) {
                     const long long g = (b0 + q) * E + e;
-                    const float s = stage[q * E + e];
+                    const float s = stage[e * kRows + q];
                     soft[g] = s;
                     if (gt) {
                         const float y = gt[g];
@@ -282,7 +342,7 @@ __global__ void __launch_bounds__(kNeuralThreads) neural_decode_kernel(
             if (threadIdx.x < 32) {
 #pragma unroll
                 for (int q = 0; q < kRows; ++q) {
-                    float v = red[q][threadIdx.x];
+                    float v = threadIdx.x < kNeuralThreads / 32 ? red[q][threadIdx.x] : -CUDART_INF_F;
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
                     if (threadIdx.x == 0 && q < nb) max_loss[b0 + q] = v;

@@ -35,17 +35,28 @@ _PACK_LIMIT = 16
 class _Packed:
     __slots__ = ("src", "table", "symmetric", "_i64", "_sorted")
 
+    def compacted(self):
+        """(table, None, cnt): the lists compacted but the columns left in edge order (identity permutation)."""
+        src = self._i64
+        valid = src >= 0
+        order = torch.argsort((~valid).to(torch.int8), dim=1, stable=True)
+        compact = torch.gather(src, 1, order)
+        return _pack(compact.clamp_min(0).contiguous()), None, valid.sum(dim=1).to(torch.uint8).contiguous()
+
     def sorted(self):
-        """(table [K,E], perm [E]) for the one-kernel decoder: edges ordered by descending neighbour count, the
-        padding of each row compacted to its end (valid neighbours keep the caller's order), column t = edge perm[t]."""
+        """(table [K,E] uint16, perm [E] uint16, cnt [E] uint8) for the one-kernel decoder: columns ordered by
+        descending neighbour count, each list compacted (valid neighbours first, in the caller's order; unused
+        slots 0), column t = edge perm[t]."""
         if self._sorted is None:
             src = self._i64
             E, K = src.shape
             valid = src >= 0
             order = torch.argsort((~valid).to(torch.int8), dim=1, stable=True)
             compact = torch.gather(src, 1, order)
-            perm = torch.argsort(valid.sum(dim=1), descending=True, stable=True)
-            self._sorted = (_pack(compact[perm].contiguous()), perm.to(torch.int32).to(torch.int16).contiguous())
+            cnt = valid.sum(dim=1)
+            perm = torch.argsort(cnt, descending=True, stable=True)
+            self._sorted = (_pack(compact[perm].clamp_min(0).contiguous()),
+                            perm.to(torch.int32).to(torch.int16).contiguous(), cnt[perm].to(torch.uint8).contiguous())
         return self._sorted
 
 

@@ -34,7 +34,11 @@ def main():
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--lib", default=None, help="alternative libldpc_b200.so (tools/build_variant.sh)")
     args = ap.parse_args()
+    if args.lib:
+        from ldpc_b200 import _native
+        _native.LIB_PATH = os.path.abspath(args.lib)
     dev = "cuda:0"
     code = QCCode.nr_2_0(32)
     _, cidx, vidx, oidx = create_LLR_mapping(code.dense().T)
@@ -43,7 +47,7 @@ def main():
     llr = (torch.randn(args.batch, code.N, device=dev, generator=g) * 0.5 + 0.4)
     llr_e = llr[:, oidx[0].to(dev)].contiguous()
     gt = torch.ones_like(llr_e)
-    out = {"batch": args.batch, "iters": args.iters, "E": code.E}
+    out = {"batch": args.batch, "iters": args.iters, "E": code.E, "lib": args.lib}
     for fused in (True, False):
         dec = LDPCNeuralDecoder(code.E, args.iters, 2, fused=fused).to(dev)
 
