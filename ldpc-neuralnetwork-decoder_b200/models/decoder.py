@@ -13,7 +13,7 @@ the repository; what exists is
     (trainer.py:245, comparative_evaluation.py:206).
 This class is the composition those three sources imply, written ONLY in terms of the
 reference's layer semantics so that it can be pinned against the reference's own layer
-classes (tests/golden/neural_decoder_z4.npz, generated by oracle/make_golden.py):
+classes (fixture tests/golden/neural_decoder_z4.npz):
 
     x_0 = llr_e                                   (edge copy of the channel LLRs)
     for l in 0 .. I-1:
