@@ -182,6 +182,21 @@ int ldpc_residual_layer_fwd(const float* llr, const float* c2v, const float* w_c
 int ldpc_neural_variable_layer_fwd(const float* llr, const float* c2v, const int64_t* idx, const float* w_ch,
                                    const float* w_res, const float* const* prev, int L, int64_t B, int64_t E, int K,
                                    float* out, void* stream);
+/* The gather-type layers on "sorted-pack" tables (same arithmetic and results as the int64
+ * entry points above; layers.py:14-66, :78-125, notebook cell 11): idx16 = [K,E] uint16 from
+ * ldpc_neural_pack_index on the table with every row compacted (valid entries first, caller's
+ * order); cnt [E] uint8 = valid entries per column; perm [E] uint16 (or NULL) = edge of column
+ * t, columns ordered by descending cnt so that a warp skips the padding.
+ * check: nstar (optional) [B,E] int32 = edge selected as the minimum, -1 if none; its backward
+ * needs only (x, out, nstar).  variable: w_ch == NULL -> out = llr + sum (VariableLayer);
+ * else out = w_ch*llr + sum + sum_{i<L} w_res[i]*prev[i] (variable + residual update).      */
+int ldpc_check_layer_fwd_sorted(const float* x, const uint16_t* idx16, int K, const uint8_t* cnt, const uint16_t* perm,
+                                int64_t B, int64_t E, float* out, int32_t* nstar, void* stream);
+int ldpc_variable_layer_fwd_sorted(const float* llr, const float* c2v, const uint16_t* idx16, int K, const uint8_t* cnt,
+                                   const uint16_t* perm, const float* w_ch, const float* w_res, const float* const* prev,
+                                   int L, int64_t B, int64_t E, float* out, void* stream);
+int ldpc_check_layer_bwd_nstar(const float* x, const float* out, const int32_t* nstar, const float* grad_out, int64_t B,
+                               int64_t E, float* grad_x, void* stream);
 /* Whole LDPCNeuralDecoder forward (inference / validation) in one kernel: `iters` unrolled
  * iterations of CheckLayer (layers.py:14-66) -> VariableLayer (:78-125) -> ResidualLayer
  * (:143-168), the last check messages summed per variable into OutputLayer (:180-210); the
@@ -198,16 +213,6 @@ int ldpc_neural_decode(const float* llr_e, const uint16_t* cidx, int Kc, const u
                        const uint16_t* vidx, int Kv, const uint8_t* vcnt, const uint16_t* vperm, const float* w_ch,
                        const float* w_res, int L, int iters, int64_t B, int64_t E, const float* gt_e, float* soft,
                        float* max_loss, void* stream);
-/* The three gather-type forwards with the neighbour table packed by ldpc_neural_pack_index
- * ([K,E] uint16, 0xFFFF = -1): same arithmetic and results as the int64 entry points above
- * (layers.py:14-66, :78-125, notebook cell 11), coalesced index loads.                    */
-int ldpc_check_layer_fwd_packed(const float* x, const uint16_t* idx16, int64_t B, int64_t E, int K, float* out,
-                                int32_t* argmin_out, void* stream);
-int ldpc_variable_layer_fwd_packed(const float* llr, const float* c2v, const uint16_t* idx16, int64_t B, int64_t E, int K,
-                                   float* out, void* stream);
-int ldpc_neural_variable_layer_fwd_packed(const float* llr, const float* c2v, const uint16_t* idx16, const float* w_ch,
-                                          const float* w_res, const float* const* prev, int L, int64_t B, int64_t E,
-                                          int K, float* out, void* stream);
 /* OutputLayer.forward, layers.py:180-210: soft = sigmoid(final+llr); if gt: per-row max of
  * BCE(soft, gt) -> max_loss [B], argmax [B] int32 (for the backward).                    */
 int ldpc_output_layer_fwd(const float* final_llr, const float* llr, const float* gt, int64_t B, int64_t E,

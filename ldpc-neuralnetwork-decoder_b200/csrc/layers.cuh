@@ -26,20 +26,14 @@ inline int layer_rows_per_cta(long long E) {
     return r < 1 ? 0 : (r > 8 ? 8 : (int)r);
 }
 
-// Neighbour-table accessors.  IdxI64 reads the reference layout directly ([E,K] int64, -1 padded): a warp's load
-// of slot k touches 32 rows K*8 bytes apart = 32 L1 wavefronts, which is what bounds the layer kernels (ncu launch
-// list r1: variable layer 606 us per 4096 x 6304 pass).  IdxU16 reads the table packed once per code by
-// ldpc_neural_pack_index ([K,E] uint16, 0xFFFF padded): one 64-byte wavefront per warp and slot.
+// Neighbour-table accessor of these kernels: the reference layout ([E,K] int64, -1 padded).  A warp's load of slot k
+// touches 32 rows K*8 bytes apart = 32 L1 wavefronts, which is what bounds them (ncu launch list r1: variable layer
+// 606 us per 4096 x 6304 pass).  The fast path is csrc/neural.cuh: tables packed once per code to k-major uint16
+// columns sorted by list length (ldpc_*_layer_fwd_sorted); these kernels remain for tables that cannot be packed
+// (E >= 65535) and as the plain int64 ABI.
 struct IdxI64 {
     const long long* p;
     __device__ __forceinline__ long long operator()(long long e, int k, long long, int K) const { return p[e * K + k]; }
-};
-struct IdxU16 {
-    const unsigned short* p;
-    __device__ __forceinline__ long long operator()(long long e, int k, long long E, int) const {
-        const unsigned short n = p[(long long)k * E + e];
-        return n == 0xFFFFu ? -1ll : (long long)n;
-    }
 };
 
 template <int kRows, bool kStage, class Idx = IdxI64>

@@ -462,46 +462,57 @@ int ldpc_neural_variable_layer_fwd(const float* llr, const float* c2v, const int
     return LDPC_OK;
 }
 
-// Packed-table variants: idx16 = [K,E] uint16 from ldpc_neural_pack_index (coalesced index loads).
-int ldpc_check_layer_fwd_packed(const float* x, const uint16_t* idx16, int64_t B, int64_t E, int K, float* out,
-                                int32_t* argmin_out, void* stream) {
-    if (!x || !idx16 || !out) return fail(LDPC_ERR_INVALID, "check_layer_fwd_packed: null argument");
-    if (B < 0 || E <= 0 || K <= 0 || E >= 0xFFFF) return fail(LDPC_ERR_INVALID, "check_layer_fwd_packed: bad shape");
+// Sorted-pack variants (csrc/neural.cuh): idx16 [K,E] uint16 compacted columns, cnt [E] uint8, perm [E] uint16 or NULL.
+static int sorted_grid(int64_t B) {
+    long long g = (B + kPackedRows - 1) / kPackedRows;
+    return (int)(g > 2ll * kNumSMs ? 2ll * kNumSMs : g);
+}
+
+int ldpc_check_layer_fwd_sorted(const float* x, const uint16_t* idx16, int K, const uint8_t* cnt, const uint16_t* perm,
+                                int64_t B, int64_t E, float* out, int32_t* nstar, void* stream) {
+    if (!x || !idx16 || !cnt || !out) return fail(LDPC_ERR_INVALID, "check_layer_fwd_sorted: null argument");
+    if (B < 0 || E <= 0 || K <= 0 || K > 255 || E >= 0xFFFF) return fail(LDPC_ERR_INVALID, "check_layer_fwd_sorted: bad shape");
+    const size_t smem = (size_t)kPackedRows * E * sizeof(float);
+    if (smem > (size_t)110 * 1024) return fail(LDPC_ERR_UNSUPPORTED, "check_layer_fwd_sorted: %lld edges exceed the staging tile", (long long)E);
     if (B == 0) return LDPC_OK;
-    cudaStream_t st = (cudaStream_t)stream;
-    LDPC_LAYER_DISPATCH(check_layer_fwd_kernel, IdxU16, x, IdxU16{idx16}, (long long)B, (long long)E, K, out, argmin_out);
-    LDPC_CHECK_LAUNCH("check_layer_fwd_kernel(packed)");
+    LDPC_CUDA(cudaFuncSetAttribute(sorted_check_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sorted_check_fwd_kernel<<<sorted_grid(B), kPackedThreads, smem, (cudaStream_t)stream>>>(x, idx16, K, cnt, perm, (long long)B,
+                                                                                           (int)E, out, nstar);
+    LDPC_CHECK_LAUNCH("sorted_check_fwd_kernel");
     return LDPC_OK;
 }
 
-int ldpc_variable_layer_fwd_packed(const float* llr, const float* c2v, const uint16_t* idx16, int64_t B, int64_t E, int K,
-                                   float* out, void* stream) {
-    if (!llr || !c2v || !idx16 || !out) return fail(LDPC_ERR_INVALID, "variable_layer_fwd_packed: null argument");
-    if (B < 0 || E <= 0 || K <= 0 || E >= 0xFFFF) return fail(LDPC_ERR_INVALID, "variable_layer_fwd_packed: bad shape");
-    if (B == 0) return LDPC_OK;
-    cudaStream_t st = (cudaStream_t)stream;
-    LDPC_LAYER_DISPATCH(variable_layer_fwd_kernel, IdxU16, llr, c2v, IdxU16{idx16}, (long long)B, (long long)E, K, out);
-    LDPC_CHECK_LAUNCH("variable_layer_fwd_kernel(packed)");
-    return LDPC_OK;
-}
-
-int ldpc_neural_variable_layer_fwd_packed(const float* llr, const float* c2v, const uint16_t* idx16, const float* w_ch,
-                                          const float* w_res, const float* const* prev, int L, int64_t B, int64_t E,
-                                          int K, float* out, void* stream) {
-    if (!llr || !c2v || !idx16 || !w_ch || !out || (L > 0 && (!prev || !w_res)))
-        return fail(LDPC_ERR_INVALID, "neural_variable_layer_fwd_packed: null argument");
-    if (L < 0 || L > kMaxResidual) return fail(LDPC_ERR_UNSUPPORTED, "neural_variable_layer_fwd_packed: depth %d outside 0..%d", L, kMaxResidual);
-    if (B < 0 || E <= 0 || K <= 0 || E >= 0xFFFF) return fail(LDPC_ERR_INVALID, "neural_variable_layer_fwd_packed: bad shape");
+int ldpc_variable_layer_fwd_sorted(const float* llr, const float* c2v, const uint16_t* idx16, int K, const uint8_t* cnt,
+                                   const uint16_t* perm, const float* w_ch, const float* w_res, const float* const* prev,
+                                   int L, int64_t B, int64_t E, float* out, void* stream) {
+    if (!llr || !c2v || !idx16 || !cnt || !out) return fail(LDPC_ERR_INVALID, "variable_layer_fwd_sorted: null argument");
+    if (L < 0 || L > kMaxResidual) return fail(LDPC_ERR_UNSUPPORTED, "variable_layer_fwd_sorted: depth %d outside 0..%d", L, kMaxResidual);
+    if (L > 0 && (!w_ch || !w_res || !prev)) return fail(LDPC_ERR_INVALID, "variable_layer_fwd_sorted: residual terms need w_ch, w_res and prev");
+    if (B < 0 || E <= 0 || K <= 0 || K > 255 || E >= 0xFFFF) return fail(LDPC_ERR_INVALID, "variable_layer_fwd_sorted: bad shape");
+    const size_t smem = (size_t)kPackedRows * E * sizeof(float);
+    if (smem > (size_t)110 * 1024) return fail(LDPC_ERR_UNSUPPORTED, "variable_layer_fwd_sorted: %lld edges exceed the staging tile", (long long)E);
     if (B == 0) return LDPC_OK;
     ResidualPtrs rp{};
     for (int i = 0; i < L; ++i) {
-        if (!prev[i]) return fail(LDPC_ERR_INVALID, "neural_variable_layer_fwd_packed: prev[%d] is null", i);
+        if (!prev[i]) return fail(LDPC_ERR_INVALID, "variable_layer_fwd_sorted: prev[%d] is null", i);
         rp.prev[i] = prev[i];
     }
+    LDPC_CUDA(cudaFuncSetAttribute(sorted_variable_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sorted_variable_fwd_kernel<<<sorted_grid(B), kPackedThreads, smem, (cudaStream_t)stream>>>(
+        llr, c2v, idx16, K, cnt, perm, w_ch, w_res, rp, L, (long long)B, (int)E, out);
+    LDPC_CHECK_LAUNCH("sorted_variable_fwd_kernel");
+    return LDPC_OK;
+}
+
+int ldpc_check_layer_bwd_nstar(const float* x, const float* out, const int32_t* nstar, const float* grad_out, int64_t B,
+                               int64_t E, float* grad_x, void* stream) {
+    if (!x || !out || !nstar || !grad_out || !grad_x) return fail(LDPC_ERR_INVALID, "check_layer_bwd_nstar: null argument");
+    if (B < 0 || E <= 0) return fail(LDPC_ERR_INVALID, "check_layer_bwd_nstar: bad shape");
+    if (B == 0) return LDPC_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    LDPC_LAYER_DISPATCH(neural_variable_fwd_kernel, IdxU16, llr, c2v, IdxU16{idx16}, w_ch, w_res, rp, L, (long long)B,
-                        (long long)E, K, out);
-    LDPC_CHECK_LAUNCH("neural_variable_fwd_kernel(packed)");
+    LDPC_CUDA(cudaMemsetAsync(grad_x, 0, sizeof(float) * (size_t)B * E, st));
+    check_layer_bwd_nstar_kernel<<<layer_grid(B * E, 256), 256, 0, st>>>(x, out, nstar, grad_out, (long long)B, (long long)E, grad_x);
+    LDPC_CHECK_LAUNCH("check_layer_bwd_nstar_kernel");
     return LDPC_OK;
 }
 

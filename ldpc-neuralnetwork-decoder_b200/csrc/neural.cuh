@@ -352,4 +352,140 @@ __global__ void __launch_bounds__(kNeuralThreads) neural_decode_kernel(
     }
 }
 
+// ---- the same machinery for ONE layer at a time (training path, and the stand-alone CheckLayer / VariableLayer) ----
+// kRows = 4 codewords per CTA, row-interleaved in shared memory (one LDS.128 per neighbour), sorted-pack tables.
+// Results go straight to global memory at edge perm[t]: 4-byte scattered stores, merged by the L2.
+constexpr int kPackedThreads = 512;
+constexpr int kPackedRows = 4;
+
+// CheckLayer.forward (layers.py:14-66).  nstar (optional) [B,E] int32: the edge whose |x| was selected as the
+// minimum, -1 if the minimum is the 1e10 stand-in of a zero / padded input (no gradient, layers.py:55-58).
+__global__ void __launch_bounds__(kPackedThreads, 2) sorted_check_fwd_kernel(
+    const float* __restrict__ x, const unsigned short* __restrict__ idx, int K, const unsigned char* __restrict__ cnts,
+    const unsigned short* __restrict__ perm, long long B, int E, float* __restrict__ out, int* __restrict__ nstar) {
+    constexpr int R = kPackedRows;
+    extern __shared__ __align__(16) float sm[];           // [E][R]
+    const int lane = threadIdx.x & 31;
+    for (long long b0 = (long long)blockIdx.x * R; b0 < B; b0 += (long long)gridDim.x * R) {
+        const int nb = (int)((B - b0) < R ? (B - b0) : R);
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+            const long long row = b0 + (q < nb ? q : nb - 1);
+            for (int e = threadIdx.x; e < E; e += kPackedThreads) sm[e * R + q] = x[row * E + e];
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t - lane < E; t += kPackedThreads) {
+            const bool live = t < E;
+            const int tt = live ? t : 0;
+            const int cnt = live ? (int)cnts[tt] : 0;
+            const unsigned short* col = idx + tt;
+            float mn[R];
+            unsigned negb[R];
+            bool zero[R];
+            int ns[R];
+#pragma unroll
+            for (int q = 0; q < R; ++q) { mn[q] = CUDART_INF_F; negb[q] = 0u; zero[q] = false; ns[q] = -1; }
+            const int kmax = __reduce_max_sync(0xffffffffu, cnt);
+            for (int k0 = 0; k0 < K; k0 += kNeuralGroup) {
+                if (k0 >= kmax) break;                   // warp-uniform
+                unsigned n[kNeuralGroup];
+                float v[kNeuralGroup][R];
+#pragma unroll
+                for (int j = 0; j < kNeuralGroup; ++j) n[j] = k0 + j < K ? col[(k0 + j) * E] : 0u;
+#pragma unroll
+                for (int j = 0; j < kNeuralGroup; ++j) neural_ldv<R>(sm + n[j] * R, v[j]);
+#pragma unroll
+                for (int j = 0; j < kNeuralGroup; ++j)
+                    if (k0 + j < cnt) {
+#pragma unroll
+                        for (int q = 0; q < R; ++q) {
+                            const float before = mn[q];
+                            neural_check_visit(v[j][q], negb[q], zero[q], mn[q]);
+                            if (mn[q] < before) ns[q] = v[j][q] != 0.0f ? (int)n[j] : -1;
+                        }
+                    }
+            }
+            if (live) {
+                const int e = perm ? perm[tt] : tt;
+#pragma unroll
+                for (int q = 0; q < R; ++q)
+                    if (q < nb) {
+                        const bool pad_wins = cnt < K && 1e10f < mn[q];
+                        const float m = pad_wins ? 1e10f : mn[q];
+                        const float sp = __uint_as_float((negb[q] & 0x80000000u) | (zero[q] ? 0u : 0x3f800000u));
+                        out[(b0 + q) * E + e] = sp * m;
+                        if (nstar) nstar[(b0 + q) * E + e] = pad_wins ? -1 : ns[q];
+                    }
+            }
+        }
+    }
+}
+
+// VariableLayer.forward (layers.py:78-125): out = llr + sum (w_ch == nullptr), or the variable + residual update
+// of LDPCNeuralDecoder: out = (w_ch*llr + sum) + sum_i w_res[i]*prev[i]  (same operation order as the two layers).
+__global__ void __launch_bounds__(kPackedThreads, 2) sorted_variable_fwd_kernel(
+    const float* __restrict__ llr, const float* __restrict__ c2v, const unsigned short* __restrict__ idx, int K,
+    const unsigned char* __restrict__ cnts, const unsigned short* __restrict__ perm, const float* __restrict__ w_ch,
+    const float* __restrict__ w_res, ResidualPtrs prev, int L, long long B, int E, float* __restrict__ out) {
+    constexpr int R = kPackedRows;
+    extern __shared__ __align__(16) float sm[];           // [E][R]
+    const int lane = threadIdx.x & 31;
+    for (long long b0 = (long long)blockIdx.x * R; b0 < B; b0 += (long long)gridDim.x * R) {
+        const int nb = (int)((B - b0) < R ? (B - b0) : R);
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+            const long long row = b0 + (q < nb ? q : nb - 1);
+            for (int e = threadIdx.x; e < E; e += kPackedThreads) sm[e * R + q] = c2v[row * E + e];
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t - lane < E; t += kPackedThreads) {
+            const bool live = t < E;
+            const int tt = live ? t : 0;
+            const int cnt = live ? (int)cnts[tt] : 0;
+            float acc[R];
+            neural_gather_sum<R, 0>(sm, idx + tt, K, E, cnt, acc);
+            if (live) {
+                const int e = perm ? perm[tt] : tt;
+                const float w = w_ch ? w_ch[e] : 1.0f;
+#pragma unroll
+                for (int q = 0; q < R; ++q)
+                    if (q < nb) {
+                        const long long g = (b0 + q) * E + e;
+                        float r;
+                        if (w_ch) {
+                            r = __fadd_rn(__fmul_rn(llr[g], w), acc[q]);
+#pragma unroll
+                            for (int i = 0; i < kMaxResidual; ++i)
+                                if (i < L) r = __fadd_rn(r, __fmul_rn(__ldg(w_res + i), prev.prev[i][g]));
+                        } else {
+                            r = __fadd_rn(llr[g], acc[q]);
+                        }
+                        out[g] = r;
+                    }
+            }
+        }
+    }
+}
+
+// Backward of CheckLayer from (out, nstar): d out[e] / d x[nstar] = sign_product * sign(x[nstar]) and
+// sign_product = sign(out[e]) (|out| = the selected |x| > 0, or out = +-0 when a sign factor was 0).
+__global__ void __launch_bounds__(256) check_layer_bwd_nstar_kernel(const float* __restrict__ x,
+                                                                    const float* __restrict__ out,
+                                                                    const int* __restrict__ nstar,
+                                                                    const float* __restrict__ grad_out, long long B,
+                                                                    long long E, float* __restrict__ grad_x) {
+    const long long total = B * E;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int n = nstar[t];
+        if (n < 0) continue;
+        const long long b = t / E;
+        const float o = out[t], v = x[b * E + n];
+        const float sp = o > 0.0f ? 1.0f : (o < 0.0f ? -1.0f : 0.0f);
+        const float sv = v > 0.0f ? 1.0f : (v < 0.0f ? -1.0f : 0.0f);
+        atomicAdd(&grad_x[b * E + n], grad_out[t] * sp * sv);
+    }
+}
+
 }  // namespace ldpc

@@ -69,11 +69,12 @@ class _NeuralVariableFn(torch.autograd.Function):
         arr = (C.c_void_p * max(len(prev_c), 1))(*[p.data_ptr() for p in prev_c])
         pk = packed_index(idx)
         with torch.cuda.device(llr_c.device):
-            if pk is not None:
-                _native.check(_native.lib().ldpc_neural_variable_layer_fwd_packed(
-                    _native.ptr(llr_c), _native.ptr(c2v_c), _native.ptr(pk.table), _native.ptr(wch_c),
-                    _native.ptr(wres_c), arr, len(prev_c), B, E, idx.shape[1], _native.ptr(out),
-                    _native.stream_ptr(llr_c.device)))
+            if pk is not None and E * 16 <= 110 * 1024:
+                table, perm, cnt = pk.sorted()
+                _native.check(_native.lib().ldpc_variable_layer_fwd_sorted(
+                    _native.ptr(llr_c), _native.ptr(c2v_c), _native.ptr(table), table.shape[0], _native.ptr(cnt),
+                    _native.ptr(perm), _native.ptr(wch_c), _native.ptr(wres_c), arr, len(prev_c), B, E,
+                    _native.ptr(out), _native.stream_ptr(llr_c.device)))
             else:
                 idx = idx.to(torch.int64).contiguous()
                 _native.check(_native.lib().ldpc_neural_variable_layer_fwd(

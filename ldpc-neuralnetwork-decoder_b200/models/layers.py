@@ -99,10 +99,11 @@ def _gather_sum(llr, c2v, idx):
     out = torch.empty_like(c2v)
     pk = packed_index(idx)
     with torch.cuda.device(c2v.device):
-        if pk is not None:
-            _native.check(_native.lib().ldpc_variable_layer_fwd_packed(
-                _native.ptr(llr), _native.ptr(c2v), _native.ptr(pk.table), B, E, idx.shape[1], _native.ptr(out),
-                _native.stream_ptr(c2v.device)))
+        if pk is not None and E * 16 <= 110 * 1024:
+            table, perm, cnt = pk.sorted()
+            _native.check(_native.lib().ldpc_variable_layer_fwd_sorted(
+                _native.ptr(llr), _native.ptr(c2v), _native.ptr(table), table.shape[0], _native.ptr(cnt),
+                _native.ptr(perm), None, None, None, 0, B, E, _native.ptr(out), _native.stream_ptr(c2v.device)))
         else:
             idx = idx.to(torch.int64).contiguous()
             _native.check(_native.lib().ldpc_variable_layer_fwd(
@@ -137,23 +138,36 @@ class _CheckFn(torch.autograd.Function):
         out = torch.empty_like(x)
         am = torch.empty((B, E), dtype=torch.int32, device=x.device)
         pk = packed_index(idx)
-        idx = idx.to(torch.int64).contiguous()
+        ctx.sorted = pk is not None and E * 16 <= 110 * 1024
         with torch.cuda.device(x.device):
-            if pk is not None:
-                _native.check(_native.lib().ldpc_check_layer_fwd_packed(
-                    _native.ptr(x), _native.ptr(pk.table), B, E, K, _native.ptr(out), _native.ptr(am),
-                    _native.stream_ptr(x.device)))
+            if ctx.sorted:
+                # am = edge selected as the minimum (-1: none); backward needs only (x, out, am)
+                table, perm, cnt = pk.sorted()
+                _native.check(_native.lib().ldpc_check_layer_fwd_sorted(
+                    _native.ptr(x), _native.ptr(table), K, _native.ptr(cnt), _native.ptr(perm), B, E, _native.ptr(out),
+                    _native.ptr(am), _native.stream_ptr(x.device)))
+                ctx.save_for_backward(x, out, am)
             else:
+                idx = idx.to(torch.int64).contiguous()
                 _native.check(_native.lib().ldpc_check_layer_fwd(
                     _native.ptr(x), _native.ptr(idx), B, E, K, _native.ptr(out), _native.ptr(am),
                     _native.stream_ptr(x.device)))
-        ctx.save_for_backward(x, idx, am)
+                ctx.save_for_backward(x, idx, am)
         return out
 
     @staticmethod
     def backward(ctx, g):
-        x, idx, am = ctx.saved_tensors
         g = g.to(torch.float32).contiguous()
+        if ctx.sorted:
+            x, out, am = ctx.saved_tensors
+            B, E = x.shape
+            gx = torch.empty_like(x)
+            with torch.cuda.device(x.device):
+                _native.check(_native.lib().ldpc_check_layer_bwd_nstar(
+                    _native.ptr(x), _native.ptr(out), _native.ptr(am), _native.ptr(g), B, E, _native.ptr(gx),
+                    _native.stream_ptr(x.device)))
+            return gx, None
+        x, idx, am = ctx.saved_tensors
         B, E = x.shape
         gx = torch.empty_like(x)
         with torch.cuda.device(x.device):
