@@ -475,9 +475,15 @@ int ldpc_check_layer_fwd_sorted(const float* x, const uint16_t* idx16, int K, co
     const size_t smem = (size_t)kPackedRows * E * sizeof(float);
     if (smem > (size_t)110 * 1024) return fail(LDPC_ERR_UNSUPPORTED, "check_layer_fwd_sorted: %lld edges exceed the staging tile", (long long)E);
     if (B == 0) return LDPC_OK;
-    LDPC_CUDA(cudaFuncSetAttribute(sorted_check_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sorted_check_fwd_kernel<<<sorted_grid(B), kPackedThreads, smem, (cudaStream_t)stream>>>(x, idx16, K, cnt, perm, (long long)B,
-                                                                                           (int)E, out, nstar);
+    if (K == 9) {         // create_LLR_mapping on the 5G BG2 graphs
+        LDPC_CUDA(cudaFuncSetAttribute(sorted_check_fwd_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sorted_check_fwd_kernel<9><<<sorted_grid(B), kPackedThreads, smem, (cudaStream_t)stream>>>(
+            x, idx16, K, cnt, perm, (long long)B, (int)E, out, nstar);
+    } else {
+        LDPC_CUDA(cudaFuncSetAttribute(sorted_check_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sorted_check_fwd_kernel<0><<<sorted_grid(B), kPackedThreads, smem, (cudaStream_t)stream>>>(
+            x, idx16, K, cnt, perm, (long long)B, (int)E, out, nstar);
+    }
     LDPC_CHECK_LAUNCH("sorted_check_fwd_kernel");
     return LDPC_OK;
 }
@@ -497,9 +503,15 @@ int ldpc_variable_layer_fwd_sorted(const float* llr, const float* c2v, const uin
         if (!prev[i]) return fail(LDPC_ERR_INVALID, "variable_layer_fwd_sorted: prev[%d] is null", i);
         rp.prev[i] = prev[i];
     }
-    LDPC_CUDA(cudaFuncSetAttribute(sorted_variable_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sorted_variable_fwd_kernel<<<sorted_grid(B), kPackedThreads, smem, (cudaStream_t)stream>>>(
-        llr, c2v, idx16, K, cnt, perm, w_ch, w_res, rp, L, (long long)B, (int)E, out);
+    if (K == 22) {
+        LDPC_CUDA(cudaFuncSetAttribute(sorted_variable_fwd_kernel<22>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sorted_variable_fwd_kernel<22><<<sorted_grid(B), kPackedThreads, smem, (cudaStream_t)stream>>>(
+            llr, c2v, idx16, K, cnt, perm, w_ch, w_res, rp, L, (long long)B, (int)E, out);
+    } else {
+        LDPC_CUDA(cudaFuncSetAttribute(sorted_variable_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sorted_variable_fwd_kernel<0><<<sorted_grid(B), kPackedThreads, smem, (cudaStream_t)stream>>>(
+            llr, c2v, idx16, K, cnt, perm, w_ch, w_res, rp, L, (long long)B, (int)E, out);
+    }
     LDPC_CHECK_LAUNCH("sorted_variable_fwd_kernel");
     return LDPC_OK;
 }

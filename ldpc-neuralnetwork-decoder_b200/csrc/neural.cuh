@@ -360,10 +360,12 @@ constexpr int kPackedRows = 4;
 
 // CheckLayer.forward (layers.py:14-66).  nstar (optional) [B,E] int32: the edge whose |x| was selected as the
 // minimum, -1 if the minimum is the 1e10 stand-in of a zero / padded input (no gradient, layers.py:55-58).
+template <int KT>      // compile-time table width (9 for the BG2 check table), 0 = run-time K
 __global__ void __launch_bounds__(kPackedThreads, 2) sorted_check_fwd_kernel(
-    const float* __restrict__ x, const unsigned short* __restrict__ idx, int K, const unsigned char* __restrict__ cnts,
+    const float* __restrict__ x, const unsigned short* __restrict__ idx, int K_rt, const unsigned char* __restrict__ cnts,
     const unsigned short* __restrict__ perm, long long B, int E, float* __restrict__ out, int* __restrict__ nstar) {
     constexpr int R = kPackedRows;
+    const int K = KT ? KT : K_rt;
     extern __shared__ __align__(16) float sm[];           // [E][R]
     const int lane = threadIdx.x & 31;
     for (long long b0 = (long long)blockIdx.x * R; b0 < B; b0 += (long long)gridDim.x * R) {
@@ -387,6 +389,7 @@ __global__ void __launch_bounds__(kPackedThreads, 2) sorted_check_fwd_kernel(
 #pragma unroll
             for (int q = 0; q < R; ++q) { mn[q] = CUDART_INF_F; negb[q] = 0u; zero[q] = false; ns[q] = -1; }
             const int kmax = __reduce_max_sync(0xffffffffu, cnt);
+#pragma unroll
             for (int k0 = 0; k0 < K; k0 += kNeuralGroup) {
                 if (k0 >= kmax) break;                   // warp-uniform
                 unsigned n[kNeuralGroup];
@@ -424,6 +427,7 @@ __global__ void __launch_bounds__(kPackedThreads, 2) sorted_check_fwd_kernel(
 
 // VariableLayer.forward (layers.py:78-125): out = llr + sum (w_ch == nullptr), or the variable + residual update
 // of LDPCNeuralDecoder: out = (w_ch*llr + sum) + sum_i w_res[i]*prev[i]  (same operation order as the two layers).
+template <int KT>      // 22 for the BG2 variable table, 0 = run-time K
 __global__ void __launch_bounds__(kPackedThreads, 2) sorted_variable_fwd_kernel(
     const float* __restrict__ llr, const float* __restrict__ c2v, const unsigned short* __restrict__ idx, int K,
     const unsigned char* __restrict__ cnts, const unsigned short* __restrict__ perm, const float* __restrict__ w_ch,
@@ -445,7 +449,7 @@ __global__ void __launch_bounds__(kPackedThreads, 2) sorted_variable_fwd_kernel(
             const int tt = live ? t : 0;
             const int cnt = live ? (int)cnts[tt] : 0;
             float acc[R];
-            neural_gather_sum<R, 0>(sm, idx + tt, K, E, cnt, acc);
+            neural_gather_sum<R, KT>(sm, idx + tt, K, E, cnt, acc);
             if (live) {
                 const int e = perm ? perm[tt] : tt;
                 const float w = w_ch ? w_ch[e] : 1.0f;
