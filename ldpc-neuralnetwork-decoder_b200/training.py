@@ -1,4 +1,5 @@
-"""One data-parallel training step of the message-GNN decoder (BASELINE.json config 5).
+"""One data-parallel training step of the message-GNN decoder (BASELINE.json config 5) and of the unrolled
+neural min-sum decoder (`LDPCNeuralDecoder`).
 
 The reference trains with SGD(momentum 0.9, weight decay 1e-4) on all-zero codewords
 (training/trainer.py:70,231; the harness itself is unimportable).
@@ -41,3 +42,17 @@ def train_step(decoder, llr, ground_truth, optimizer, group=None):
     allreduce_gradients(decoder, group)
     optimizer.step()
     return loss.detach()
+
+
+def train_step_neural(decoder, llr, check_index_tensor, var_index_tensor, ground_truth, optimizer, group=None):
+    """The reference's training iteration for `LDPCNeuralDecoder` (training/trainer.py:95-110: forward with the
+    index tensors and the transmitted bits, `loss.mean().backward()`, optimizer step), data-parallel: codewords
+    sharded by rank, one flat all-reduce of the gradient of `w_ch` (E,) and `w_res` (L,).  Returns the local
+    mean of the per-frame max loss."""
+    optimizer.zero_grad(set_to_none=False)
+    _, loss = decoder(llr, check_index_tensor, var_index_tensor, ground_truth)
+    batch_loss = loss.mean()
+    batch_loss.backward()
+    allreduce_gradients(decoder, group)
+    optimizer.step()
+    return batch_loss.detach()

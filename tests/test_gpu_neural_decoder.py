@@ -173,3 +173,19 @@ def test_c_abi_identity_order_equals_sorted_order():
     ref = oracle.neural_minsum_forward(llr_e.cpu().numpy(), cidx.cpu().numpy(), vidx.cpu().numpy(), w_ch.cpu().numpy(),
                                        w_res.cpu().numpy(), iters)
     np.testing.assert_allclose(outs[0].cpu().numpy(), ref["soft"], rtol=1e-4, atol=1e-6)
+
+
+def test_training_steps_reduce_the_loss():
+    """trainer.py:95-110 loop shape through train_step_neural: SGD on w_ch / w_res lowers the mean max-loss of a fixed batch."""
+    from ldpc_b200.training import train_step_neural
+    g = load_golden("neural_decoder_z4")
+    t = lambda k, dt=torch.float32: torch.from_numpy(g[k]).to(DEV).to(dt)
+    dec = _decoder(g, True)
+    cidx, vidx = t("check", torch.int64), t("var", torch.int64)
+    opt = torch.optim.SGD(dec.parameters(), lr=1e-2, momentum=0.9, weight_decay=1e-4)     # trainer.py:70
+    losses = [float(train_step_neural(dec, t("llr_e"), cidx, vidx, t("gt_e"), opt)) for _ in range(8)]
+    np.testing.assert_allclose(losses[0], g["max_loss"].mean(), rtol=1e-5)
+    assert losses[-1] < losses[0]
+    with torch.no_grad():                                            # the trained weights also run through the one-kernel path
+        soft, ml = dec(t("llr_e"), cidx, vidx, t("gt_e"))
+    assert torch.isfinite(soft).all() and float(ml.mean()) <= losses[0]
