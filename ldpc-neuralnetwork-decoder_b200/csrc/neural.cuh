@@ -195,10 +195,15 @@ __global__ void __launch_bounds__(kNeuralThreads) neural_decode_kernel(
         for (int l = 0; l < iters; ++l) {
             // ---- CheckLayer on x = ring[cur] ----
             const float* x = ring + cur * RE;
+            // loads that do not depend on the gathers are issued a round early (cnt) or at the top of the round
+            // (perm, w_ch): otherwise every round is a chain of three or four serialised L2 round trips
+            int cnt_next = (int)threadIdx.x < E ? (int)ccnt[threadIdx.x] : 0;
             for (int t = threadIdx.x; t - lane < E; t += kNeuralThreads) {
                 const bool live = t < E;
                 const int tt = live ? t : 0;
-                const int cnt = live ? (int)ccnt[tt] : 0;
+                const int cnt = cnt_next;
+                cnt_next = t + kNeuralThreads < E ? (int)ccnt[t + kNeuralThreads] : 0;
+                const int e = cperm ? (int)cperm[tt] : tt;
                 const unsigned short* col = cidx + tt;
                 float mn[kRows];
                 unsigned negb[kRows];
@@ -243,7 +248,6 @@ __global__ void __launch_bounds__(kNeuralThreads) neural_decode_kernel(
                     }
                 }
                 if (live) {
-                    const int e = cperm ? cperm[tt] : tt;
                     float o[kRows];
 #pragma unroll
                     for (int q = 0; q < kRows; ++q) {
@@ -262,15 +266,17 @@ __global__ void __launch_bounds__(kNeuralThreads) neural_decode_kernel(
             int slot_off[kNeuralMaxL];
 #pragma unroll
             for (int i = 0; i < kNeuralMaxL; ++i) slot_off[i] = ((cur - i + 2 * Lb) % Lb) * RE;
+            int vcnt_next = (int)threadIdx.x < E ? (int)vcnt[threadIdx.x] : 0;
             for (int t = threadIdx.x; t - lane < E; t += kNeuralThreads) {
                 const bool live = t < E;
                 const int tt = live ? t : 0;
-                const int cnt = live ? (int)vcnt[tt] : 0;
+                const int cnt = vcnt_next;
+                vcnt_next = t + kNeuralThreads < E ? (int)vcnt[t + kNeuralThreads] : 0;
+                const int e = vperm ? (int)vperm[tt] : tt;
+                const float w = w_ch[e];
                 float acc[kRows];
                 neural_gather_sum<kRows, KV>(c2v, vidx + tt, Kv_rt, E, cnt, acc);
                 if (live) {
-                    const int e = vperm ? vperm[tt] : tt;
-                    const float w = w_ch[e];
                     float r[kRows], ll[kRows], pv[kRows];
                     neural_ldv<kRows>(lls + e * kRows, ll);
 #pragma unroll
@@ -292,14 +298,16 @@ __global__ void __launch_bounds__(kNeuralThreads) neural_decode_kernel(
         // ---- final = VariableLayer(c2v, c2v); OutputLayer(final, llr, gt).  The ring is free now: soft values
         //      are staged there so that the global stores (and the ground-truth loads) are coalesced. ----
         float* stage = ring;
+        int cnt_next = (int)threadIdx.x < E ? (int)vcnt[threadIdx.x] : 0;
         for (int t = threadIdx.x; t - lane < E; t += kNeuralThreads) {
             const bool live = t < E;
             const int tt = live ? t : 0;
-            const int cnt = live ? (int)vcnt[tt] : 0;
+            const int cnt = cnt_next;
+            cnt_next = t + kNeuralThreads < E ? (int)vcnt[t + kNeuralThreads] : 0;
+            const int e = vperm ? (int)vperm[tt] : tt;
             float acc[kRows];
             neural_gather_sum<kRows, KV>(c2v, vidx + tt, Kv_rt, E, cnt, acc);
             if (live) {
-                const int e = vperm ? vperm[tt] : tt;
                 float own[kRows], ll[kRows], s[kRows];
                 neural_ldv<kRows>(c2v + e * kRows, own);
                 neural_ldv<kRows>(lls + e * kRows, ll);
@@ -377,10 +385,13 @@ __global__ void __launch_bounds__(kPackedThreads, 2) sorted_check_fwd_kernel(
             for (int e = threadIdx.x; e < E; e += kPackedThreads) sm[e * R + q] = x[row * E + e];
         }
         __syncthreads();
+        int cnt_next = (int)threadIdx.x < E ? (int)cnts[threadIdx.x] : 0;
         for (int t = threadIdx.x; t - lane < E; t += kPackedThreads) {
             const bool live = t < E;
             const int tt = live ? t : 0;
-            const int cnt = live ? (int)cnts[tt] : 0;
+            const int cnt = cnt_next;
+            cnt_next = t + kPackedThreads < E ? (int)cnts[t + kPackedThreads] : 0;
+            const int e = perm ? (int)perm[tt] : tt;
             const unsigned short* col = idx + tt;
             float mn[R];
             unsigned negb[R];
@@ -410,7 +421,6 @@ __global__ void __launch_bounds__(kPackedThreads, 2) sorted_check_fwd_kernel(
                     }
             }
             if (live) {
-                const int e = perm ? perm[tt] : tt;
 #pragma unroll
                 for (int q = 0; q < R; ++q)
                     if (q < nb) {
@@ -444,27 +454,32 @@ __global__ void __launch_bounds__(kPackedThreads, 2) sorted_variable_fwd_kernel(
             for (int e = threadIdx.x; e < E; e += kPackedThreads) sm[e * R + q] = c2v[row * E + e];
         }
         __syncthreads();
+        int cnt_next = (int)threadIdx.x < E ? (int)cnts[threadIdx.x] : 0;
         for (int t = threadIdx.x; t - lane < E; t += kPackedThreads) {
             const bool live = t < E;
             const int tt = live ? t : 0;
-            const int cnt = live ? (int)cnts[tt] : 0;
+            const int cnt = cnt_next;
+            cnt_next = t + kPackedThreads < E ? (int)cnts[t + kPackedThreads] : 0;
+            const int e = perm ? (int)perm[tt] : tt;
+            const float w = w_ch ? w_ch[e] : 1.0f;
+            float ll[R];                                   // channel LLRs in flight during the gathers
+#pragma unroll
+            for (int q = 0; q < R; ++q) ll[q] = llr[(b0 + (q < nb ? q : nb - 1)) * E + e];
             float acc[R];
             neural_gather_sum<R, KT>(sm, idx + tt, K, E, cnt, acc);
             if (live) {
-                const int e = perm ? perm[tt] : tt;
-                const float w = w_ch ? w_ch[e] : 1.0f;
 #pragma unroll
                 for (int q = 0; q < R; ++q)
                     if (q < nb) {
                         const long long g = (b0 + q) * E + e;
                         float r;
                         if (w_ch) {
-                            r = __fadd_rn(__fmul_rn(llr[g], w), acc[q]);
+                            r = __fadd_rn(__fmul_rn(ll[q], w), acc[q]);
 #pragma unroll
                             for (int i = 0; i < kMaxResidual; ++i)
                                 if (i < L) r = __fadd_rn(r, __fmul_rn(__ldg(w_res + i), prev.prev[i][g]));
                         } else {
-                            r = __fadd_rn(llr[g], acc[q]);
+                            r = __fadd_rn(ll[q], acc[q]);
                         }
                         out[g] = r;
                     }
