@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libldpc_b200.so")
+# LDPC_B200_LIB: load an experimental build (tools/build_variant.sh) instead of the in-tree library
+LIB_PATH = os.environ.get("LDPC_B200_LIB") or os.path.join(_HERE, "libldpc_b200.so")
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NOMEM = 0, -1, -2, -3, -4
 HARD_F32, HARD_U8, HARD_PACKED = 0, 1, 2
