@@ -189,3 +189,28 @@ def test_training_steps_reduce_the_loss():
     with torch.no_grad():                                            # the trained weights also run through the one-kernel path
         soft, ml = dec(t("llr_e"), cidx, vidx, t("gt_e"))
     assert torch.isfinite(soft).all() and float(ml.mean()) <= losses[0]
+
+
+def test_unit_channel_weights_without_residuals_equal_classic_min_sum():
+    """With w_ch = 1 and w_res = 0 the unrolled network IS flooding min-sum with scaling factor 1
+    (x_{l+1} = llr + sum of the other check messages; output = llr + sum of all), so its decisions must equal
+    MinSumScaledDecoder(scaling_factor=1.0) on the same LLRs: the edge-space path (generic index tables) checked
+    against the QC-structured kernel family on the headline code."""
+    from ldpc_b200.models import MinSumScaledDecoder
+    code = QCCode.nr_2_0(32)
+    _, cidx, vidx, oidx = create_LLR_mapping(code.dense().T)
+    iters, B = 6, 256
+    llr = torch.from_numpy(oracle.awgn_llr(None, B, code.N, snr_db=-2.0, seed=77)).to(DEV)
+    dec = LDPCNeuralDecoder(code.E, iters, 2, output_index_tensor=oidx).to(DEV)
+    with torch.no_grad():
+        dec.residual_layer.w_res.zero_()
+        soft, _ = dec(llr, cidx.to(DEV), vidx.to(DEV))               # sigmoid(posterior LLR), (B, N)
+    classic = MinSumScaledDecoder(code, max_iterations=iters, scaling_factor=1.0, early_stopping=False, path="exact")
+    beliefs, bits = classic.forward(llr)
+    mine = (soft < 0.5).float()                                      # posterior < 0  <=>  bit 1
+    differ = (mine != bits.float())
+    # the two paths add the messages in different orders: decisions may differ only where the belief is ~0
+    assert int(differ.sum()) <= 8 and (beliefs[differ].abs() < 1e-3).all()
+    sure = beliefs.abs() < 10
+    np.testing.assert_allclose(torch.logit(soft[sure].double()).cpu().numpy(), beliefs[sure].double().cpu().numpy(),
+                               rtol=2e-3, atol=2e-3)
