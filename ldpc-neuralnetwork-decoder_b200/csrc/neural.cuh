@@ -32,7 +32,7 @@ namespace ldpc {
 constexpr int kNeuralThreads = LDPC_NEURAL_THREADS;
 constexpr unsigned short kNeuralPad = 0xFFFFu;
 #ifndef LDPC_NEURAL_GROUP
-#define LDPC_NEURAL_GROUP 4
+#define LDPC_NEURAL_GROUP 8
 #endif
 constexpr int kNeuralGroup = LDPC_NEURAL_GROUP;
 // 1: load a column's whole index list before the first gather.  Measured slower (2.3-2.6 M cw/s at 768 / 1024
@@ -363,13 +363,19 @@ __global__ void __launch_bounds__(kNeuralThreads) neural_decode_kernel(
 // ---- the same machinery for ONE layer at a time (training path, and the stand-alone CheckLayer / VariableLayer) ----
 // kRows = 4 codewords per CTA, row-interleaved in shared memory (one LDS.128 per neighbour), sorted-pack tables.
 // Results go straight to global memory at edge perm[t]: 4-byte scattered stores, merged by the L2.
-constexpr int kPackedThreads = 512;
+#ifndef LDPC_PACKED_THREADS
+#define LDPC_PACKED_THREADS 512
+#endif
+#ifndef LDPC_PACKED_CTAS
+#define LDPC_PACKED_CTAS 2
+#endif
+constexpr int kPackedThreads = LDPC_PACKED_THREADS;
 constexpr int kPackedRows = 4;
 
 // CheckLayer.forward (layers.py:14-66).  nstar (optional) [B,E] int32: the edge whose |x| was selected as the
 // minimum, -1 if the minimum is the 1e10 stand-in of a zero / padded input (no gradient, layers.py:55-58).
 template <int KT>      // compile-time table width (9 for the BG2 check table), 0 = run-time K
-__global__ void __launch_bounds__(kPackedThreads, 2) sorted_check_fwd_kernel(
+__global__ void __launch_bounds__(kPackedThreads, LDPC_PACKED_CTAS) sorted_check_fwd_kernel(
     const float* __restrict__ x, const unsigned short* __restrict__ idx, int K_rt, const unsigned char* __restrict__ cnts,
     const unsigned short* __restrict__ perm, long long B, int E, float* __restrict__ out, int* __restrict__ nstar) {
     constexpr int R = kPackedRows;
@@ -438,7 +444,7 @@ __global__ void __launch_bounds__(kPackedThreads, 2) sorted_check_fwd_kernel(
 // VariableLayer.forward (layers.py:78-125): out = llr + sum (w_ch == nullptr), or the variable + residual update
 // of LDPCNeuralDecoder: out = (w_ch*llr + sum) + sum_i w_res[i]*prev[i]  (same operation order as the two layers).
 template <int KT>      // 22 for the BG2 variable table, 0 = run-time K
-__global__ void __launch_bounds__(kPackedThreads, 2) sorted_variable_fwd_kernel(
+__global__ void __launch_bounds__(kPackedThreads, LDPC_PACKED_CTAS) sorted_variable_fwd_kernel(
     const float* __restrict__ llr, const float* __restrict__ c2v, const unsigned short* __restrict__ idx, int K,
     const unsigned char* __restrict__ cnts, const unsigned short* __restrict__ perm, const float* __restrict__ w_ch,
     const float* __restrict__ w_res, ResidualPtrs prev, int L, long long B, int E, float* __restrict__ out) {
