@@ -37,27 +37,31 @@ class _Packed:
 
     def compacted(self):
         """(table, None, cnt): the lists compacted but the columns left in edge order (identity permutation)."""
-        src = self._i64
-        valid = src >= 0
-        order = torch.argsort((~valid).to(torch.int8), dim=1, stable=True)
-        compact = torch.gather(src, 1, order)
-        return _pack(compact.clamp_min(0).contiguous()), None, valid.sum(dim=1).to(torch.uint8).contiguous()
+        compact, _, cnt = sort_plan(self._i64, sort=False)
+        return _pack(compact), None, cnt
 
     def sorted(self):
-        """(table [K,E] uint16, perm [E] uint16, cnt [E] uint8) for the one-kernel decoder: columns ordered by
-        descending neighbour count, each list compacted (valid neighbours first, in the caller's order; unused
-        slots 0), column t = edge perm[t]."""
+        """(table [K,E] uint16, perm [E] uint16, cnt [E] uint8) for the engine's sorted-pack kernels."""
         if self._sorted is None:
-            src = self._i64
-            E, K = src.shape
-            valid = src >= 0
-            order = torch.argsort((~valid).to(torch.int8), dim=1, stable=True)
-            compact = torch.gather(src, 1, order)
-            cnt = valid.sum(dim=1)
-            perm = torch.argsort(cnt, descending=True, stable=True)
-            self._sorted = (_pack(compact[perm].clamp_min(0).contiguous()),
-                            perm.to(torch.int32).to(torch.int16).contiguous(), cnt[perm].to(torch.uint8).contiguous())
+            compact, perm, cnt = sort_plan(self._i64)
+            self._sorted = (_pack(compact), perm.to(torch.int32).to(torch.int16).contiguous(), cnt)
         return self._sorted
+
+
+def sort_plan(src, sort=True):
+    """Host-side plan of the sorted-pack format (pure tensor algebra, any device).  src: [E,K] int64, -1 padded.
+    Returns (rows [E,K] int64, perm [E] int64, cnt [E] uint8): row t lists the neighbours of edge perm[t] with the
+    valid entries first in the caller's order and unused slots 0; rows are ordered by descending neighbour count
+    (stable, so equal counts keep edge order); cnt[t] = number of valid entries of row t."""
+    E, K = src.shape
+    if K > 255:
+        raise ValueError("neighbour tables wider than 255 slots are not supported")
+    valid = src >= 0
+    order = torch.argsort((~valid).to(torch.int8), dim=1, stable=True)
+    compact = torch.gather(src, 1, order)
+    cnt = valid.sum(dim=1)
+    perm = torch.argsort(cnt, descending=True, stable=True) if sort else torch.arange(E, device=src.device)
+    return compact[perm].clamp_min(0).contiguous(), perm, cnt[perm].to(torch.uint8).contiguous()
 
 
 def _pack(src):

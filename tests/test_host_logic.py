@@ -198,3 +198,26 @@ def test_encoder_plan_and_oracle_encoder(Z):
     assert not oracle.encode_dense(code.shifts, Z, np.zeros((1, code.K), dtype=np.uint8)).any()
     with pytest.raises(ValueError):
         SystematicEncoder(QCCode(np.array([[0, 0, -1], [0, -1, 0]]), 2))      # every row owns a degree-1 column: no core block
+
+
+def test_sorted_pack_plan_of_the_neighbour_tables():
+    """models/layers.py:sort_plan (host side of the sorted-pack tables the layer / neural-decoder kernels read):
+    row t holds exactly the valid neighbours of edge perm[t] in the caller's order, counts are right and
+    non-increasing, perm is a permutation; padding anywhere in the caller's rows is tolerated."""
+    from ldpc_b200.models.layers import sort_plan
+    g = load_golden("mapping_layers")
+    for name in ("z4_check", "z4_var", "toy_check", "toy_var"):
+        src = torch.from_numpy(g[name].astype(np.int64))
+        if name == "z4_check":
+            src = torch.flip(src, dims=[1])                          # padding first
+        rows, perm, cnt = sort_plan(src)
+        E, K = src.shape
+        assert sorted(perm.tolist()) == list(range(E))
+        c = cnt.to(torch.int64)
+        assert bool((c[:-1] >= c[1:]).all())
+        for t in range(E):
+            want = [int(v) for v in src[perm[t]] if v >= 0]
+            assert rows[t, :len(want)].tolist() == want and int(c[t]) == len(want)
+            assert bool((rows[t, len(want):] == 0).all())
+        rows_id, perm_id, cnt_id = sort_plan(src, sort=False)
+        assert perm_id.tolist() == list(range(E)) and int(cnt_id.to(torch.int64).sum()) == int((src >= 0).sum())
