@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Throughput of LDPCNeuralDecoder (unrolled neural min-sum, edge space) on one GPU:
 fused variable+residual kernel vs the literal two-layer composition, inference and one
-training step (forward + loss.mean().backward()).  BG2 Z=32, E = 6304.
+training step (forward + loss.mean().backward()).  BG2 Z=32 (E = 6304) or Z=4 (E = 788).
 Usage: python tools/neural_bench.py [--batch 4096] [--iters 5] [--reps 5]"""
 import argparse
 import json
@@ -34,20 +34,21 @@ def main():
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--z", type=int, default=32, choices=[4, 32], help="lifting size of the BG2 code")
     ap.add_argument("--lib", default=None, help="alternative libldpc_b200.so (tools/build_variant.sh)")
     args = ap.parse_args()
     if args.lib:
         from ldpc_b200 import _native
         _native.LIB_PATH = os.path.abspath(args.lib)
     dev = "cuda:0"
-    code = QCCode.nr_2_0(32)
+    code = QCCode.nr_2_0(args.z)
     _, cidx, vidx, oidx = create_LLR_mapping(code.dense().T)
     cidx, vidx = cidx.to(dev), vidx.to(dev)
     g = torch.Generator(device=dev).manual_seed(1)
     llr = (torch.randn(args.batch, code.N, device=dev, generator=g) * 0.5 + 0.4)
     llr_e = llr[:, oidx[0].to(dev)].contiguous()
     gt = torch.ones_like(llr_e)
-    out = {"batch": args.batch, "iters": args.iters, "E": code.E, "lib": args.lib}
+    out = {"batch": args.batch, "iters": args.iters, "Z": args.z, "E": code.E, "lib": args.lib}
     for fused in (True, False):
         dec = LDPCNeuralDecoder(code.E, args.iters, 2, fused=fused).to(dev)
 
