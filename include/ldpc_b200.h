@@ -52,7 +52,12 @@ typedef enum ldpc_status {
  * traditional_decoders.py:102-106,255-258) is built by the caller from `valid_mask`.     */
 
 /* kernel selection */
-#define LDPC_PATH_AUTO 0  /* fastest kernel that supports the code                          */
+#define LDPC_PATH_AUTO 0  /* fastest kernel that supports the code.  NOT reference operation order for
+                           * min-sum: the specialised kernel forms v2c as posterior - own message, so soft
+                           * outputs differ from the reference by rounding and +-inf channel LLRs can give
+                           * inf - inf = NaN where the reference keeps inf.  Callers with non-finite LLRs
+                           * (hard-decision inputs) must use LDPC_PATH_EXACT; the Python classes do that
+                           * themselves.  BP under AUTO handles non-finite messages exactly.             */
 #define LDPC_PATH_EXACT 1 /* table-driven kernel, reference operation order (any QC code)   */
 #define LDPC_PATH_FAST 2  /* register/shuffle kernel specialised for a shipped 5G table     */
 
@@ -236,7 +241,9 @@ int ldpc_gnn_forward(const ldpc_gnn_t* g, const float* params, const float* llr,
                      float* prob_out, void* workspace, size_t ws_bytes, int training, void* stream);
 /* mean-BCE loss on prob_out vs gt (message_gnn_decoder.py:313-315) and its gradient w.r.t.
  * every parameter (autograd of the reference module); needs the workspace of a
- * training=1 forward.  grad_params is accumulated into (+=).                              */
+ * training=1 forward with the SAME params.  grad_params is accumulated into (+=).  The weight
+ * images are re-packed from `params` here, so other forwards on the handle in between are
+ * harmless; a handle is single-stream (its packed-weight scratch is shared by all calls).  */
 int ldpc_gnn_backward(const ldpc_gnn_t* g, const float* params, const float* llr, const float* gt, int64_t B,
                       float* loss_out, float* grad_params, void* workspace, size_t ws_bytes, void* stream);
 

@@ -234,36 +234,49 @@ int ldpc_decode_host_q(const ldpc_code_t* code, int algo, const void* llr_host, 
             LDPC_CUDA(cudaMalloc(&hs.d_soft[s], need_soft)); hs.cap_soft[s] = need_soft;
         }
     }
+    // error inside the chunk loop: async D2H copies into the CALLER's buffers may still be in flight on the staging
+    // streams, so settle all of them before the error code goes back
+    auto settle = [&hs]() { for (int s = 0; s < HostStage::kStages; ++s) if (hs.st[s]) cudaStreamSynchronize(hs.st[s]); };
+#define LDPC_CUDA_SETTLE(expr)                                                                                     \
+    do {                                                                                                           \
+        cudaError_t _e = (expr);                                                                                   \
+        if (_e != cudaSuccess) {                                                                                   \
+            settle();                                                                                              \
+            return fail(LDPC_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+        }                                                                                                          \
+    } while (0)
     int64_t done = 0;
     for (int it = 0; done < B; ++it, done += chunk) {
         const int s = it % HostStage::kStages;
         const int64_t b = (B - done) < chunk ? (B - done) : chunk;
         // same-stream ordering makes reuse of stage s safe: its previous D2H precedes this H2D
         if (raw_elem == 0) {
-            LDPC_CUDA(cudaMemcpyAsync(hs.d_llr[s], (const float*)llr_host + (size_t)done * N, sizeof(float) * (size_t)b * N,
+            LDPC_CUDA_SETTLE(cudaMemcpyAsync(hs.d_llr[s], (const float*)llr_host + (size_t)done * N, sizeof(float) * (size_t)b * N,
                                       cudaMemcpyHostToDevice, hs.st[s]));
         } else {
             const long long n = (long long)b * N;
-            LDPC_CUDA(cudaMemcpyAsync(hs.d_raw[s], (const char*)llr_host + raw_elem * (size_t)done * N, raw_elem * (size_t)n,
+            LDPC_CUDA_SETTLE(cudaMemcpyAsync(hs.d_raw[s], (const char*)llr_host + raw_elem * (size_t)done * N, raw_elem * (size_t)n,
                                       cudaMemcpyHostToDevice, hs.st[s]));
             const int grid = (int)((n + 1023) / 1024 < (long long)kNumSMs * 8 ? (n + 1023) / 1024 : (long long)kNumSMs * 8);
             if (llr_format == LDPC_LLR_I8)
                 llr_dequant_kernel<int8_t><<<grid, 256, 0, hs.st[s]>>>((const int8_t*)hs.d_raw[s], llr_scale, n, (float*)hs.d_llr[s]);
             else
                 llr_dequant_kernel<__half><<<grid, 256, 0, hs.st[s]>>>((const __half*)hs.d_raw[s], llr_scale, n, (float*)hs.d_llr[s]);
-            LDPC_CHECK_LAUNCH("llr_dequant_kernel");
+            LDPC_COUNT_LAUNCH();
+            LDPC_CUDA_SETTLE(cudaGetLastError());
         }
         int rc = decode_common(code, algo, (const float*)hs.d_llr[s], b, iters, alpha, LDPC_STOP_FIXED, path,
                                soft_host ? (float*)hs.d_soft[s] : nullptr, hs.d_hard[s], hard_dtype, nullptr, nullptr,
                                nullptr, 0, hs.st[s]);
-        if (rc) return rc;
-        LDPC_CUDA(cudaMemcpyAsync((char*)hard_host + hard_row * (size_t)done, hs.d_hard[s], hard_row * (size_t)b,
+        if (rc) { settle(); return rc; }
+        LDPC_CUDA_SETTLE(cudaMemcpyAsync((char*)hard_host + hard_row * (size_t)done, hs.d_hard[s], hard_row * (size_t)b,
                                   cudaMemcpyDeviceToHost, hs.st[s]));
         if (soft_host)
-            LDPC_CUDA(cudaMemcpyAsync(soft_host + (size_t)done * N, hs.d_soft[s], sizeof(float) * (size_t)b * N,
+            LDPC_CUDA_SETTLE(cudaMemcpyAsync(soft_host + (size_t)done * N, hs.d_soft[s], sizeof(float) * (size_t)b * N,
                                       cudaMemcpyDeviceToHost, hs.st[s]));
     }
     for (int s = 0; s < HostStage::kStages; ++s) LDPC_CUDA(cudaStreamSynchronize(hs.st[s]));
+#undef LDPC_CUDA_SETTLE
     return LDPC_OK;
 }
 
@@ -839,6 +852,13 @@ int ldpc_gnn_backward(const ldpc_gnn_t* g, const float* params, const float* llr
     float *G = base + tw.G, *DC = base + tw.DC, *HR = base + tw.HR, *DH = base + tw.DH;
     float *DPV = base + tw.DPV, *MV = base + tw.MV, *DMV = base + tw.DMV, *DPC = base + tw.DPC, *MC = base + tw.MC, *DMC = base + tw.DMC;
     float* PG = base + tw.PG;
+    // The packed weight images live in the handle and an inference forward with other weights (EMA copy, evaluation
+    // pass) may have overwritten them since the training forward: re-pack from THIS call's parameters (two small
+    // launches).  A handle is still single-stream: d_packed / d_tc are shared scratch.
+    gnn_pack_kernel<<<dim3(32, L), 256, 0, st>>>(params, lay, L, g->d_packed, g->d_emb);
+    LDPC_CHECK_LAUNCH("gnn_pack_kernel");
+    gnn_pack_tc_kernel<<<dim3(16, L), 256, 0, st>>>(g->d_packed, g->d_tc);
+    LDPC_CHECK_LAUNCH("gnn_pack_tc_kernel");
     LDPC_CUDA(cudaMemsetAsync(PG, 0, sizeof(float) * (size_t)L * tw.pg_layer, st));
     LDPC_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), st));
     // loss and d(loss)/d(soft)

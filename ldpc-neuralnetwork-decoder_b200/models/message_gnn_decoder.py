@@ -158,6 +158,11 @@ class MessageGNNDecoder(nn.Module):
     def __init__(self, num_messages, num_iterations=5, hidden_dim=64, num_message_types=1, code=None,
                  base_edge_types=None):
         super().__init__()
+        if int(hidden_dim) != 64:
+            # message_gnn_decoder.py:162,539 accept any width; the tensor-core kernels (128-row tiles, K = 64/128 MMA
+            # shapes, TMEM column map) are built for the width every shipped entry point uses
+            raise ValueError(f"MessageGNNDecoder: hidden_dim={hidden_dim} is not supported by the B200 engine; "
+                             "its kernels are compiled for hidden_dim=64 (the reference's default)")
         self.num_messages = num_messages
         self.num_iterations = num_iterations
         self.hidden_dim = hidden_dim

@@ -10,6 +10,13 @@ num_iterations int)` contract, including the reference's batch-global early-stop
 `__call__` returning `(soft LLRs, hard bits)`, construction from `(base_graph, Z)` or a
 `QCCode` so no dense H is needed, and `decode_with_iterations` (per-codeword early exit).
 
+`path`: "exact" = the reference's operation order (min-sum beliefs bit-identical to the reference);
+"fast" = the kernels specialised for the shipped 5G tables; "auto" (default) = fast for min-sum,
+exact for BP.  "auto"/"fast" min-sum is NOT reference order: hard decisions equal the reference's on
+every fixture and on 2^20 frames at the bench point (bench.py `parity`), soft outputs agree to
+rounding (1e-4 relative on converged frames); batches containing non-finite LLRs are routed to the
+exact kernel automatically.
+
 All arithmetic happens in the CUDA engine (csrc/decode_exact.cuh, csrc/decode_fast.cuh)
 behind the C ABI; these classes only marshal tensors.  CPU tensors are staged through the
 current CUDA device and results are returned on the input's device; without a GPU every call
@@ -48,7 +55,14 @@ class _FloodingDecoder:
             if not torch.cuda.is_available():
                 raise RuntimeError("the LDPC engine needs a CUDA device (no CPU fallback)")
             dev = torch.device("cuda", torch.cuda.current_device())
-        return llr.detach().to(device=dev, dtype=torch.float32).contiguous(), dev
+        llr_d = llr.detach().to(device=dev, dtype=torch.float32).contiguous()
+        # path "auto" sends min-sum to the specialised kernel, whose variable update is posterior - own message: with
+        # +-inf channel LLRs (hard-decision inputs) that is inf - inf = NaN where the reference's sum over the OTHER
+        # checks keeps inf (traditional_decoders.py:235-244).  Such batches take the reference-order kernel.
+        self._route = self.path
+        if self.path == "auto" and self._ALGO == _native.ALGO_MINSUM and llr_d.numel() and not bool(torch.isfinite(llr_d).all()):
+            self._route = "exact"
+        return llr_d, dev
 
     def _launch(self, llr_d, dev, iters, stop_mode=_native.STOP_FIXED, soft=True, hard_dtype=_native.HARD_F32,
                 syndrome=False, iters_out=False, mask=False, path=None):
@@ -68,7 +82,7 @@ class _FloodingDecoder:
             return soft_t, hard_t, syn_t, it_t, mask_t
         L = _native.lib()
         h = self.code.handle(dev)
-        p = _native.PATHS[path or self.path]
+        p = _native.PATHS[path or getattr(self, '_route', self.path)]
         with torch.cuda.device(dev):
             st = _native.stream_ptr(dev)
             if self._ALGO == _native.ALGO_MINSUM:
@@ -95,9 +109,10 @@ class _FloodingDecoder:
     def _fast_early_allowed(self):
         """The specialised early-exit kernel may replace the exact validity-mask pass: path "auto" for min-sum,
         "fast" for either algorithm (the same policy as for fixed iteration counts); never for path "exact"."""
-        if self.path == "exact":
+        route = getattr(self, "_route", self.path)
+        if route == "exact":
             return False
-        return self.path == "fast" or self._ALGO == _native.ALGO_MINSUM
+        return route == "fast" or self._ALGO == _native.ALGO_MINSUM
 
     def _decode_full(self, llr, soft=True):
         """Batch-global early stopping of the reference (:102-106 / :255-258): stop after the first iteration T at
@@ -112,7 +127,7 @@ class _FloodingDecoder:
         if self.early_stopping and llr_d.shape[0] > 0:
             # two exact passes (docstring), on the specialised kernels where they exist and the policy allows them,
             # otherwise on the exact kernel -- either way far fewer iterations than a max_iterations-long mask pass
-            for route in (["fast"] if self._fast_early_allowed() else []) + [self.path]:
+            for route in (["fast"] if self._fast_early_allowed() else []) + [self._route]:
                 try:
                     _, _, syn, its, _ = self._launch(llr_d, dev, iters, stop_mode=_native.STOP_PER_CODEWORD, soft=False,
                                                      hard_dtype=_native.HARD_PACKED, syndrome=True, iters_out=True, path=route)

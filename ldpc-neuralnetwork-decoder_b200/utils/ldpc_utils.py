@@ -116,7 +116,11 @@ class QCCode:
     # ---- constructors ----
     @classmethod
     def from_base_matrix(cls, base_matrix, Z):
-        return cls(torch.as_tensor(base_matrix).cpu().numpy(), Z)
+        """Base graph as the reference's files hold it: non-negative shifts are taken mod Z, exactly what
+        expand_base_matrix's roll does (ldpc_utils.py:121-123), so `NR_2_0_32.txt` lifted with Z=16 works as it
+        does upstream.  The raw constructor keeps the strict [0, Z) check."""
+        s = np.rint(np.asarray(torch.as_tensor(base_matrix).cpu().numpy(), dtype=np.float64)).astype(np.int64)
+        return cls(np.where(s >= 0, s % int(Z), -1), Z)
 
     @classmethod
     def from_file(cls, path, Z):
