@@ -108,3 +108,68 @@ def test_two_rank_gloo_counters_equal_single_rank():
         assert p.exitcode == 0
     want = local_counters(0, FRAMES).tolist()
     assert got == want and got[2] == FRAMES
+
+
+# ---- checkpointed sweep (sim.simulate_fer): killed after some blocks, resumed on another world size ----------------
+def _oracle_block(code, algo, iters, alpha, snr_db, seed, first, count, dev, max_frames_per_call):
+    """Stand-in for sim._run_block (the fused GPU kernel) with the same Philox keying, on the CPU oracle."""
+    from oracle import oracle
+    if count == 0:
+        return torch.zeros(4, dtype=torch.int64)
+    llr = oracle.awgn_llr(None, count, code.N, snr_db, seed, first_frame=first)
+    o = oracle.decode(code.shifts, code.Z, llr, iters, algo, alpha, order="fast", want_mask=True)
+    nerr = o["hard"].sum(axis=1)
+    valid = ((o["valid_mask"][:, 0] >> np.uint64(iters - 1)) & np.uint64(1)).astype(bool)
+    return torch.tensor([int(nerr.sum()), int((nerr > 0).sum()), count, int(((nerr > 0) & valid).sum())], dtype=torch.int64)
+
+
+SWEEP = dict(snr_db_list=[-1.0, 0.5], frames=203, algo="minsum", iters=4, alpha=0.75, seed=5, block_frames=50)
+
+
+def sweep_worker(rank, world, port, q, ckpt, stop_after):
+    import sys
+    sys.path.insert(0, ROOT)
+    import ldpc_b200  # noqa: F401
+    from ldpc_b200 import sim
+    sim._run_block = _oracle_block
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    res = sim.simulate_fer(QCCode.nr_2_0(4), rank=rank, world=world, checkpoint=ckpt, stop_after_blocks=stop_after, **SWEEP)
+    dist.barrier()
+    if rank == 0:
+        q.put(res)
+    dist.destroy_process_group()
+
+
+def test_sweep_checkpoint_resumes_on_another_world_size(tmp_path, monkeypatch):
+    from ldpc_b200 import sim
+    monkeypatch.setattr(sim, "_run_block", _oracle_block)
+    code = QCCode.nr_2_0(4)
+    want = sim.simulate_fer(code, **SWEEP)                                  # uninterrupted, one rank, no checkpoint
+    assert [p["frames"] for p in want] == [203, 203] and want[0]["frame_errors"] > 0
+    ckpt = str(tmp_path / "sweep.json")
+    # 2 gloo ranks, "killed" after 3 of the 5 + 5 blocks
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=sweep_worker, args=(r, 2, port, q, ckpt, 3)) for r in range(2)]
+    for p in procs:
+        p.start()
+    assert q.get(timeout=180) is None
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    st = sim.load_checkpoint(ckpt, sim.sweep_signature(code, SWEEP["snr_db_list"], 203, "minsum", 4, 0.75, 5))
+    assert st["current"]["point"] == 0 and st["current"]["frames_done"] == 150 and st["points"] == []
+    # resumed on ONE rank, killed again inside point 1, then finished: identical to the uninterrupted sweep
+    assert sim.simulate_fer(code, checkpoint=ckpt, stop_after_blocks=4, **SWEEP) is None
+    st = sim.load_checkpoint(ckpt, st["signature"])
+    assert len(st["points"]) == 1 and st["current"] == {"point": 1, "frames_done": 100, "counters": st["current"]["counters"]}
+    got = sim.simulate_fer(code, checkpoint=ckpt, **SWEEP)
+    assert got == want
+    assert sim.simulate_fer(code, checkpoint=ckpt, **SWEEP) == want         # a finished sweep replays from the file
+    with pytest.raises(ValueError):                                         # a different sweep must not adopt this file
+        sim.simulate_fer(code, checkpoint=ckpt, **dict(SWEEP, seed=6))

@@ -221,3 +221,45 @@ def test_sorted_pack_plan_of_the_neighbour_tables():
             assert bool((rows[t, len(want):] == 0).all())
         rows_id, perm_id, cnt_id = sort_plan(src, sort=False)
         assert perm_id.tolist() == list(range(E)) and int(cnt_id.to(torch.int64).sum()) == int((src >= 0).sum())
+
+
+def test_base_matrix_shifts_are_reduced_mod_z_like_the_reference_lift():
+    """the reference's expand_base_matrix rolls by the raw shift, i.e. mod Z (ldpc_utils.py:121-123), so
+    NR_2_0_32.txt lifted with --lifting_factor 16 works upstream; the (base_graph, Z) constructors must accept it too
+    and describe the same dense H.  The raw constructor keeps the strict range check."""
+    base32 = QCCode.nr_2_0(32).base_matrix()                       # shifts up to 31
+    code = QCCode.from_base_matrix(base32, 16)
+    assert code.Z == 16 and int(code.shifts.max()) < 16
+    assert np.array_equal(code.shifts, QCCode.nr_2_0(16).shifts)
+    assert torch.equal(code.dense(), expand_base_matrix(base32, 16))
+    assert np.array_equal(as_code(base_graph=base32, Z=16).shifts, code.shifts)
+    with pytest.raises(ValueError):
+        QCCode(base32.numpy(), 16)
+
+
+def test_gnn_rejects_other_hidden_widths_in_the_constructor():
+    from ldpc_b200.models import MessageGNNDecoder
+    with pytest.raises(ValueError, match="hidden_dim"):
+        MessageGNNDecoder(788, 5, hidden_dim=32)
+
+
+def test_bench_roofline_counts_match_the_kernel_sources():
+    """bench.py computes roofline.frac from per-codeword counts measured with ncu (tools/ncu_to_profile.py).  The count
+    file records the SHA-256 of the kernel sources it was captured on: if the kernel changed since, the counts are
+    stale and this test says so (re-capture: tools/ncu_to_profile.py, DESIGN.md 'Measurement')."""
+    import hashlib
+    import json
+    import bench
+    for workload, rel in bench.COUNTS_FILES.items():
+        path = os.path.join(ROOT, rel)
+        if not os.path.exists(path):
+            assert workload != "minsum", "the headline workload needs its count file"
+            continue
+        c = json.load(open(path))
+        assert c["inst_per_cw"] > 0 and c["dram_bytes_per_cw"] > 0 and c["codewords"] > 0
+        assert c["source_sha256"], "count file does not say which sources it was measured on"
+        for src, sha in c["source_sha256"].items():
+            now = hashlib.sha256(open(os.path.join(ROOT, src), "rb").read()).hexdigest()
+            assert now == sha, f"{src} changed after the ncu capture behind {rel}: re-run the capture"
+        k = bench.kernel_counts(workload)
+        assert k["inst_per_cw"] == c["inst_per_cw"] and k["file"] == rel
