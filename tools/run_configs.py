@@ -86,7 +86,7 @@ pts4, dt4 = timed(lambda: simulate_fer(code, snrs4, per_point, algo="minsum", it
 chk4 = []
 for k, s in enumerate(snrs4[:4]):
     n = 20000
-    be, fe = oracle_counts(code, 32, "minsum", 10, s, 99 + k, n, "fast")
+    be, fe = oracle_counts(code, 32, "minsum", 10, s, 99 + k, n, "reference")
     sub = simulate_fer(code, [s], n, algo="minsum", iters=10, seed=99 + k, device=dev)[0]
     lo, hi = wilson_interval(pts4[k]["frame_errors"], pts4[k]["frames"])
     chk4.append({"snr_db": s, "frames": n, "oracle_frame_errors": fe, "engine_frame_errors": sub["frame_errors"],
