@@ -102,20 +102,29 @@ __global__ void __launch_bounds__(256) decode_exact_kernel(const DecodeParams p)
                 if constexpr (kAlgo == LDPC_ALGO_MINSUM) {
                     float m1 = CUDART_INF_F, m2 = CUDART_INF_F;
                     uint32_t sg = 0;
+                    int nn = 0;                    // NaN inputs (only reachable from non-finite channel LLRs)
 #pragma unroll
                     for (int k = 0; k < kMaxDc; ++k)
                         if (k < d) {
+                            // reference :216-222: `mag < min_mag` is false for a NaN magnitude, i.e. a NaN never becomes a
+                            // minimum: it takes part as +inf here
                             const float a = fabsf(v[k]);
-                            m2 = fminf(m2, fmaxf(m1, a));
-                            m1 = fminf(m1, a);
+                            const float an = (a != a) ? CUDART_INF_F : a;
+                            m2 = fminf(m2, fmaxf(m1, an));
+                            m1 = fminf(m1, an);
                             sg ^= f2u(v[k]);
+                            nn += (a != a) ? 1 : 0;
                         }
                     const float s1 = __fmul_rn(p.alpha, m1), s2 = __fmul_rn(p.alpha, m2);
 #pragma unroll
                     for (int k = 0; k < kMaxDc; ++k)
                         if (k < d) {
+                            // torch.sign(NaN) = 0 (:213), so a NaN among the OTHER inputs zeroes the sign product: the
+                            // message is 0 * scaled_min = 0, or NaN when that minimum is infinite
+                            const bool other_nan = nn - ((v[k] != v[k]) ? 1 : 0) > 0;
                             const float mag = (fabsf(v[k]) == m1) ? s2 : s1;
-                            v[k] = u2f(f2u(mag) ^ ((sg ^ f2u(v[k])) & 0x80000000u));
+                            const float out = u2f(f2u(mag) ^ ((sg ^ f2u(v[k])) & 0x80000000u));
+                            v[k] = other_nan ? __fmul_rn(0.0f, mag) : out;
                         }
                 } else {
                     float t[kMaxDc];

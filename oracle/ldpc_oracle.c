@@ -104,7 +104,8 @@ static void graph_free(graph_t* g) {
     free(g);
 }
 
-static inline float sgnf(float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : (x == 0.0f ? 0.0f : x)); }
+/* torch.sign: (0 < x) - (x < 0), hence sign(NaN) = 0 (pinned by tests/golden/nonfinite_z4_b24.npz) */
+static inline float sgnf(float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : 0.0f); }
 static inline float tanh_ref(float x) { return (float)tanh((double)x); }
 static inline float atanh_ref(float x) { return (float)atanh((double)x); }
 

@@ -107,6 +107,33 @@ def classic(Z, B, iters, snr_db, seed, alpha, tag):
           f"bp nonfinite {(~torch.isfinite(bp_bel)).float().mean():.3f}")
 
 
+def nonfinite(Z=4, B=24, iters=6, seed=21):
+    """Non-finite channel LLRs through the unmodified reference (min-sum and BP): hard-decision inputs (+-inf), single
+    huge / infinite entries, a NaN entry.  Pins how inf - inf, sign(NaN) and `mag < min_mag` behave in the reference
+    (traditional_decoders.py:207-244) -- the engine's exact kernel and the oracle must reproduce the NaN/inf pattern."""
+    base = load_base_matrix(TABLES[Z])
+    H = expand_base_matrix(base, Z)
+    ms = MinSumScaledDecoder(H, max_iterations=iters, scaling_factor=0.75, early_stopping=False)
+    bp = share_indices(ms, BeliefPropagationDecoder, max_iterations=iters, early_stopping=False)
+    torch.manual_seed(seed)
+    llr = AWGNChannel().transmit(torch.zeros(B, H.shape[1]), 1.0)
+    hd = torch.where(llr >= 0, torch.tensor(float("inf")), torch.tensor(float("-inf")))
+    llr[:8] = hd[:8]                                   # frames 0-7: pure hard-decision input
+    llr[8:12, ::3] = hd[8:12, ::3]                     # frames 8-11: every third LLR saturated
+    llr[12, 5] = float("inf")
+    llr[13, 7] = float("-inf")
+    llr[14, 11] = float("nan")
+    llr[15, 3] = 1e30
+    llr[16, :4] = 0.0
+    llr[16, 9] = float("inf")
+    ms_bits, ms_it, ms_bel = run_capturing_beliefs(ms, llr)
+    bp_bits, bp_it, bp_bel = run_capturing_beliefs(bp, llr)
+    np.savez_compressed(os.path.join(OUT, f"nonfinite_z{Z}_b{B}.npz"), Z=Z, iters=iters, alpha=0.75, llr=llr.numpy(),
+                        ms_bits=pack(ms_bits), ms_beliefs=ms_bel.numpy(), bp_bits=pack(bp_bits), bp_beliefs=bp_bel.numpy())
+    print(f"nonfinite: ms nan {torch.isnan(ms_bel).float().mean():.3f} inf {torch.isinf(ms_bel).float().mean():.3f}; "
+          f"bp nan {torch.isnan(bp_bel).float().mean():.3f} inf {torch.isinf(bp_bel).float().mean():.3f}")
+
+
 def early_stop(Z, B, iters, snr_db, seed, tag):
     """early_stopping=True: batch-global stop rule (traditional_decoders.py:255-258)."""
     base = load_base_matrix(TABLES[Z])
@@ -297,6 +324,7 @@ JOBS = {
     # headline code, BG2 Z=32, 10 iterations
     "classic_z32": lambda: classic(32, 16, 10, -2.0, 1234, 0.75, "z32_b16_it10"),
     "classic_z32_hi": lambda: classic(32, 8, 10, 0.0, 99, 0.75, "z32_b8_it10_snr0"),
+    "nonfinite_z4": nonfinite,
     "earlystop_z4": lambda: early_stop(4, 8, 20, 1.0, 5, "z4_b8"),
     "gnn_z4": lambda: gnn(4, 4, 1.0, "z4_b4", True),
     "gnn_z32": lambda: gnn(32, 2, -2.0, "z32_b2", True),

@@ -426,6 +426,25 @@ def test_fast_kernel_against_reference_order_kernel_at_scale():
     assert abs(par["frame_errors_exact"] - par["frame_errors_fast"]) <= 2, par
 
 
+def test_non_finite_llrs_against_the_reference_golden():
+    """The reference's own outputs on +-inf / NaN / huge LLRs (tests/golden/nonfinite_z4_b24.npz): the default path
+    (auto -> routed to the exact kernel) reproduces its min-sum beliefs bit for bit, NaN pattern included, and its BP
+    hard bits and inf/NaN classes."""
+    g = load_golden("nonfinite_z4_b24")
+    code = QCCode.nr_2_0(4)
+    it = int(g["iters"])
+    soft, hard = run(MinSumScaledDecoder(code, it, 0.75, early_stopping=False), g["llr"])
+    assert np.array_equal(soft, g["ms_beliefs"], equal_nan=True)
+    assert np.array_equal(hard, unpack(g["ms_bits"], code.N))
+    soft, hard = run(BeliefPropagationDecoder(code, it, early_stopping=False), g["llr"])
+    ref = g["bp_beliefs"]
+    assert np.array_equal(hard, unpack(g["bp_bits"], code.N))
+    for f in (np.isnan, np.isposinf, np.isneginf):
+        assert np.array_equal(f(ref), f(soft))
+    fin = np.isfinite(ref)
+    assert np.all(np.abs(soft[fin] - ref[fin]) <= 2e-4 * np.maximum(np.abs(ref[fin]), 1.0))
+
+
 def test_auto_path_routes_non_finite_llrs_to_the_reference_order_kernel():
     """+-inf channel LLRs (hard-decision inputs) make posterior - own message an inf - inf on the specialised
     kernel; the drop-in class sends such batches to the exact kernel, so `auto` equals `exact` bit for bit (NaN == NaN)

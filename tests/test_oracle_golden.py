@@ -133,3 +133,23 @@ def test_generator_statistics():
     again = np.concatenate([oracle.awgn_llr(None, 100, N, snr_db, 7, 0), oracle.awgn_llr(None, 156, N, snr_db, 7, 100)])
     assert np.array_equal(llr, again)
     assert not np.array_equal(llr, oracle.awgn_llr(None, B, N, snr_db, seed=8))
+
+
+def test_non_finite_llrs_oracle_matches_reference():
+    """+-inf / NaN / huge channel LLRs through the unmodified reference (oracle/make_golden.py:nonfinite): min-sum
+    beliefs bit-identical including the NaN pattern (torch.sign(NaN) = 0, `mag < min_mag` skips NaN, inf - inf = NaN);
+    BP: identical hard bits and inf/NaN classes, finite beliefs within 2e-4."""
+    g = load_golden("nonfinite_z4_b24")
+    code = QCCode.nr_2_0(4)
+    it = int(g["iters"])
+    o = oracle.decode(code.shifts, 4, g["llr"], it, "minsum", 0.75)
+    assert np.isnan(g["ms_beliefs"]).any() and np.isinf(g["ms_beliefs"]).any()
+    assert np.array_equal(o["beliefs"], g["ms_beliefs"], equal_nan=True)
+    assert np.array_equal(o["hard"], unpack(g["ms_bits"], code.N))
+    o = oracle.decode(code.shifts, 4, g["llr"], it, "bp")
+    ref, got = g["bp_beliefs"], o["beliefs"]
+    assert np.array_equal(o["hard"], unpack(g["bp_bits"], code.N))
+    for f in (np.isnan, np.isposinf, np.isneginf):
+        assert np.array_equal(f(ref), f(got))
+    fin = np.isfinite(ref)
+    assert np.all(np.abs(got[fin] - ref[fin]) <= 2e-4 * np.maximum(np.abs(ref[fin]), 1.0))
