@@ -43,40 +43,59 @@ namespace ldpc {
 // The reference's variable update adds the OTHER checks' messages in order, unclipped, so +-inf and
 // NaN messages are routine and "posterior minus own message" would give inf-inf.
 // Per column the kernel therefore keeps F = llr + sum of the FINITE messages (ascending check
-// order) and K = counts of +inf (bits 0-7), -inf (8-15) and NaN (16-23) messages; the sum over
-// the others is rebuilt from (F, K) and the own message with IEEE semantics.
-__device__ __forceinline__ int bp_nonfinite_code(float x) {
-    const unsigned b = f2u(x);
-    const bool nonfin = (b & 0x7fffffffu) >= 0x7f800000u;
-    const int code = (b & 0x007fffffu) ? 0x10000 : ((b >> 31) ? 0x100 : 1);
-    return nonfin ? code : 0;
+// order) and K = count of +inf messages (bits 0-7) | count of -inf messages (bits 8-15); a NaN message
+// counts as both (either way every OTHER edge of the column sees NaN).  The sum over the others is
+// rebuilt from (F - own finite part, K - own code) with IEEE semantics.
+// BP messages are stored VARIABLE-aligned (lane <-> variable row of the circulant), so F, K and the own
+// message meet in the same lane: only the resolved v2c and the new c2v cross lanes (2 rotations per edge).
+struct BpCode {
+    int code;       // contribution to K, 0 for a finite message
+    bool nonfin;
+};
+__device__ __forceinline__ BpCode bp_code(float x) {
+    BpCode c;
+    c.nonfin = !(fabsf(x) < CUDART_INF_F);
+    int k = (int)(f2u(x) >> 31) * 0xff + 1;          // +inf -> 0x001, -inf -> 0x100
+    k = (x != x) ? 0x101 : k;
+    c.code = c.nonfin ? k : 0;
+    return c;
 }
 __device__ __forceinline__ float bp_resolve(float finite_sum, int k) {
-    const int np = k & 0xff, nm = k & 0xff00, nn = k >> 16;
-    const float inf_part = np ? CUDART_INF_F : -CUDART_INF_F;
-    float r = (np | nm) ? inf_part : finite_sum;
-    r = (nn | (np && nm)) ? CUDART_NAN_F : r;
+    float r = (k & 0xff) ? CUDART_INF_F : finite_sum;
+    r = (k & 0xff00) ? __fadd_rn(r, -CUDART_INF_F) : r;          // +inf and -inf present: NaN
     return r;
 }
 
-// Out-of-line on purpose: inlined, the two functions are ~55 instructions per edge and the unrolled
-// iteration grows to 320 KB of SASS, far beyond the instruction cache (measured: 2.3 M cw/s, fetch-bound).
-#ifndef LDPC_BP_NOINLINE
-#define LDPC_BP_NOINLINE 1
-#endif
-// LDPC_BP_REF_FN=1: the exact kernel's once-rounded double evaluation (math_ref.cuh) instead of tanhf/atanhf
+// tanh(v/2) and 2*atanh(p) on the special-function unit, inline (7 instructions each, 2 MUFU):
+//   tanh(v/2)  = 1 - 2e/(1+e),  e = 2^(-|v| log2 e)      -- one rounding in the final FMA, so the result saturates to
+//                exactly 1.0f where the correctly rounded tanh does (e < 2^-26, |v| > 18.02) up to the 2-ulp error of
+//                ex2.approx; v = +-inf gives e = 0 -> 1, NaN propagates;
+//   2 atanh(p) = ln((1+|p|)/(1-|p|)) = lg2(q) ln 2        -- |p| = 1 gives rcp(0) = inf -> inf, NaN propagates.
+// Absolute error of both is ~1e-7 (relative error grows for |v|, |p| << 1, where the message is added to O(1) terms);
+// the previous out-of-line tanhf/atanhf cost ~55 instructions + two calls per edge.
+// LDPC_BP_REF_FN=1: the exact kernel's once-rounded double evaluation (math_ref.cuh), out of line (diagnostics).
 #ifndef LDPC_BP_REF_FN
 #define LDPC_BP_REF_FN 0
 #endif
+__device__ __forceinline__ float mufu_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float mufu_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float mufu_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 #if LDPC_BP_REF_FN
 __device__ __noinline__ float bp_tanh_half(float v) { return tanh_ref(0.5f * v); }
 __device__ __noinline__ float bp_two_atanh(float p) { return 2.0f * atanh_ref(p); }
-#elif LDPC_BP_NOINLINE
-__device__ __noinline__ float bp_tanh_half(float v) { return tanhf(0.5f * v); }
-__device__ __noinline__ float bp_two_atanh(float p) { return 2.0f * atanhf(p); }
 #else
-__device__ __forceinline__ float bp_tanh_half(float v) { return tanhf(0.5f * v); }
-__device__ __forceinline__ float bp_two_atanh(float p) { return 2.0f * atanhf(p); }
+__device__ __forceinline__ float bp_tanh_half(float v) {
+    const float e = mufu_ex2(__fmul_rn(fabsf(v), -1.4426950408889634f));
+    const float r = mufu_rcp(__fadd_rn(1.0f, e));
+    const float t = __fmaf_rn(__fmul_rn(e, r), -2.0f, 1.0f);
+    return u2f(f2u(t) | (f2u(v) & 0x80000000u));
+}
+__device__ __forceinline__ float bp_two_atanh(float p) {
+    const float a = fabsf(p);
+    const float q = __fmul_rn(__fadd_rn(1.0f, a), mufu_rcp(__fsub_rn(1.0f, a)));
+    const float r = __fmul_rn(mufu_lg2(q), 0.6931471805599453f);
+    return u2f(f2u(r) | (f2u(p) & 0x80000000u));
+}
 #endif
 
 // ---- optional: resident messages in Tensor Memory instead of shared memory (LDPC_FAST_TMEM=1) -------
@@ -310,13 +329,15 @@ __global__ void __launch_bounds__(kWarps * 32, 1) decode_fast_kernel(const Decod
                             ov[mi] = q4.x; ov[mi + 1] = q4.y; ov[mi + 2] = q4.z; ov[mi + 3] = q4.w;
 #endif
                         }
-                        const float t = (s == 0) ? Tc[c] : __shfl_sync(kFull, Tc[c], lp[s], Z);
                         if constexpr (kAlgo == LDPC_ALGO_MINSUM) {
+                            const float t = (s == 0) ? Tc[c] : __shfl_sync(kFull, Tc[c], lp[s], Z);
                             v[k] = t - ov[mi];
                         } else {
-                            const int kr = (s == 0) ? Kc[c] : __shfl_sync(kFull, Kc[c], lp[s], Z);
-                            const int own = bp_nonfinite_code(ov[mi]);
-                            v[k] = bp_resolve(t - (own ? 0.0f : ov[mi]), kr - own);
+                            // variable-aligned: F, K and the own message are in this lane; rotate the resolved v2c
+                            const BpCode own = bp_code(ov[mi]);
+                            const float f = own.nonfin ? Tc[c] : __fsub_rn(Tc[c], ov[mi]);
+                            const float vv = bp_resolve(f, Kc[c] - own.code);
+                            v[k] = (s == 0) ? vv : __shfl_sync(kFull, vv, lp[s], Z);
                         }
                     } else {
                         static_assert(BG::kind[e] == 0 || BG::shift[e] == 0, "degree-1 columns are expected unshifted");
@@ -390,7 +411,9 @@ __global__ void __launch_bounds__(kWarps * 32, 1) decode_fast_kernel(const Decod
                     if constexpr (BG::kind[e] == 0) {
                         constexpr int c = BG::slot[e], s = BG::shift[e], mi = BG::msg[e];
                         const float cnew = cn[k];
-                        nv[mi] = cnew;
+                        // min-sum stores the message check-aligned, BP variable-aligned (rotated back first)
+                        const float tback = (s == 0) ? cnew : __shfl_sync(kFull, cnew, lp[Z - s], Z);
+                        nv[mi] = (kAlgo == LDPC_ALGO_MINSUM) ? cnew : tback;
                         if constexpr (mi % 4 == 3 || mi == EC - 1) {
                             constexpr int b = (mi / 4) * 4;
                             const float4 q4 = make_float4(nv[b], b + 1 < EC ? nv[b + 1] : 0.f, b + 2 < EC ? nv[b + 2] : 0.f,
@@ -401,13 +424,13 @@ __global__ void __launch_bounds__(kWarps * 32, 1) decode_fast_kernel(const Decod
                             mq[(mi / 4) * 32] = q4;
 #endif
                         }
-                        const float t = (s == 0) ? cnew : __shfl_sync(kFull, cnew, lp[Z - s], Z);
+                        const float t = tback;
                         if constexpr (kAlgo == LDPC_ALGO_MINSUM) {
                             Tn[c] = __fadd_rn(Tn[c], t);
                         } else {
-                            const int code = bp_nonfinite_code(t);
-                            Tn[c] = __fadd_rn(Tn[c], code ? 0.0f : t);
-                            Kn[c] += code;
+                            const BpCode cd = bp_code(t);
+                            Tn[c] = cd.nonfin ? Tn[c] : __fadd_rn(Tn[c], t);
+                            Kn[c] += cd.code;
                         }
                     } else if constexpr (kMode == 1) {
                         constexpr int x = BG::slot[e];
