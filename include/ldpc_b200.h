@@ -118,6 +118,20 @@ int ldpc_syndrome_check(const ldpc_code_t* code, const void* hard, int hard_dtyp
 int ldpc_encode(const ldpc_code_t* code, const uint8_t* info, int64_t B, const int32_t* plan, int64_t plan_len,
                 const uint32_t* binv, uint8_t* codeword, void* stream);
 
+/* 5G NR rate matching (3GPP TS 38.212 5.4.2.1 bit selection + 5.4.2.2 bit interleaving) and the receiver-side inverse
+ * that produces the punctured / rate-matched LLR layout the decoders consume.  No counterpart in the reference, which
+ * feeds its decoders the full N-long, un-punctured all-zero codeword (trainer.py:86, comparative_evaluation.py:132,
+ * utils/channel.py:205-231); SURVEY.md section 8 f3.  Tables come from utils/rate_match.py (device int32 / fp32):
+ *   sel     [E]    codeword position (0..N-1) carried by transmitted bit t
+ *   inv_ptr [N+1], inv_idx [E]   CSR inverse of sel (transmissions of position n, in circular-buffer order)
+ *   base    [N]    LLR a position starts from: 0 (punctured first 2Z columns, untransmitted tail), the known-zero
+ *                  LLR for filler bits
+ * ldpc_rate_match:   out[b][t] = codeword[b][sel[t]]                       (uint8 0/1)
+ * ldpc_rate_recover: llr_out[b][n] = base[n] + sum_k rx_llr[b][inv_idx[k]]   (soft-combines repetitions)        */
+int ldpc_rate_match(const uint8_t* codeword, const int32_t* sel, int64_t B, int64_t N, int64_t E, uint8_t* out, void* stream);
+int ldpc_rate_recover(const float* rx_llr, const int32_t* inv_ptr, const int32_t* inv_idx, const float* base, int64_t B,
+                      int64_t N, int64_t E, float* llr_out, void* stream);
+
 /* Host-buffer variant (the `e2e` path of bench.py): llr_host / hard_host are HOST pointers
  * (pinned memory recommended).  The call chunks the batch, overlaps H2D, decode and D2H on
  * internal streams and returns when hard_host (and soft_host if given) are complete.     */

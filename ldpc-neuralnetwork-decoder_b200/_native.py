@@ -33,6 +33,8 @@ PROTOTYPES = {
     "ldpc_bp_decode": (_i, [_p, _p, _i64, _i, _i, _i, _p, _p, _i, _p, _p, _p, _i, _p]),
     "ldpc_syndrome_check": (_i, [_p, _p, _i, _i64, _p, _p]),
     "ldpc_encode": (_i, [_p, _p, _i64, _p, _i64, _p, _p, _p]),
+    "ldpc_rate_match": (_i, [_p, _p, _i64, _i64, _i64, _p, _p]),
+    "ldpc_rate_recover": (_i, [_p, _p, _p, _p, _i64, _i64, _i64, _p, _p]),
     "ldpc_decode_host": (_i, [_p, _i, _p, _i64, _i, _f, _i, _p, _p, _i, _i64]),
     "ldpc_decode_host_q": (_i, [_p, _i, _p, _i, _f, _i64, _i, _f, _i, _p, _p, _i, _i64]),
     "ldpc_awgn_llr": (_i, [_p, _i64, _i64, _f, _u64, _u64, _p, _p]),

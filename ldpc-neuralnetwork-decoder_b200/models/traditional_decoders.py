@@ -11,11 +11,13 @@ num_iterations int)` contract, including the reference's batch-global early-stop
 `QCCode` so no dense H is needed, and `decode_with_iterations` (per-codeword early exit).
 
 `path`: "exact" = the reference's operation order (min-sum beliefs bit-identical to the reference);
-"fast" = the kernels specialised for the shipped 5G tables; "auto" (default) = fast for min-sum,
-exact for BP.  "auto"/"fast" min-sum is NOT reference order: hard decisions equal the reference's on
-every fixture and on 2^20 frames at the bench point (bench.py `parity`), soft outputs agree to
-rounding (1e-4 relative on converged frames); batches containing non-finite LLRs are routed to the
-exact kernel automatically.
+"fast" = the kernels specialised for the shipped 5G tables; "auto" (default) = fast where a specialised
+kernel exists, else exact.  "auto"/"fast" is NOT reference operation order: min-sum hard decisions
+equal the reference-order kernel's on every fixture and on 2^20 frames at the bench point (bench.py
+`parity`), soft outputs agree to rounding (1e-4 relative on converged frames); BP hard decisions are
+equal on the same 2^20 frames, the inf/NaN pattern differs in ~1e-8 of the beliefs and finite beliefs
+near saturation (|L| > 12) by up to percent level (tanh-domain products are ill-conditioned there).
+Batches containing non-finite LLRs are routed to the exact kernel automatically.
 
 All arithmetic happens in the CUDA engine (csrc/decode_exact.cuh, csrc/decode_fast.cuh)
 behind the C ABI; these classes only marshal tensors.  CPU tensors are staged through the
@@ -60,7 +62,7 @@ class _FloodingDecoder:
         # +-inf channel LLRs (hard-decision inputs) that is inf - inf = NaN where the reference's sum over the OTHER
         # checks keeps inf (traditional_decoders.py:235-244).  Such batches take the reference-order kernel.
         self._route = self.path
-        if self.path == "auto" and self._ALGO == _native.ALGO_MINSUM and llr_d.numel() and not bool(torch.isfinite(llr_d).all()):
+        if self.path == "auto" and llr_d.numel() and not bool(torch.isfinite(llr_d).all()):
             self._route = "exact"
         return llr_d, dev
 
@@ -107,12 +109,8 @@ class _FloodingDecoder:
         return int(idx[0]) if idx.numel() else None
 
     def _fast_early_allowed(self):
-        """The specialised early-exit kernel may replace the exact validity-mask pass: path "auto" for min-sum,
-        "fast" for either algorithm (the same policy as for fixed iteration counts); never for path "exact"."""
-        route = getattr(self, "_route", self.path)
-        if route == "exact":
-            return False
-        return route == "fast" or self._ALGO == _native.ALGO_MINSUM
+        """The specialised early-exit kernel may replace the exact validity-mask pass unless path is "exact"."""
+        return getattr(self, "_route", self.path) != "exact"
 
     def _decode_full(self, llr, soft=True):
         """Batch-global early stopping of the reference (:102-106 / :255-258): stop after the first iteration T at

@@ -60,7 +60,7 @@ def test_bp_against_reference_and_oracle(name):
     g = load_golden(name)
     Z = int(g["Z"])
     code = QCCode.nr_2_0(Z)
-    dec = BeliefPropagationDecoder(code, int(g["iters"]), early_stopping=False)
+    dec = BeliefPropagationDecoder(code, int(g["iters"]), early_stopping=False, path="exact")
     soft, hard = run(dec, g["llr"])
     ref = g["bp_beliefs"]
     assert np.array_equal(hard, unpack(g["bp_bits"], code.N))
@@ -140,7 +140,7 @@ def test_bp_inf_nan_semantics():
     llr = oracle.awgn_llr(None, 32, code.N, 4.0, seed=5)          # high SNR: |llr| ~ 5..30, saturates
     llr[0, :64] = -llr[0, :64]
     o = oracle.decode(code.shifts, 32, llr, 10, "bp")
-    soft, hard = run(BeliefPropagationDecoder(code, 10, early_stopping=False), llr)
+    soft, hard = run(BeliefPropagationDecoder(code, 10, early_stopping=False, path="exact"), llr)
     assert np.isinf(soft).any()
     assert np.array_equal(soft, o["beliefs"], equal_nan=True) and np.array_equal(hard, o["hard"])
     assert not hard[np.isnan(soft)].any()

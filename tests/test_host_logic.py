@@ -263,3 +263,36 @@ def test_bench_roofline_counts_match_the_kernel_sources():
             assert now == sha, f"{src} changed after the ncu capture behind {rel}: re-run the capture"
         k = bench.kernel_counts(workload)
         assert k["inst_per_cw"] == c["inst_per_cw"] and k["file"] == rel
+
+
+def test_rate_match_tables_hand_computed_case_and_oracle():
+    """TS 38.212 5.4.2 on BG2 Z=2 (N = 104, d has 100 bits, K = 20): payload 16 bits -> fillers c[16..19] = d[12..15].
+    rv 0, E = 10, Qm = 2: e = d[0..9] and f = [e0 e5 e1 e6 e2 e7 e3 e8 e4 e9]; full-codeword index = d index + 2Z."""
+    from ldpc_b200.utils import rate_match_tables
+    from oracle import oracle
+    code = QCCode.nr_2_0(2)
+    sel, kind = rate_match_tables(code, 10, payload_bits=16, rv=0, Qm=2)
+    assert sel.tolist() == [4 + x for x in (0, 5, 1, 6, 2, 7, 3, 8, 4, 9)]
+    assert kind[:4].tolist() == [1] * 4 and kind[16:20].tolist() == [2] * 4 and int((kind == 0).sum()) == 104 - 8
+    # E = 20 crosses the filler block: d[12..15] are skipped
+    sel, _ = rate_match_tables(code, 20, payload_bits=16, rv=0, Qm=1)
+    assert sel.tolist() == [4 + x for x in list(range(12)) + list(range(16, 24))]
+    # rv 2: k0 = floor(25 * 100 / 100) * 2 = 50; wrap-around with repetition when E exceeds the 96 usable bits
+    sel, _ = rate_match_tables(code, 100, payload_bits=16, rv=2, Qm=1)
+    usable = [x for x in range(100) if not 12 <= x < 16]
+    start = usable.index(50)
+    want = [usable[(start + t) % 96] + 4 for t in range(100)]
+    assert sel.tolist() == want and sel[96] == sel[0]
+    # against the specification's loops (oracle), bit by bit, over rv / Qm / limited buffers / both lifting sizes
+    rng = np.random.default_rng(0)
+    for Z, Kp, E, rv, Qm, Ncb in ((2, 16, 10, 0, 2, None), (2, 20, 96, 1, 4, None), (2, 13, 300, 3, 6, 80), (4, 33, 128, 2, 8, None),
+                                  (32, 300, 2048, 0, 2, None), (32, 320, 1600, 3, 1, 1200)):
+        c = QCCode.nr_2_0(Z)
+        sel, kind = rate_match_tables(c, E, payload_bits=Kp, rv=rv, Qm=Qm, Ncb=Ncb)
+        cw = rng.integers(0, 2, c.N).astype(np.uint8)
+        assert np.array_equal(cw[sel], oracle.rate_match_38212(Z, c.cols, c.K, Kp, cw, E, rv, Qm, Ncb))
+        assert not (kind[sel] != 0).any()                 # punctured and filler positions are never transmitted
+    with pytest.raises(ValueError):
+        rate_match_tables(code, 11, payload_bits=16, Qm=2)
+    with pytest.raises(ValueError):
+        rate_match_tables(code, 10, payload_bits=3)
