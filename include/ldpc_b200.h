@@ -232,6 +232,14 @@ int ldpc_neural_decode(const float* llr_e, const uint16_t* cidx, int Kc, const u
                        const uint16_t* vidx, int Kv, const uint8_t* vcnt, const uint16_t* vperm, const float* w_ch,
                        const float* w_res, int L, int iters, int64_t B, int64_t E, const float* gt_e, float* soft,
                        float* max_loss, void* stream);
+/* The same decoder on the quasi-cyclic structure of the code (csrc/neural_qc.cuh): no index tables -- the neighbour
+ * lists of create_LLR_mapping (utils/ldpc_utils.py:62-95) are implied by the base graph, check neighbours are lane
+ * rotations, variable neighbours are lane-local, the edge state lives in Tensor Memory.  Compiled for the 5G BG2 Z=32
+ * table (LDPC_ERR_UNSUPPORTED otherwise) and residual depth L <= 2.  llr_e / gt_e / soft: [B, E] in the variable-major
+ * edge order of create_LLR_mapping(H.T); bit-identical to ldpc_neural_decode with that code's tables.  save_x: NULL, or
+ * [iters, B, E] receiving the input of every CheckLayer (what ldpc_neural_backward_qc needs).                     */
+int ldpc_neural_decode_qc(const ldpc_code_t* code, const float* llr_e, const float* w_ch, const float* w_res, int L, int iters,
+                          int64_t B, const float* gt_e, float* soft, float* max_loss, float* save_x, void* stream);
 /* OutputLayer.forward, layers.py:180-210: soft = sigmoid(final+llr); if gt: per-row max of
  * BCE(soft, gt) -> max_loss [B], argmax [B] int32 (for the backward).                    */
 int ldpc_output_layer_fwd(const float* final_llr, const float* llr, const float* gt, int64_t B, int64_t E,

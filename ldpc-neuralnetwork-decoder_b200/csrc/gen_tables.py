@@ -60,6 +60,33 @@ def emit(name, rows, cols, cells, Z):
         row_ptr.append(len(col))
     E = len(col)
     maxdc = max(row_ptr[i + 1] - row_ptr[i] for i in range(rows))
+    # variable-major views (the edge numbering of create_LLR_mapping, utils/ldpc_utils.py:62-95: edges of variable
+    # j*Z+r are consecutive, in ascending check = ascending base row): vm[e] = D_j + k with D_j = edges of the columns
+    # before j and k = rank of e's row within column j; cm[e] = the same restricted to core columns (-1 for degree-1)
+    col_vm0, acc = [], 0
+    for j in range(cols):
+        col_vm0.append(acc)
+        acc += coldeg[j]
+    core_cm0, acc = [], 0
+    for j in core_cols:
+        core_cm0.append(acc)
+        acc += coldeg[j]
+    seen = [0] * cols
+    vm, cm, vrank = [], [], []
+    core_edge = [0] * ncore_e
+    ext_edge = [0] * len(ext_cols)
+    for e in range(E):
+        j = col[e]
+        k = seen[j]
+        seen[j] += 1
+        vm.append(col_vm0[j] + k)
+        vrank.append(k)
+        if coldeg[j] > 1:
+            cm.append(core_cm0[core_of[j]] + k)
+            core_edge[core_cm0[core_of[j]] + k] = e
+        else:
+            cm.append(-1)
+            ext_edge[ext_of[j]] = e
 
     def arr(ctype, nm, vals):
         return f"    static constexpr {ctype} {nm}[{len(vals)}] = {{{', '.join(str(v) for v in vals)}}};"
@@ -77,6 +104,14 @@ def emit(name, rows, cols, cells, Z):
            arr("short", "col_slot", [core_of[j] if coldeg[j] > 1 else ext_of[j] for j in range(cols)]),
            arr("short", "core_col", core_cols),
            arr("short", "ext_col", ext_cols),
+           arr("short", "col_deg", coldeg),
+           arr("short", "col_vm0", col_vm0) + "   // variable-major edge offset of a column (in base edges)",
+           arr("short", "vm", vm) + "   // variable-major base-edge index of edge e: col_vm0[col] + rank of its row in the column",
+           arr("short", "vrank", vrank),
+           arr("short", "cm", cm) + "   // the same among core columns only (-1 for degree-1 columns)",
+           arr("short", "core_cm0", core_cm0 + [ncore_e]),
+           arr("short", "core_edge", core_edge) + "   // row-major edge index of core-column-major position",
+           arr("short", "ext_edge", ext_edge) + "   // row-major edge index of the edge of degree-1 column x",
            "};", ""]
     return "\n".join(out)
 

@@ -8,6 +8,7 @@
 #include "channel_kernels.cuh"
 #include "layers.cuh"
 #include "neural.cuh"
+#include "neural_qc.cuh"
 #include "gnn.cuh"
 #include "gnn_bwd.cuh"
 #include <cuda_fp16.h>
@@ -624,6 +625,21 @@ int ldpc_neural_decode(const float* llr_e, const uint16_t* cidx, int Kc, const u
     if (2 * per_row <= cap && B >= 2 * kNumSMs) return launch_neural<2>(a, 2 * per_row, st);
     if (per_row <= cap) return launch_neural<1>(a, per_row, st);
     return fail(LDPC_ERR_UNSUPPORTED, "neural_decode: %zu bytes of resident state per codeword exceed shared memory", per_row);
+}
+
+int ldpc_neural_decode_qc(const ldpc_code_t* code, const float* llr_e, const float* w_ch, const float* w_res, int L, int iters,
+                          int64_t B, const float* gt_e, float* soft, float* max_loss, float* save_x, void* stream) {
+    if (!code || !llr_e || !w_ch || !soft || (L > 0 && !w_res)) return fail(LDPC_ERR_INVALID, "neural_decode_qc: null argument");
+    if (gt_e && !max_loss) return fail(LDPC_ERR_INVALID, "neural_decode_qc: ground truth given without max_loss buffer");
+    if (L < 0 || L > 2) return fail(LDPC_ERR_UNSUPPORTED, "neural_decode_qc: residual depth %d outside 0..2 (two ring slots in Tensor Memory)", L);
+    if (iters < 1 || B < 0) return fail(LDPC_ERR_INVALID, "neural_decode_qc: bad shape");
+    if (B == 0) return LDPC_OK;
+    DeviceGuard g(code->device);
+    if (!g.ok) return fail(LDPC_ERR_CUDA, "neural_decode_qc: cannot select device %d", code->device);
+    NeuralQcParams p{};
+    p.llr = llr_e; p.w_ch = w_ch; p.w_res = w_res; p.L = L; p.iters = iters; p.B = B; p.gt = gt_e; p.soft = soft;
+    p.max_loss = max_loss; p.save_x = save_x;
+    return launch_neural_qc(code, p, (cudaStream_t)stream);
 }
 
 int ldpc_output_layer_fwd(const float* final_llr, const float* llr, const float* gt, int64_t B, int64_t E, float* soft,

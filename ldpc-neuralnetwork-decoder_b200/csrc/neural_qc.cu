@@ -1,0 +1,22 @@
+// neural_qc.cu -- translation unit of the QC-structured LDPCNeuralDecoder kernels (neural_qc.cuh) and their launcher;
+// separate from ldpc_b200.cu so that the fully unrolled bodies compile in parallel with the rest.
+#include "neural_qc.cuh"
+#include "tables.cuh"
+
+namespace ldpc {
+
+int launch_neural_qc(const ldpc_code_t* c, const NeuralQcParams& p, cudaStream_t st) {
+    if (c->fast_kind != 1)
+        return fail(LDPC_ERR_UNSUPPORTED, "neural_decode_qc: the QC-structured kernel is compiled for the 5G BG2 Z=32 table only");
+    auto kern = neural_qc_kernel<BG2Z32>;
+    constexpr size_t smem = neural_qc_smem_bytes<BG2Z32>();
+    static_assert(smem <= (size_t)kMaxSmemPerBlock, "neural_qc shared memory");
+    LDPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long long blocks = (p.B + kNqWarps - 1) / kNqWarps;
+    if (blocks > kNumSMs) blocks = kNumSMs;
+    kern<<<(int)blocks, kNqWarps * 32, smem, st>>>(p);
+    LDPC_CHECK_LAUNCH("neural_qc_kernel");
+    return LDPC_OK;
+}
+
+}  // namespace ldpc

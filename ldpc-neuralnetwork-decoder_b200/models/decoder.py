@@ -96,8 +96,35 @@ class _NeuralVariableFn(torch.autograd.Function):
         return (g * w_ch.unsqueeze(0), g_c2v, None, (g * llr).sum(dim=0), g_wres, *g_prev)
 
 
+# ---- QC-structured path (csrc/neural_qc.cuh) -------------------------------------------------------------------------
+# The kernel implies the neighbour tables from the base graph, so it may only run when the caller's tables ARE the ones
+# create_LLR_mapping produces for that code.  Checked once per (tensor, version); canonical tables built once per device.
+_QC_CANON = {}      # device index -> (QCCode, check table, var table)
+_QC_SEEN = {}       # (data_ptr, version, shape, data_ptr, version, shape) -> bool
+
+
+def _qc_code_for(check_index_tensor, var_index_tensor, num_nodes):
+    from ..utils.ldpc_utils import QCCode, create_LLR_mapping
+    if num_nodes != 197 * 32 or tuple(check_index_tensor.shape) != (num_nodes, 9) or tuple(var_index_tensor.shape) != (num_nodes, 22):
+        return None
+    dev = check_index_tensor.device
+    canon = _QC_CANON.get(dev.index)
+    if canon is None:
+        code = QCCode.nr_2_0(32)
+        _, c, v, _ = create_LLR_mapping(code.dense().T)
+        canon = _QC_CANON[dev.index] = (code, c.to(dev), v.to(dev))
+    key = (check_index_tensor.data_ptr(), check_index_tensor._version, var_index_tensor.data_ptr(), var_index_tensor._version)
+    ok = _QC_SEEN.get(key)
+    if ok is None:
+        ok = bool(torch.equal(check_index_tensor.to(torch.int64), canon[1]) and torch.equal(var_index_tensor.to(torch.int64), canon[2]))
+        if len(_QC_SEEN) > 64:
+            _QC_SEEN.clear()
+        _QC_SEEN[key] = ok
+    return canon[0] if ok else None
+
+
 class LDPCNeuralDecoder(nn.Module):
-    def __init__(self, num_nodes, num_iterations=5, depth_L=2, output_index_tensor=None, fused=True):
+    def __init__(self, num_nodes, num_iterations=5, depth_L=2, output_index_tensor=None, fused=True, qc=True):
         super().__init__()
         if num_iterations < 1:
             raise ValueError("num_iterations must be >= 1")
@@ -105,6 +132,7 @@ class LDPCNeuralDecoder(nn.Module):
         self.num_iterations = int(num_iterations)
         self.depth_L = int(depth_L)
         self.fused = bool(fused)
+        self.qc = bool(qc)          # allow the QC-structured kernels when the index tensors are the 5G BG2 Z=32 tables
         self.check_layer = CheckLayer()
         self.variable_layer = VariableLayer()
         self.residual_layer = ResidualLayer(self.num_nodes, self.depth_L)   # owns w_ch (E,), w_res (L,)
@@ -162,6 +190,20 @@ class LDPCNeuralDecoder(nn.Module):
         B, E = llr_c.shape
         if check_index_tensor.shape[0] != E or var_index_tensor.shape[0] != E:
             raise ValueError("index tensors must have one row per edge")
+        code = _qc_code_for(check_index_tensor, var_index_tensor, E) if (self.qc and self.depth_L <= 2) else None
+        if code is not None:
+            # the tables are create_LLR_mapping's for 5G BG2 Z=32: neighbours come from the base graph (no index loads)
+            w_ch = res.w_ch.detach().to(torch.float32).contiguous()
+            w_res = res.w_res.detach().to(torch.float32).contiguous()
+            y = gt_e.detach().to(torch.float32).contiguous() if gt_e is not None else None
+            soft = torch.empty_like(llr_c)
+            ml = torch.empty(B, dtype=torch.float32, device=llr_c.device) if y is not None else None
+            with torch.cuda.device(llr_c.device):
+                _native.check(_native.lib().ldpc_neural_decode_qc(
+                    code.handle(llr_c.device), _native.ptr(llr_c), _native.ptr(w_ch), _native.ptr(w_res), self.depth_L,
+                    self.num_iterations, B, _native.ptr(y), _native.ptr(soft), _native.ptr(ml), None,
+                    _native.stream_ptr(llr_c.device)))
+            return soft, ml
         cp, cperm, ccnt = packed_index(check_index_tensor).sorted()
         vp, vperm, vcnt = packed_index(var_index_tensor).sorted()
         w_ch = res.w_ch.detach().to(torch.float32).contiguous()

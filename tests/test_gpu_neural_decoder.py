@@ -214,3 +214,47 @@ def test_unit_channel_weights_without_residuals_equal_classic_min_sum():
     sure = beliefs.abs() < 10
     np.testing.assert_allclose(torch.logit(soft[sure].double()).cpu().numpy(), beliefs[sure].double().cpu().numpy(),
                                rtol=2e-3, atol=2e-3)
+
+
+@pytest.mark.parametrize("depth_L,iters", [(2, 5), (1, 3), (0, 2), (2, 1), (2, 8)])
+def test_qc_structured_kernel_is_bit_identical_to_the_table_driven_kernels(depth_L, iters):
+    """csrc/neural_qc.cuh (neighbours implied by the base graph, state in Tensor Memory, no index tables) against the
+    table-driven one-kernel decoder and the per-layer chain on BG2 Z=32: same bits for every soft output and per-frame
+    max loss; per-edge LLRs that differ between the edges of one variable, zeros, a ragged batch."""
+    code = QCCode.nr_2_0(32)
+    _, cidx, vidx, oidx = create_LLR_mapping(code.dense().T)
+    cidx, vidx = cidx.to(DEV), vidx.to(DEV)
+    rng = np.random.default_rng(100 * depth_L + iters)
+    B = 4 * 148 + 7                                                  # more codewords than warps in the grid, ragged tail
+    llr_e = (rng.normal(size=(B, code.E)) * 0.8 + 0.4).astype(np.float32)      # edge space: independent value per edge
+    llr_e[3, ::7] = 0.0
+    llr_e[4, 5:900:3] = -1e-10
+    llr_e[5] = np.abs(llr_e[5]) * 30.0
+    w_ch = (rng.random(code.E) * 0.5 + 0.75).astype(np.float32)
+    w_res = np.array([0.2, -0.1, 0.05][:max(depth_L, 1)], np.float32)
+    gt_e = (rng.random((B, code.E)) < 0.5).astype(np.float32)
+
+    def make(qc, fused=True):
+        d = LDPCNeuralDecoder(code.E, iters, depth_L, fused=fused, qc=qc).to(DEV)
+        with torch.no_grad():
+            d.residual_layer.w_ch.copy_(torch.from_numpy(w_ch))
+            d.residual_layer.w_res.copy_(torch.from_numpy(w_res[:depth_L]))
+        return d
+    x, y = torch.from_numpy(llr_e).to(DEV), torch.from_numpy(gt_e).to(DEV)
+    with torch.no_grad():
+        launches0 = ldpc_b200._native.lib().ldpc_launch_count()
+        s_qc, m_qc = make(True)(x, cidx, vidx, y)
+        assert ldpc_b200._native.lib().ldpc_launch_count() == launches0 + 1          # ONE kernel, no table packing
+        s_tb, m_tb = make(False)(x, cidx, vidx, y)
+        s_n, _ = make(True)(x, cidx, vidx)                                            # without ground truth
+    assert torch.equal(s_qc, s_tb) and torch.equal(m_qc, m_tb) and torch.equal(s_n, s_qc)
+    chain = make(False, fused=False)
+    s_ch, m_ch = chain(x[:64], cidx, vidx, y[:64])                                  # literal four-layer composition
+    assert torch.equal(s_ch.detach(), s_qc[:64]) and torch.equal(m_ch.detach(), m_qc[:64])
+    # tables that are NOT the code's (one entry changed) must not take the QC path
+    other = cidx.clone()
+    other[0, 0] = other[0, 1]
+    with torch.no_grad():
+        s_o, _ = make(True)(x[:8], other, vidx)
+        s_t, _ = make(False)(x[:8], other, vidx)
+    assert torch.equal(s_o, s_t)

@@ -49,8 +49,10 @@ def main():
     llr_e = llr[:, oidx[0].to(dev)].contiguous()
     gt = torch.ones_like(llr_e)
     out = {"batch": args.batch, "iters": args.iters, "Z": args.z, "E": code.E, "lib": args.lib}
-    for fused in (True, False):
-        dec = LDPCNeuralDecoder(code.E, args.iters, 2, fused=fused).to(dev)
+    for tag, fused, qc in (("qc", True, True), ("fused", True, False), ("composed", False, False)):
+        if tag == "qc" and args.z != 32:
+            continue
+        dec = LDPCNeuralDecoder(code.E, args.iters, 2, fused=fused, qc=qc).to(dev)
 
         def infer():
             with torch.no_grad():
@@ -62,7 +64,6 @@ def main():
             ml.mean().backward()
 
         ms_i, ms_t = timed(infer, args.reps), timed(train, args.reps)
-        tag = "fused" if fused else "composed"
         out[tag] = {"infer_ms": ms_i, "infer_cw_per_s": args.batch / ms_i * 1e3,
                     "train_ms": ms_t, "train_cw_per_s": args.batch / ms_t * 1e3}
     print(json.dumps(out))
