@@ -129,7 +129,123 @@ def main():
     old = open(DST).read() if os.path.exists(DST) else None
     if new != old:
         open(DST, "w").write(new)
+    emit_nq(rows, cols, cells, 32, os.path.join(HERE, "nq_tables.h"))
     return DST
+
+
+
+
+# ---- schedule tables of the rolled QC neural-decoder kernels (csrc/neural_qc_kernel.cuh) ----------------------------------
+NQ_MEMBERS = 4                                     # warps that share one codeword (same TMEM lane quarter)
+NQ_ROW_CLASSES = [(2, 1), (3, 1), (4, 1), (5, 1), (8, 0), (10, 0)]      # (core edges, degree-1 edges) of a base row
+NQ_COL_CLASSES = [6, 8, 10, 13, 16, 23]            # unrolled body sizes for the ordered sums over a base column
+
+
+def emit_nq(rows, cols, cells, Z, dst):
+    cells = sorted((i, j, s % Z) for i, j, s in cells)
+    coldeg = [0] * cols
+    for _, j, _ in cells:
+        coldeg[j] += 1
+    core_cols = [j for j in range(cols) if coldeg[j] > 1]
+    ext_cols = [j for j in range(cols) if coldeg[j] == 1]
+    assert core_cols == list(range(len(core_cols))), "core columns are expected first"
+    vm0, acc = [], 0
+    for j in range(cols):
+        vm0.append(acc)
+        acc += coldeg[j]
+    seen = [0] * cols
+    row_meta, row_ext, row_class = [], [], []
+    for i in range(rows):
+        meta, ext = [], 255
+        for (ii, j, s) in cells:
+            if ii != i:
+                continue
+            k = seen[j]
+            seen[j] += 1
+            if coldeg[j] > 1:
+                meta.append((vm0[j] + k) | (s << 8))
+            else:
+                assert s == 0 and ext == 255
+                ext = ext_cols.index(j)
+        row_class.append(NQ_ROW_CLASSES.index((len(meta), 0 if ext == 255 else 1)))
+        row_meta.append(meta + [0] * (10 - len(meta)))
+        row_ext.append(ext)
+
+    def balance(items, cost, classes_of):
+        """LPT: heaviest first to the lightest member; returns per member the items ordered by class."""
+        load = [0.0] * NQ_MEMBERS
+        got = [[] for _ in range(NQ_MEMBERS)]
+        for it in sorted(items, key=lambda x: -cost(x)):
+            m = min(range(NQ_MEMBERS), key=lambda q: load[q])
+            load[m] += cost(it)
+            got[m].append(it)
+        return [sorted(g, key=lambda x: (classes_of(x), x)) for g in got], load
+
+    row_cost = lambda i: 31 * NQ_ROW_CLASSES[row_class[i]][0] + 14 * NQ_ROW_CLASSES[row_class[i]][1] + 15
+    srows, rload = balance(list(range(rows)), row_cost, lambda i: row_class[i])
+    col_class = [min(c for c in range(len(NQ_COL_CLASSES)) if NQ_COL_CLASSES[c] >= coldeg[j]) for j in core_cols]
+    col_cost = lambda j: NQ_COL_CLASSES[col_class[j]] * (NQ_COL_CLASSES[col_class[j]] - 1) / 2 + 17 * NQ_COL_CLASSES[col_class[j]] + 10
+    scols, cload = balance(core_cols, col_cost, lambda j: col_class[j])
+    # degree-1 cells of phase B go to the members with the lightest column load
+    sext = [[] for _ in range(NQ_MEMBERS)]
+    load = list(cload)
+    for x in range(len(ext_cols)):
+        m = min(range(NQ_MEMBERS), key=lambda q: load[q])
+        load[m] += 12
+        sext[m].append(x)
+    chunk = []
+    for m in range(vm0[-1] + coldeg[-1]):
+        j = max(jj for jj in range(cols) if vm0[jj] <= m)
+        d = coldeg[j]
+        inv = 65536 // d + 1
+        for off in range(32 * d):
+            assert (off * inv) >> 16 == off // d
+        chunk.append((vm0[j], d, inv))
+
+    def arr(ctype, nm, vals, dims):
+        flat = ", ".join(str(v) for v in vals)
+        return f"__constant__ {ctype} {nm}{dims} = {{{flat}}};"
+
+    def pad(lists, n):
+        return [v for l in lists for v in (l + [0] * (n - len(l)))]
+
+    def prefix(lists, class_of, ncls):
+        out = []
+        for l in lists:
+            cnt = [sum(1 for x in l if class_of(x) == c) for c in range(ncls)]
+            p = [0]
+            for c in cnt:
+                p.append(p[-1] + c)
+            out += p
+        return out
+    nr = max(len(l) for l in srows)
+    ncm = max(len(l) for l in scols)
+    nxm = max(len(l) for l in sext)
+    text = ["// GENERATED by csrc/gen_tables.py (emit_nq) from codes/bg2_ils0_mod32.triples -- do not edit.",
+            "// Work schedule of the rolled QC neural-decoder kernels: 4 warps (\"members\") share one codeword; every base row /",
+            "// base column is owned by one member; rows are grouped by (core edges, degree-1 edges), columns by body size.",
+            f"// member loads (model instructions): rows {[int(x) for x in rload]}, columns + degree-1 cells {[int(x) for x in load]}",
+            "#pragma once", "", "namespace ldpc {", "namespace nq {", "",
+            f"constexpr int kMembers = {NQ_MEMBERS}, kRowClasses = {len(NQ_ROW_CLASSES)}, kColClasses = {len(NQ_COL_CLASSES)};",
+            f"constexpr int kRowsMax = {nr}, kColsMax = {ncm}, kExtMax = {nxm}, kCells = {len(chunk)};",
+            arr("unsigned short", "row_meta", pad(row_meta, 10), f"[{rows}][10]") + "   // per core edge of a row: cell | shift << 8",
+            arr("unsigned char", "row_ext", row_ext, f"[{rows}]") + "   // degree-1 slot of the row's last edge, 255 = none",
+            arr("unsigned char", "sched_rows", pad(srows, nr), f"[{NQ_MEMBERS}][{nr}]"),
+            arr("unsigned char", "sched_row_ptr", prefix(srows, lambda i: row_class[i], len(NQ_ROW_CLASSES)), f"[{NQ_MEMBERS}][{len(NQ_ROW_CLASSES) + 1}]"),
+            arr("unsigned char", "col_b0", [vm0[j] for j in core_cols], f"[{len(core_cols)}]"),
+            arr("unsigned char", "col_d", [coldeg[j] for j in core_cols], f"[{len(core_cols)}]"),
+            arr("unsigned char", "sched_cols", pad(scols, ncm), f"[{NQ_MEMBERS}][{ncm}]"),
+            arr("unsigned char", "sched_col_ptr", prefix(scols, lambda j: col_class[j], len(NQ_COL_CLASSES)), f"[{NQ_MEMBERS}][{len(NQ_COL_CLASSES) + 1}]"),
+            arr("unsigned char", "sched_ext", pad(sext, nxm), f"[{NQ_MEMBERS}][{nxm}]"),
+            arr("unsigned char", "sched_ext_cnt", [len(l) for l in sext], f"[{NQ_MEMBERS}]"),
+            arr("unsigned int", "chunk_meta", [D | (d << 8) | (inv << 13) for D, d, inv in chunk], f"[{len(chunk)}]") +
+            "   // per 32-edge chunk of a row: first cell of its column | degree << 8 | (65536 / degree + 1) << 13",
+            "", "}  // namespace nq", "}  // namespace ldpc", ""]
+    new = "\n".join(text)
+    old = open(dst).read() if os.path.exists(dst) else None
+    if new != old:
+        open(dst, "w").write(new)
+    return rload, load
 
 
 if __name__ == "__main__":

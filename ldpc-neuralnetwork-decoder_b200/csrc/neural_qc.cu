@@ -1,6 +1,6 @@
 // neural_qc.cu -- translation unit of the QC-structured LDPCNeuralDecoder kernels (neural_qc.cuh) and their launcher;
 // separate from ldpc_b200.cu so that the fully unrolled bodies compile in parallel with the rest.
-#include "neural_qc.cuh"
+#include "neural_qc_kernel.cuh"
 #include "tables.cuh"
 
 namespace ldpc {
@@ -12,9 +12,9 @@ int launch_neural_qc(const ldpc_code_t* c, const NeuralQcParams& p, cudaStream_t
     constexpr size_t smem = neural_qc_smem_bytes<BG2Z32>();
     static_assert(smem <= (size_t)kMaxSmemPerBlock, "neural_qc shared memory");
     LDPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    long long blocks = (p.B + kNqWarps - 1) / kNqWarps;
+    long long blocks = (p.B + kNqGroups - 1) / kNqGroups;
     if (blocks > kNumSMs) blocks = kNumSMs;
-    kern<<<(int)blocks, kNqWarps * 32, smem, st>>>(p);
+    kern<<<(int)blocks, kNqThreads, smem, st>>>(p);
     LDPC_CHECK_LAUNCH("neural_qc_kernel");
     return LDPC_OK;
 }
