@@ -32,8 +32,8 @@ constexpr int kNqColMin[nq::kColClasses] = {5, 7, 9, 12, 14, 22};   // smallest 
 template <class BG>
 constexpr int nq_group_floats() { return BG::kEdges * kNqPitch + 3 * BG::kExtCols * 32 + 8; }
 template <class BG>
-constexpr size_t neural_qc_smem_bytes() {
-    return sizeof(float) * ((size_t)BG::kEdges * 32 + (size_t)kNqGroups * nq_group_floats<BG>());
+constexpr size_t neural_qc_smem_bytes() {      // w_ch tile | per-codeword state | tile addresses of the row chunks (uint16)
+    return sizeof(float) * ((size_t)BG::kEdges * 32 + (size_t)kNqGroups * nq_group_floats<BG>()) + sizeof(unsigned short) * BG::kEdges * 32;
 }
 
 __device__ __forceinline__ void nq_ld1_issue(uint32_t taddr, float& a) {
@@ -63,13 +63,18 @@ __global__ void __launch_bounds__(kNqThreads, 1) neural_qc_kernel(const NeuralQc
     constexpr int E = EB * 32;
     static_assert(EB == nq::kCells && 3 * ECP <= 512, "schedule tables / TMEM budget");
     extern __shared__ float nq_smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // the warp index is broadcast from lane 0 so that the compiler KNOWS it is warp-uniform: schedule-table indices,
+    // TMEM addresses and loop bounds then live in uniform registers (the first build spent 5.5 k R2UR per codeword
+    // moving per-access TMEM addresses into them)
+    const int lane = threadIdx.x & 31, warp = __shfl_sync(kFull, (int)(threadIdx.x >> 5), 0);
     const int grp = warp & (kNqGroups - 1), mem = warp / kNqGroups;       // TMEM lane quarter = codeword slot; member in it
     float* wsm = nq_smem;                                                  // [EB][32]  w_ch per (cell, lane)
     float* lls = nq_smem + EB * 32 + grp * nq_group_floats<BG>();         // [EB][33]  llr_e, later the soft outputs
     float* xe0 = lls + EB * kNqPitch;                                      // [2][NX][32] ring of the degree-1 cells
     float* ces = xe0 + 2 * NX * 32;                                        // [NX][32]  their last check message
     float* red = ces + NX * 32;                                            // [4] per-member loss maxima
+    // where element `lane` of the m-th 32-edge chunk of a row sits in the tile: (D + k) * 33 + r (the same for every codeword)
+    unsigned short* tile_addr = reinterpret_cast<unsigned short*>(nq_smem + EB * 32 + kNqGroups * nq_group_floats<BG>());
 
     __shared__ uint32_t tmem_base_s;
     if (warp == 0) {
@@ -82,11 +87,13 @@ __global__ void __launch_bounds__(kNqThreads, 1) neural_qc_kernel(const NeuralQc
         const unsigned cmeta = nq::chunk_meta[m];
         const int D = cmeta & 0xff, d = (cmeta >> 8) & 0x1f;
         wsm[m * 32 + lane] = __ldg(p.w_ch + 32 * D + lane * d + (m - D));
+        const int inv = cmeta >> 13, off = 32 * (m - D) + lane, r = (off * inv) >> 16, k = off - r * d;
+        tile_addr[m * 32 + lane] = (unsigned short)((D + k) * kNqPitch + r);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tbase = tmem_base_s + (((uint32_t)grp * 32u) << 16);
+    const uint32_t tbase = __shfl_sync(kFull, tmem_base_s, 0) + (((uint32_t)grp * 32u) << 16);
     const uint32_t tC = tbase;                          // c2v
     uint32_t tXc = tbase + ECP, tXo = tbase + 2 * ECP;  // ring: current x, older x (roles swap every iteration)
     int xc_off = 0, xo_off = NX * 32;                   // the same for the degree-1 ring in shared memory
@@ -99,14 +106,8 @@ __global__ void __launch_bounds__(kNqThreads, 1) neural_qc_kernel(const NeuralQc
         // ---- load llr_e[cw]: coalesced 128-byte chunks -> [cell][lane] tile ----
         {
             const float* src = p.llr + cw * E + lane;
-#pragma unroll 4
-            for (int m = mem; m < EB; m += nq::kMembers) {
-                const unsigned cmeta = nq::chunk_meta[m];
-                const int D = cmeta & 0xff, d = (cmeta >> 8) & 0x1f, inv = cmeta >> 13;
-                const float v = __ldg(src + 32 * m);
-                const int off = 32 * (m - D) + lane, r = (off * inv) >> 16, k = off - r * d;
-                lls[(D + k) * kNqPitch + r] = v;
-            }
+#pragma unroll 8
+            for (int m = mem; m < EB; m += nq::kMembers) lls[tile_addr[m * 32 + lane]] = __ldg(src + 32 * m);
         }
         nq_group_sync(grp);
         // x_0 = llr_e in the current ring slot, zeros in the older one (its residual weight is zero until it is written)
@@ -163,13 +164,17 @@ __global__ void __launch_bounds__(kNqThreads, 1) neural_qc_kernel(const NeuralQc
             });
             // fewer than 9 other edges: the table's padded slots are zero inputs, magnitude 1e10 (layers.py:48-57)
             const float m1c = (d - 1 < 9) ? fminf(m1, 1e10f) : m1, m2c = (d - 1 < 9) ? fminf(m2, 1e10f) : m2;
+            // a zero FACTOR needs v = -1e-10f exactly (or NaN): practically never.  Without one the sign product is +-1 and
+            // the message is the minimum with the sign bits xor-ed in (what the multiplication by +-1.0f yields); the
+            // general form runs only when some lane of the warp saw a zero factor or a non-finite minimum.
+            const bool special = __any_sync(kFull, zc != 0 || !(m2c < CUDART_INF_F));
             static_for<0, d>([&](auto kc) {
                 constexpr int k = decltype(kc)::value;
                 if (k < NC || last) {
                     const float m = (a[k] == m1) ? m2c : m1c;                       // minimum over the OTHER edges
                     const unsigned sgn = (nb ^ sb[k]) & 0x80000000u;               // their sign product
-                    const float sp = u2f(sgn | ((zc - zi[k]) > 0 ? 0u : 0x3f800000u));
-                    const float o = __fmul_rn(sp, m);
+                    float o = u2f(sgn | f2u(m));
+                    if (special) o = __fmul_rn(u2f(sgn | ((zc - zi[k]) > 0 ? 0u : 0x3f800000u)), m);
                     if constexpr (k < NC) nq_st1(tC + cell[k], __shfl_sync(kFull, o, lane - sft[k]));
                     else ces[xs * 32 + lane] = o;
                 }
@@ -191,14 +196,20 @@ __global__ void __launch_bounds__(kNqThreads, 1) neural_qc_kernel(const NeuralQc
             constexpr int DM = decltype(dmc)::value, DMIN = decltype(dnc)::value;
             constexpr bool kFinal = decltype(finalc)::value != 0;
             float c[DM], xc[DM], xo[DM];
-            static_for<0, DM>([&](auto kc) {
-                constexpr int k = decltype(kc)::value;
-                nq_ld1_issue(tC + b0 + k, c[k]);
-                if constexpr (!kFinal) {
-                    nq_ld1_issue(tXc + b0 + k, xc[k]);
-                    nq_ld1_issue(tXo + b0 + k, xo[k]);
-                }
-            });
+            float* lcol = lls + b0 * kNqPitch + lane;          // this lane's LLRs / soft outputs of the column, pitch 33
+            const float* wcol = wsm + b0 * 32 + lane;
+            const uint32_t tcol = tXo + b0;
+            {
+                const uint32_t ta = tC + b0, tb = tXc + b0;
+                static_for<0, DM>([&](auto kc) {
+                    constexpr int k = decltype(kc)::value;
+                    nq_ld1_issue(ta + k, c[k]);
+                    if constexpr (!kFinal) {
+                        nq_ld1_issue(tb + k, xc[k]);
+                        nq_ld1_issue(tcol + k, xo[k]);
+                    }
+                });
+            }
             nq_wait_ld();
             static_for<0, DM>([&](auto kc) {
                 constexpr int k = decltype(kc)::value;
@@ -213,16 +224,15 @@ __global__ void __launch_bounds__(kNqThreads, 1) neural_qc_kernel(const NeuralQc
                 static_for<k + 1, DM>([&](auto k2) { s = __fadd_rn(s, c[decltype(k2)::value]); });
                 pre = __fadd_rn(pre, c[k]);
                 if (k < DMIN || k < d) {
-                    const int m = b0 + k;
-                    const float ll = lls[m * kNqPitch + lane];
+                    const float ll = lcol[k * kNqPitch];
                     if constexpr (kFinal) {
                         const float z = __fadd_rn(__fadd_rn(c[k], s), ll);
-                        lls[m * kNqPitch + lane] = 1.0f / (1.0f + expf(-z));
+                        lcol[k * kNqPitch] = 1.0f / (1.0f + expf(-z));
                     } else {
-                        float r = __fadd_rn(__fmul_rn(ll, wsm[m * 32 + lane]), s);
+                        float r = __fadd_rn(__fmul_rn(ll, wcol[k * 32]), s);
                         r = __fadd_rn(r, __fmul_rn(wr0, xc[k]));
                         r = __fadd_rn(r, __fmul_rn(wr1, xo[k]));
-                        nq_st1(tXo + m, r);
+                        nq_st1(tcol + k, r);
                     }
                 }
             });
@@ -289,10 +299,7 @@ __global__ void __launch_bounds__(kNqThreads, 1) neural_qc_kernel(const NeuralQc
             float best = -CUDART_INF_F;
 #pragma unroll 2
             for (int m = mem; m < EB; m += nq::kMembers) {
-                const unsigned cmeta = nq::chunk_meta[m];
-                const int D = cmeta & 0xff, d = (cmeta >> 8) & 0x1f, inv = cmeta >> 13;
-                const int off = 32 * (m - D) + lane, r = (off * inv) >> 16, k = off - r * d;
-                const float s = lls[(D + k) * kNqPitch + r];
+                const float s = lls[tile_addr[m * 32 + lane]];
                 if (live) dst[32 * m] = s;
                 if (gts) {
                     const float y = __ldg(gts + 32 * m);
