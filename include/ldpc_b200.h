@@ -236,10 +236,16 @@ int ldpc_neural_decode(const float* llr_e, const uint16_t* cidx, int Kc, const u
  * lists of create_LLR_mapping (utils/ldpc_utils.py:62-95) are implied by the base graph, check neighbours are lane
  * rotations, variable neighbours are lane-local, the edge state lives in Tensor Memory.  Compiled for the 5G BG2 Z=32
  * table (LDPC_ERR_UNSUPPORTED otherwise) and residual depth L <= 2.  llr_e / gt_e / soft: [B, E] in the variable-major
- * edge order of create_LLR_mapping(H.T); bit-identical to ldpc_neural_decode with that code's tables.  save_x: NULL, or
- * [iters, B, E] receiving the input of every CheckLayer (what ldpc_neural_backward_qc needs).                     */
+ * edge order of create_LLR_mapping(H.T); bit-identical to ldpc_neural_decode with that code's tables.
+ * Training (the loop of training/trainer.py:95-110, `loss.mean().backward()`): pass save_x [iters, B, 197, 32] (the input of
+ * every CheckLayer, stored lane-major) and argmax [B] (edge whose BCE is the frame's max_loss); ldpc_neural_backward_qc then
+ * accumulates d(sum_b g_ml[b] * max_loss[b]) / d w_ch into g_wch [E] and / d w_res into g_wres [L] (+=) -- the autograd of
+ * the four reference layers in that composition, one forward and one backward kernel per step.                        */
 int ldpc_neural_decode_qc(const ldpc_code_t* code, const float* llr_e, const float* w_ch, const float* w_res, int L, int iters,
-                          int64_t B, const float* gt_e, float* soft, float* max_loss, float* save_x, void* stream);
+                          int64_t B, const float* gt_e, float* soft, float* max_loss, float* save_x, int32_t* argmax, void* stream);
+int ldpc_neural_backward_qc(const ldpc_code_t* code, const float* save_x, const float* soft, const float* gt_e, const int32_t* argmax,
+                            const float* g_ml, const float* w_res, int L, int iters, int64_t B, float* g_wch, float* g_wres,
+                            void* stream);
 /* OutputLayer.forward, layers.py:180-210: soft = sigmoid(final+llr); if gt: per-row max of
  * BCE(soft, gt) -> max_loss [B], argmax [B] int32 (for the backward).                    */
 int ldpc_output_layer_fwd(const float* final_llr, const float* llr, const float* gt, int64_t B, int64_t E,

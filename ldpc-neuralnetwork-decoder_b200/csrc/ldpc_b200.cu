@@ -628,7 +628,7 @@ int ldpc_neural_decode(const float* llr_e, const uint16_t* cidx, int Kc, const u
 }
 
 int ldpc_neural_decode_qc(const ldpc_code_t* code, const float* llr_e, const float* w_ch, const float* w_res, int L, int iters,
-                          int64_t B, const float* gt_e, float* soft, float* max_loss, float* save_x, void* stream) {
+                          int64_t B, const float* gt_e, float* soft, float* max_loss, float* save_x, int32_t* argmax, void* stream) {
     if (!code || !llr_e || !w_ch || !soft || (L > 0 && !w_res)) return fail(LDPC_ERR_INVALID, "neural_decode_qc: null argument");
     if (gt_e && !max_loss) return fail(LDPC_ERR_INVALID, "neural_decode_qc: ground truth given without max_loss buffer");
     if (L < 0 || L > 2) return fail(LDPC_ERR_UNSUPPORTED, "neural_decode_qc: residual depth %d outside 0..2 (two ring slots in Tensor Memory)", L);
@@ -638,8 +638,25 @@ int ldpc_neural_decode_qc(const ldpc_code_t* code, const float* llr_e, const flo
     if (!g.ok) return fail(LDPC_ERR_CUDA, "neural_decode_qc: cannot select device %d", code->device);
     NeuralQcParams p{};
     p.llr = llr_e; p.w_ch = w_ch; p.w_res = w_res; p.L = L; p.iters = iters; p.B = B; p.gt = gt_e; p.soft = soft;
-    p.max_loss = max_loss; p.save_x = save_x;
+    p.max_loss = max_loss; p.save_x = save_x; p.argmax = argmax;
+    if (argmax && !gt_e) return fail(LDPC_ERR_INVALID, "neural_decode_qc: argmax needs the ground truth");
     return launch_neural_qc(code, p, (cudaStream_t)stream);
+}
+
+int ldpc_neural_backward_qc(const ldpc_code_t* code, const float* save_x, const float* soft, const float* gt_e, const int32_t* argmax,
+                            const float* g_ml, const float* w_res, int L, int iters, int64_t B, float* g_wch, float* g_wres,
+                            void* stream) {
+    if (!code || !save_x || !soft || !gt_e || !argmax || !g_ml || !g_wch || (L > 0 && (!w_res || !g_wres)))
+        return fail(LDPC_ERR_INVALID, "neural_backward_qc: null argument");
+    if (L < 0 || L > 2) return fail(LDPC_ERR_UNSUPPORTED, "neural_backward_qc: residual depth %d outside 0..2", L);
+    if (iters < 1 || B < 0) return fail(LDPC_ERR_INVALID, "neural_backward_qc: bad shape");
+    if (B == 0) return LDPC_OK;
+    DeviceGuard g(code->device);
+    if (!g.ok) return fail(LDPC_ERR_CUDA, "neural_backward_qc: cannot select device %d", code->device);
+    NeuralQcBwdParams p{};
+    p.save_x = save_x; p.soft = soft; p.gt = gt_e; p.argmax = argmax; p.g_ml = g_ml; p.w_res = w_res; p.L = L; p.iters = iters;
+    p.B = B; p.g_wch = g_wch; p.g_wres = g_wres;
+    return launch_neural_qc_bwd(code, p, (cudaStream_t)stream);
 }
 
 int ldpc_output_layer_fwd(const float* final_llr, const float* llr, const float* gt, int64_t B, int64_t E, float* soft,

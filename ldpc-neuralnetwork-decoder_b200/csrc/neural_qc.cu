@@ -19,4 +19,18 @@ int launch_neural_qc(const ldpc_code_t* c, const NeuralQcParams& p, cudaStream_t
     return LDPC_OK;
 }
 
+int launch_neural_qc_bwd(const ldpc_code_t* c, const NeuralQcBwdParams& p, cudaStream_t st) {
+    if (c->fast_kind != 1)
+        return fail(LDPC_ERR_UNSUPPORTED, "neural_backward_qc: the QC-structured kernel is compiled for the 5G BG2 Z=32 table only");
+    auto kern = neural_qc_bwd_kernel<BG2Z32>;
+    constexpr size_t smem = neural_qc_bwd_smem_bytes<BG2Z32>();
+    static_assert(smem <= (size_t)kMaxSmemPerBlock, "neural_qc_bwd shared memory");
+    LDPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long long blocks = (p.B + kNqGroups - 1) / kNqGroups;
+    if (blocks > kNumSMs) blocks = kNumSMs;
+    kern<<<(int)blocks, kNqThreads, smem, st>>>(p);
+    LDPC_CHECK_LAUNCH("neural_qc_bwd_kernel");
+    return LDPC_OK;
+}
+
 }  // namespace ldpc

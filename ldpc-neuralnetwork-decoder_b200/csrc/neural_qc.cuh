@@ -38,10 +38,27 @@ struct NeuralQcParams {
     float* soft;           // [B, E]
     float* max_loss;       // [B] (with gt)
     // training forward: activations the backward pass reads, or null
-    float* save_x;         // [iters, B, E] input of every CheckLayer (x_0 = llr_e, x_1, ...)
+    float* save_x;         // [iters, B, 197 cells, 32 lanes] input of every CheckLayer (x_0 = llr_e, x_1, ...), lane-major
+    int32_t* argmax;       // [B] edge (caller's numbering) whose loss is the frame's maximum, or null
+};
+
+// backward of (max_loss) w.r.t. w_ch and w_res from the activations a save_x forward left behind
+struct NeuralQcBwdParams {
+    const float* save_x;   // [iters, B, 197, 32]
+    const float* soft;     // [B, E]
+    const float* gt;       // [B, E]
+    const int32_t* argmax; // [B]
+    const float* g_ml;     // [B] d(loss)/d(max_loss[b])
+    const float* w_res;    // [L]
+    int L;
+    int iters;
+    long long B;
+    float* g_wch;          // [E]  accumulated (+=)
+    float* g_wres;         // [2]  accumulated (+=), entries >= L stay untouched
 };
 
 // defined in neural_qc.cu (kernels: neural_qc_kernel.cuh)
 int launch_neural_qc(const ldpc_code_t* c, const NeuralQcParams& p, cudaStream_t st);
+int launch_neural_qc_bwd(const ldpc_code_t* c, const NeuralQcBwdParams& p, cudaStream_t st);
 
 }  // namespace ldpc

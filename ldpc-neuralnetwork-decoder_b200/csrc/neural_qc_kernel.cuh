@@ -266,19 +266,19 @@ __global__ void __launch_bounds__(kNqThreads, 1) neural_qc_kernel(const NeuralQc
 
         for (int l = 0; l < p.iters; ++l) {
             if (p.save_x && live) {
-                // training forward: the input of this CheckLayer in the caller's edge order (d_j-strided 4-byte stores,
-                // merged by the L2: each column's block of 32*d_j floats is written completely by one member)
-                float* dst = p.save_x + ((long long)l * p.B + cw) * E;
-                for (int m = mem; m < EC; m += nq::kMembers) {
-                    const unsigned cmeta = nq::chunk_meta[m];
-                    const int D = cmeta & 0xff, d = (cmeta >> 8) & 0x1f;
-                    float xv;
-                    nq_ld1_issue(tXc + m, xv);
+                // training forward: the input of this CheckLayer as [cell][lane] (one coalesced 128-byte line per cell) --
+                // the layout the backward kernel reads back without a transposing tile
+                float* dst = p.save_x + ((long long)l * p.B + cw) * E + lane;
+                for (int m0 = mem * 4; m0 < EC; m0 += nq::kMembers * 4) {
+                    float xv[4];
+                    static_for<0, 4>([&](auto ic) { if (m0 + decltype(ic)::value < EC) nq_ld1_issue(tXc + m0 + decltype(ic)::value, xv[decltype(ic)::value]); });
                     nq_wait_ld();
-                    nq_tie(xv);
-                    dst[32 * D + lane * d + (m - D)] = xv;
+                    static_for<0, 4>([&](auto ic) {
+                        constexpr int i = decltype(ic)::value;
+                        if (m0 + i < EC) { nq_tie(xv[i]); dst[32 * (m0 + i)] = xv[i]; }
+                    });
                 }
-                for (int x = mem; x < NX; x += nq::kMembers) dst[32 * (EC + x) + lane] = xe0[xc_off + x * 32 + lane];
+                for (int x = mem; x < NX; x += nq::kMembers) dst[32 * (EC + x)] = xe0[xc_off + x * 32 + lane];
             }
             const bool last = l == p.iters - 1;
             phase_a(last);
@@ -297,6 +297,7 @@ __global__ void __launch_bounds__(kNqThreads, 1) neural_qc_kernel(const NeuralQc
             float* dst = p.soft + cw * E + lane;
             const float* gts = p.gt ? p.gt + cw * E + lane : nullptr;
             float best = -CUDART_INF_F;
+            int besti = 0x7fffffff;
 #pragma unroll 2
             for (int m = mem; m < EB; m += nq::kMembers) {
                 const float s = lls[tile_addr[m * 32 + lane]];
@@ -305,22 +306,271 @@ __global__ void __launch_bounds__(kNqThreads, 1) neural_qc_kernel(const NeuralQc
                     const float y = __ldg(gts + 32 * m);
                     const float l1 = fmaxf(logf(s), -100.0f), l0 = fmaxf(logf(1.0f - s), -100.0f);
                     const float loss = -(y * l1 + (1.0f - y) * l0);
-                    best = loss > best ? loss : best;
+                    if (loss > best) { best = loss; besti = 32 * m + lane; }      // first (lowest) edge among equal maxima
                 }
             }
             if (gts) {
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(kFull, best, o));
-                if (lane == 0) red[mem] = best;
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float ob = __shfl_xor_sync(kFull, best, o);
+                    const int oi = __shfl_xor_sync(kFull, besti, o);
+                    if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+                }
+                if (lane == 0) { red[mem] = best; red[4 + mem] = __int_as_float(besti); }
             }
         }
         nq_group_sync(grp);                                  // tile and `red` are complete; the next codeword may overwrite the tile
-        if (p.gt && live && mem == 0 && lane == 0)
-            p.max_loss[cw] = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+        if (p.gt && live && mem == 0 && lane == 0) {
+            float best = red[0];
+            int besti = __float_as_int(red[4]);
+#pragma unroll
+            for (int q = 1; q < nq::kMembers; ++q) {
+                const float ob = red[q];
+                const int oi = __float_as_int(red[4 + q]);
+                if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+            }
+            p.max_loss[cw] = best;
+            if (p.argmax) p.argmax[cw] = besti;
+        }
         nq_group_sync(grp);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem_base_s) : "memory");
+}
+
+
+// ---- backward: d(sum_b g_ml[b] * max_loss[b]) / d(w_ch, w_res) from the saved CheckLayer inputs ---------------------------
+// The autograd graph of the composition (models/decoder.py), walked per codeword with the same 4-warp / TMEM-quarter
+// organisation as the forward:
+//   OutputLayer: the frame's loss is the BCE of ONE edge e* (the arg-max): gz = g_ml (s-y)/max(s(1-s),1e-12) s(1-s)
+//     (torch's own BCE and sigmoid backward formulas, as models/layers.py:_OutputFn uses them); final = sum of ALL check
+//     messages of the variable, so every edge of e*'s variable receives gz as d/d c2v_last;
+//   level l = I-1 .. 1:
+//     CheckLayer backward (per base row): out_n = sign_n * min_{k != n} |x_k| sends its gradient to the first arg-min
+//     k1 (from every n != k1) and to the runner-up k2 (from n = k1); nothing flows through the sign product, through a
+//     zero input or through the 1e10 stand-in (layers.py:48-58, torch.min / abs / sign backward);
+//     Variable + Residual backward (per base column, lane-local): g_c2v[n] = sum_{e != n} gx[e]; g_w_ch[e] += gx[e] llr[e];
+//     g_w_res[i] += gx . x_{l-1-i};  gx_{l-1-i} += w_res[i] gx   (only where that output is a queue entry);
+//   level 0 (x_0 = llr_e) owns no parameter and is skipped.
+// State: three gradient arrays (gx of this level and the pass-through of the next two) in Tensor Memory, g_c2v in shared
+// memory, g_w_ch accumulated over the CTA's codewords in shared memory and flushed once with global atomics.
+template <class BG>
+constexpr int nqb_group_floats() { return BG::kCoreEdges * 32 + 4 * BG::kExtCols * 32; }
+template <class BG>
+constexpr size_t neural_qc_bwd_smem_bytes() {
+    return sizeof(float) * ((size_t)BG::kEdges * 32 + (size_t)kNqGroups * nqb_group_floats<BG>());
+}
+
+template <class BG>
+__global__ void __launch_bounds__(kNqThreads, 1) neural_qc_bwd_kernel(const NeuralQcBwdParams p) {
+    static_assert(BG::kZ == 32, "one codeword per warp-wide lane set");
+    constexpr int EB = BG::kEdges, EC = BG::kCoreEdges, NX = BG::kExtCols;
+    constexpr int ECP = (EC + 3) / 4 * 4;
+    constexpr int E = EB * 32;
+    extern __shared__ float nq_smem[];
+    const int lane = threadIdx.x & 31, warp = __shfl_sync(kFull, (int)(threadIdx.x >> 5), 0);
+    const int grp = warp & (kNqGroups - 1), mem = warp / kNqGroups;
+    float* gw = nq_smem;                                                   // [EB][32]  g_w_ch per (cell, lane), all codewords
+    float* gc = nq_smem + EB * 32 + grp * nqb_group_floats<BG>();         // [EC][32]  d/d c2v of the core cells (variable-aligned)
+    float* ae = gc + EC * 32;                                              // [3][NX][32] gradient ring of the degree-1 cells
+    float* gce = ae + 3 * NX * 32;                                         // [NX][32]  d/d c2v of the degree-1 cells (last level only)
+
+    __shared__ uint32_t tmem_base_s;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;"
+                     :: "r"((uint32_t)__cvta_generic_to_shared(&tmem_base_s)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < EB * 32; i += kNqThreads) gw[i] = 0.0f;
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tbase = __shfl_sync(kFull, tmem_base_s, 0) + (((uint32_t)grp * 32u) << 16);
+    uint32_t tA0 = tbase, tA1 = tbase + ECP, tA2 = tbase + 2 * ECP;       // gx of this level | pass-through to l-1 | to l-2
+    int a0 = 0, a1 = NX * 32, a2 = 2 * NX * 32;
+    const float wres0 = p.L >= 1 ? __ldg(p.w_res) : 0.0f, wres1 = p.L >= 2 ? __ldg(p.w_res + 1) : 0.0f;
+    float acc_wr0 = 0.0f, acc_wr1 = 0.0f;
+
+    for (long long cw0 = (long long)blockIdx.x * kNqGroups; cw0 < p.B; cw0 += (long long)gridDim.x * kNqGroups) {
+        const bool live = cw0 + grp < p.B;
+        const long long cw = live ? cw0 + grp : p.B - 1;
+        // ---- OutputLayer backward at the arg-max edge ----
+        const int es = __ldg(p.argmax + cw);
+        float gz;
+        {
+            const float s = __ldg(p.soft + cw * E + es), y = __ldg(p.gt + cw * E + es);
+            gz = __ldg(p.g_ml + cw) * (s - y) / fmaxf((1.0f - s) * s, 1e-12f) * (s * (1.0f - s));
+            if (!live) gz = 0.0f;                                          // a group past the end of the batch contributes nothing
+        }
+        const unsigned smeta = nq::chunk_meta[es >> 5];
+        const int sD = smeta & 0xff, sd = (smeta >> 8) & 0x1f;
+        const int soff = 32 * ((es >> 5) - sD) + (es & 31), srow = (soff * (int)(smeta >> 13)) >> 16;      // circulant row of e*
+        for (int m = mem; m < EC; m += nq::kMembers) {
+            gc[m * 32 + lane] = (m >= sD && m < sD + sd && lane == srow) ? gz : 0.0f;
+            nq_st1(tA0 + m, 0.0f);
+            nq_st1(tA1 + m, 0.0f);
+        }
+        for (int x = mem; x < NX; x += nq::kMembers) {
+            gce[x * 32 + lane] = (EC + x == sD && lane == srow) ? gz : 0.0f;
+            ae[a0 + x * 32 + lane] = 0.0f;
+            ae[a1 + x * 32 + lane] = 0.0f;
+        }
+        nq_group_sync(grp);
+
+        auto row_bwd = [&](auto ncc, auto nec, int row, const float* xl, bool last) {
+            constexpr int NC = decltype(ncc)::value, NE = decltype(nec)::value, d = NC + NE;
+            float v[d], g[d], old[NC];
+            unsigned sb[d];
+            int cell[NC], sft[NC];
+            static_for<0, NC>([&](auto kc) {
+                constexpr int k = decltype(kc)::value;
+                const unsigned meta = nq::row_meta[row][k];
+                cell[k] = meta & 0xff;
+                sft[k] = meta >> 8;
+                v[k] = __ldg(xl + 32 * cell[k]);
+                g[k] = gc[cell[k] * 32 + lane];
+                nq_ld1_issue(tA0 + cell[k], old[k]);
+            });
+            int xs = 0;
+            if constexpr (NE) {
+                xs = nq::row_ext[row];
+                v[NC] = __ldg(xl + 32 * (EC + xs));
+                g[NC] = last ? gce[xs * 32 + lane] : 0.0f;      // a degree-1 variable consumes its check message only in `final`
+            }
+            static_for<0, NC>([&](auto kc) {
+                constexpr int k = decltype(kc)::value;
+                v[k] = __shfl_sync(kFull, v[k], lane + sft[k]);
+                g[k] = __shfl_sync(kFull, g[k], lane + sft[k]);
+            });
+            // forward quantities again: sign bits of (v + 1e-10), first arg-min k1 and runner-up k2 of |v| (zeros -> 1e10)
+            unsigned nb = 0;
+            float m1 = CUDART_INF_F, m2 = CUDART_INF_F;
+            int k1 = -1, k2 = -1;
+            bool r1 = false, r2 = false;
+            static_for<0, d>([&](auto kc) {
+                constexpr int k = decltype(kc)::value;
+                sb[k] = f2u(__fadd_rn(v[k], 1e-10f));
+                nb ^= sb[k];
+                const float av = fabsf(v[k]);
+                const bool real = av > 0.0f;
+                const float a = real ? av : 1e10f;
+                if (a < m1) { m2 = m1; k2 = k1; r2 = r1; m1 = a; k1 = k; r1 = real; }
+                else if (a < m2) { m2 = a; k2 = k; r2 = real; }
+            });
+            // fewer than 9 other edges: a minimum above 1e10 loses to the padded slot and carries no gradient
+            if (d - 1 < 9) { r1 = r1 && !(m1 > 1e10f); r2 = r2 && !(m2 > 1e10f); }
+            float tex = 0.0f, gs1 = 0.0f;                          // sum_{n != k1} g_n sign_n,  g_k1 sign_k1
+            static_for<0, d>([&](auto kc) {
+                constexpr int k = decltype(kc)::value;
+                const float gs = u2f(f2u(g[k]) ^ ((nb ^ sb[k]) & 0x80000000u));
+                tex += (k == k1) ? 0.0f : gs;
+                gs1 += (k == k1) ? gs : 0.0f;
+            });
+            const float val1 = r1 ? tex : 0.0f, val2 = r2 ? gs1 : 0.0f;
+            nq_wait_ld();
+            static_for<0, d>([&](auto kc) {
+                constexpr int k = decltype(kc)::value;
+                float c = (k == k1) ? val1 : ((k == k2) ? val2 : 0.0f);
+                c = u2f(f2u(c) ^ (f2u(v[k]) & 0x80000000u));                       // d|x|/dx = sign(x)
+                if constexpr (k < NC) {
+                    nq_tie(old[k]);
+                    nq_st1(tA0 + cell[k], __fadd_rn(old[k], __shfl_sync(kFull, c, lane - sft[k])));
+                } else {
+                    ae[a0 + xs * 32 + lane] += c;
+                }
+            });
+        };
+
+        for (int l = p.iters - 1; l >= 1; --l) {
+            const float* xl = p.save_x + ((long long)l * p.B + cw) * E + lane;
+            const bool last = l == p.iters - 1;
+            static_for<0, nq::kRowClasses>([&](auto cc) {
+                constexpr int c = decltype(cc)::value;
+                const int t1 = nq::sched_row_ptr[mem][c + 1];
+#pragma unroll 1
+                for (int t = nq::sched_row_ptr[mem][c]; t < t1; ++t)
+                    row_bwd(IC<kNqRowNc[c]>{}, IC<kNqRowNe[c]>{}, (int)nq::sched_rows[mem][t], xl, last);
+            });
+            nq_group_sync(grp);
+            // ---- Variable + Residual backward ----
+            const float* x0 = p.save_x + cw * E + lane;                                   // llr_e
+            const float* xm1 = p.save_x + ((long long)(l - 1) * p.B + cw) * E + lane;      // x_{l-1}: queue entry iff l-1 >= 1
+            const float* xm2 = p.save_x + ((long long)(l >= 2 ? l - 2 : 0) * p.B + cw) * E + lane;
+            const float w0 = l >= 2 ? wres0 : 0.0f, w1 = l >= 3 ? wres1 : 0.0f;
+            const int c1 = nq::sched_col_ptr[mem][nq::kColClasses];
+#pragma unroll 1
+            for (int t = 0; t < c1; ++t) {
+                const int j = nq::sched_cols[mem][t], b0 = nq::col_b0[j], d = nq::col_d[j];
+                float S = 0.0f;
+#pragma unroll 1
+                for (int k0 = 0; k0 < d; k0 += 4) {
+                    float gx[4];
+                    static_for<0, 4>([&](auto ic) { nq_ld1_issue(tA0 + b0 + k0 + decltype(ic)::value, gx[decltype(ic)::value]); });
+                    nq_wait_ld();
+                    static_for<0, 4>([&](auto ic) {
+                        constexpr int i = decltype(ic)::value;
+                        nq_tie(gx[i]);
+                        S += (k0 + i < d) ? gx[i] : 0.0f;
+                    });
+                }
+#pragma unroll 1
+                for (int k0 = 0; k0 < d; k0 += 4) {
+                    float gx[4], pa[4];
+                    static_for<0, 4>([&](auto ic) {
+                        nq_ld1_issue(tA0 + b0 + k0 + decltype(ic)::value, gx[decltype(ic)::value]);
+                        nq_ld1_issue(tA1 + b0 + k0 + decltype(ic)::value, pa[decltype(ic)::value]);
+                    });
+                    nq_wait_ld();
+                    static_for<0, 4>([&](auto ic) {
+                        constexpr int i = decltype(ic)::value;
+                        nq_tie(gx[i]); nq_tie(pa[i]);
+                        if (k0 + i < d) {
+                            const int m = b0 + k0 + i;
+                            gc[m * 32 + lane] = S - gx[i];
+                            atomicAdd(&gw[m * 32 + lane], gx[i] * __ldg(x0 + 32 * m));
+                            acc_wr0 += (l >= 2) ? gx[i] * __ldg(xm1 + 32 * m) : 0.0f;
+                            acc_wr1 += (l >= 3) ? gx[i] * __ldg(xm2 + 32 * m) : 0.0f;
+                            nq_st1(tA1 + m, __fadd_rn(pa[i], w0 * gx[i]));
+                            nq_st1(tA2 + m, w1 * gx[i]);
+                        }
+                    });
+                }
+            }
+            const int nx = nq::sched_ext_cnt[mem];
+#pragma unroll 1
+            for (int t = 0; t < nx; ++t) {
+                const int x = nq::sched_ext[mem][t], m = EC + x;
+                const float gx = ae[a0 + x * 32 + lane];
+                atomicAdd(&gw[m * 32 + lane], gx * __ldg(x0 + 32 * m));
+                acc_wr0 += (l >= 2) ? gx * __ldg(xm1 + 32 * m) : 0.0f;
+                acc_wr1 += (l >= 3) ? gx * __ldg(xm2 + 32 * m) : 0.0f;
+                ae[a1 + x * 32 + lane] += w0 * gx;
+                ae[a2 + x * 32 + lane] = w1 * gx;
+            }
+            nq_group_sync(grp);
+            { const uint32_t t = tA0; tA0 = tA1; tA1 = tA2; tA2 = t; }
+            { const int t = a0; a0 = a1; a1 = a2; a2 = t; }
+        }
+        nq_group_sync(grp);
+    }
+    // ---- flush the parameter gradients ----
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc_wr0 += __shfl_xor_sync(kFull, acc_wr0, o);
+        acc_wr1 += __shfl_xor_sync(kFull, acc_wr1, o);
+    }
+    if (lane == 0) {
+        if (p.L >= 1) atomicAdd(p.g_wres, acc_wr0);
+        if (p.L >= 2) atomicAdd(p.g_wres + 1, acc_wr1);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    for (int m = warp; m < EB; m += kNqThreads / 32) {
+        const unsigned cmeta = nq::chunk_meta[m];
+        const int D = cmeta & 0xff, d = (cmeta >> 8) & 0x1f;
+        atomicAdd(p.g_wch + 32 * D + lane * d + (m - D), gw[m * 32 + lane]);
+    }
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem_base_s) : "memory");
 }
 

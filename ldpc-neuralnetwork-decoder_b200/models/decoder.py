@@ -27,7 +27,10 @@ classes (fixture tests/golden/neural_decoder_z4.npz):
                                                           edge's variable
     soft, max_loss = OutputLayer(final, llr_e, ground_truth_e)          layers.py:180-210
 
-Two execution paths, both CUDA, bit-identical to each other:
+On the 5G BG2 Z=32 code with the index tensors of create_LLR_mapping (checked once per tensor) both inference and
+training run on the QC-structured kernels (csrc/neural_qc_kernel.cuh: no index tables, state in Tensor Memory;
+training = one forward kernel that saves the CheckLayer inputs + one backward kernel); `qc=False` disables that.
+Otherwise two execution paths, both CUDA, bit-identical to each other and to the QC forward:
   * no gradient needed (`torch.no_grad()`, `.decode()`, frozen parameters): the WHOLE decoder
     is one kernel (`ldpc_neural_decode`, csrc/neural.cuh) that keeps the messages of a
     codeword in shared memory across all iterations; the index tensors are packed once per
@@ -123,6 +126,48 @@ def _qc_code_for(check_index_tensor, var_index_tensor, num_nodes):
     return canon[0] if ok else None
 
 
+class _NeuralQcTrainFn(torch.autograd.Function):
+    """The whole decoder as ONE forward and ONE backward kernel on the QC structure (csrc/neural_qc_kernel.cuh): the
+    call shape of training/trainer.py:95-110 -- `soft, loss = decoder(llr, cidx, vidx, gt); loss.mean().backward()`.
+    Differentiable output: max_loss (w.r.t. w_ch and w_res).  `soft` is returned for monitoring and is NOT part of the
+    graph on this path (a loss built on `soft`, or gradients w.r.t. the LLRs, take the per-layer path instead)."""
+
+    @staticmethod
+    def forward(ctx, llr_e, gt_e, w_ch, w_res, code, iters, depth_L):
+        llr_c = llr_e.detach().to(torch.float32).contiguous()
+        y = gt_e.detach().to(torch.float32).contiguous()
+        wch = w_ch.detach().to(torch.float32).contiguous()
+        wres = w_res.detach().to(torch.float32).contiguous()
+        B, E = llr_c.shape
+        dev = llr_c.device
+        soft = torch.empty_like(llr_c)
+        ml = torch.empty(B, dtype=torch.float32, device=dev)
+        am = torch.empty(B, dtype=torch.int32, device=dev)
+        save_x = torch.empty((iters, B, E), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _native.check(_native.lib().ldpc_neural_decode_qc(
+                code.handle(dev), _native.ptr(llr_c), _native.ptr(wch), _native.ptr(wres), depth_L, iters, B, _native.ptr(y),
+                _native.ptr(soft), _native.ptr(ml), _native.ptr(save_x), _native.ptr(am), _native.stream_ptr(dev)))
+        ctx.save_for_backward(save_x, soft, y, am, wres)
+        ctx.code, ctx.iters, ctx.depth_L, ctx.E = code, iters, depth_L, E
+        ctx.mark_non_differentiable(soft)
+        return soft, ml
+
+    @staticmethod
+    def backward(ctx, _g_soft, g_ml):
+        save_x, soft, y, am, wres = ctx.saved_tensors
+        dev = soft.device
+        B = soft.shape[0]
+        g = (g_ml if g_ml is not None else torch.zeros(B, device=dev)).to(torch.float32).contiguous()
+        g_wch = torch.zeros(ctx.E, dtype=torch.float32, device=dev)
+        g_wres = torch.zeros(max(ctx.depth_L, 1), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _native.check(_native.lib().ldpc_neural_backward_qc(
+                ctx.code.handle(dev), _native.ptr(save_x), _native.ptr(soft), _native.ptr(y), _native.ptr(am), _native.ptr(g),
+                _native.ptr(wres), ctx.depth_L, ctx.iters, B, _native.ptr(g_wch), _native.ptr(g_wres), _native.stream_ptr(dev)))
+        return None, None, g_wch, g_wres[:ctx.depth_L], None, None, None
+
+
 class LDPCNeuralDecoder(nn.Module):
     def __init__(self, num_nodes, num_iterations=5, depth_L=2, output_index_tensor=None, fused=True, qc=True):
         super().__init__()
@@ -201,7 +246,7 @@ class LDPCNeuralDecoder(nn.Module):
             with torch.cuda.device(llr_c.device):
                 _native.check(_native.lib().ldpc_neural_decode_qc(
                     code.handle(llr_c.device), _native.ptr(llr_c), _native.ptr(w_ch), _native.ptr(w_res), self.depth_L,
-                    self.num_iterations, B, _native.ptr(y), _native.ptr(soft), _native.ptr(ml), None,
+                    self.num_iterations, B, _native.ptr(y), _native.ptr(soft), _native.ptr(ml), None, None,
                     _native.stream_ptr(llr_c.device)))
             return soft, ml
         cp, cperm, ccnt = packed_index(check_index_tensor).sorted()
@@ -228,7 +273,15 @@ class LDPCNeuralDecoder(nn.Module):
         gt_e = self._to_edges(ground_truth)
         needs_grad = torch.is_grad_enabled() and (llr_e.requires_grad or any(
             p.requires_grad for p in self.parameters()))
-        if self.fused and not needs_grad and self.num_nodes < 0xFFFF and self.depth_L <= 4:
+        code = None
+        if (self.fused and self.qc and needs_grad and gt_e is not None and self.depth_L <= 2 and not llr_e.requires_grad
+                and check_index_tensor.shape[0] == self.num_nodes and var_index_tensor.shape[0] == self.num_nodes):
+            code = _qc_code_for(check_index_tensor, var_index_tensor, self.num_nodes)
+        if code is not None:
+            # training on the QC structure: one forward kernel that saves the CheckLayer inputs + one backward kernel
+            res = self.residual_layer
+            soft, max_loss = _NeuralQcTrainFn.apply(llr_e, gt_e, res.w_ch, res.w_res, code, self.num_iterations, self.depth_L)
+        elif self.fused and not needs_grad and self.num_nodes < 0xFFFF and self.depth_L <= 4:
             soft, max_loss = self._forward_one_kernel(llr_e, check_index_tensor, var_index_tensor, gt_e)
         else:
             c2v = self._messages(llr_e, check_index_tensor, var_index_tensor)

@@ -258,3 +258,38 @@ def test_qc_structured_kernel_is_bit_identical_to_the_table_driven_kernels(depth
         s_o, _ = make(True)(x[:8], other, vidx)
         s_t, _ = make(False)(x[:8], other, vidx)
     assert torch.equal(s_o, s_t)
+
+
+@pytest.mark.parametrize("depth_L,iters", [(2, 5), (1, 4), (0, 3), (2, 2)])
+def test_qc_structured_training_step_matches_the_per_layer_autograd(depth_L, iters):
+    """One forward + one backward kernel on the QC structure (the trainer's `loss.mean().backward()`, trainer.py:105-107)
+    against the per-layer kernels under torch.autograd (themselves pinned to the reference layers' autograd on the Z=4
+    golden): same max_loss bits, gradients of w_ch and w_res within 1e-4 of each tensor's scale."""
+    code = QCCode.nr_2_0(32)
+    _, cidx, vidx, _ = create_LLR_mapping(code.dense().T)
+    cidx, vidx = cidx.to(DEV), vidx.to(DEV)
+    rng = np.random.default_rng(7 + depth_L)
+    B = 4 * 148 + 5
+    llr_e = (rng.normal(size=(B, code.E)) * 0.3 + 0.2).astype(np.float32) * 0.5      # keeps sigmoid / BCE out of saturation
+    w_ch = (rng.random(code.E) * 0.5 + 0.75).astype(np.float32)
+    w_res = np.array([0.2, -0.1][:depth_L], np.float32)
+    gt_e = (rng.random((B, code.E)) < 0.7).astype(np.float32)
+    x, y = torch.from_numpy(llr_e).to(DEV), torch.from_numpy(gt_e).to(DEV)
+
+    def run(qc):
+        d = LDPCNeuralDecoder(code.E, iters, depth_L, qc=qc).to(DEV)
+        with torch.no_grad():
+            d.residual_layer.w_ch.copy_(torch.from_numpy(w_ch))
+            d.residual_layer.w_res.copy_(torch.from_numpy(w_res))
+        n0 = ldpc_b200._native.lib().ldpc_launch_count()
+        soft, ml = d(x, cidx, vidx, y)
+        (ml * torch.linspace(0.5, 1.5, B, device=DEV)).mean().backward()            # non-uniform upstream gradient
+        return soft.detach(), ml.detach(), d.residual_layer.w_ch.grad, d.residual_layer.w_res.grad, ldpc_b200._native.lib().ldpc_launch_count() - n0
+    s_q, m_q, gw_q, gr_q, n_q = run(True)
+    s_t, m_t, gw_t, gr_t, n_t = run(False)
+    assert n_q == 2 and n_t > 2                                       # one forward + one backward kernel
+    assert torch.equal(s_q, s_t) and torch.equal(m_q, m_t)
+    assert float(gw_t.abs().max()) > 0
+    assert float((gw_q - gw_t).abs().max()) <= 1e-4 * float(gw_t.abs().max())
+    if depth_L:
+        assert float((gr_q - gr_t).abs().max()) <= 1e-4 * max(float(gr_t.abs().max()), 1e-12), (gr_q, gr_t)
