@@ -193,6 +193,21 @@ def emit_nq(rows, cols, cells, Z, dst):
         m = min(range(NQ_MEMBERS), key=lambda q: load[q])
         load[m] += 12
         sext[m].append(x)
+    # backward, variable step: the member's cells flattened (column after column) in chunks of 8, with the member-local slot
+    # of their column (its sum is kept in a register); 255 = padding
+    scells, sslots = [], []
+    for m in range(NQ_MEMBERS):
+        cl, sl = [], []
+        for slot, j in enumerate(scols[m]):
+            for k in range(coldeg[j]):
+                cl.append(vm0[j] + k)
+                sl.append(slot)
+        while len(cl) % 8:
+            cl.append(255)
+            sl.append(0)
+        scells.append(cl)
+        sslots.append(sl)
+    ncell = max(len(l) for l in scells)
     chunk = []
     for m in range(vm0[-1] + coldeg[-1]):
         j = max(jj for jj in range(cols) if vm0[jj] <= m)
@@ -236,6 +251,10 @@ def emit_nq(rows, cols, cells, Z, dst):
             arr("unsigned char", "col_d", [coldeg[j] for j in core_cols], f"[{len(core_cols)}]"),
             arr("unsigned char", "sched_cols", pad(scols, ncm), f"[{NQ_MEMBERS}][{ncm}]"),
             arr("unsigned char", "sched_col_ptr", prefix(scols, lambda j: col_class[j], len(NQ_COL_CLASSES)), f"[{NQ_MEMBERS}][{len(NQ_COL_CLASSES) + 1}]"),
+            f"constexpr int kCellsMax = {ncell};",
+            arr("unsigned char", "sched_cells", [v for l in scells for v in (l + [255] * (ncell - len(l)))], f"[{NQ_MEMBERS}][{ncell}]"),
+            arr("unsigned char", "sched_cell_slot", [v for l in sslots for v in (l + [0] * (ncell - len(l)))], f"[{NQ_MEMBERS}][{ncell}]"),
+            arr("unsigned char", "sched_cell_cnt", [len(l) for l in scells], f"[{NQ_MEMBERS}]"),
             arr("unsigned char", "sched_ext", pad(sext, nxm), f"[{NQ_MEMBERS}][{nxm}]"),
             arr("unsigned char", "sched_ext_cnt", [len(l) for l in sext], f"[{NQ_MEMBERS}]"),
             arr("unsigned int", "chunk_meta", [D | (d << 8) | (inv << 13) for D, d, inv in chunk], f"[{len(chunk)}]") +

@@ -45,6 +45,12 @@ __device__ __forceinline__ void nq_tie(float& a) { asm volatile("" : "+f"(a)); }
 __device__ __forceinline__ void nq_st1(uint32_t taddr, float v) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" :: "r"(taddr), "r"(f2u(v)) : "memory");
 }
+// L1-allocating load: unlike ld.global.nc (__ldg) it hits the lines prefetch.global.L1 brought in
+__device__ __forceinline__ float nq_ldca(const float* p) {
+    float v;
+    asm volatile("ld.global.ca.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ void nq_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void nq_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // the members of a codeword meet: TMEM stores settled, ordered before / after the barrier, shared memory too
@@ -103,6 +109,17 @@ __global__ void __launch_bounds__(kNqThreads, 1) neural_qc_kernel(const NeuralQc
         // groups past the end of the batch keep walking (on the last codeword, without storing): every barrier is reached
         const bool live = cw0 + grp < p.B;
         const long long cw = live ? cw0 + grp : p.B - 1;
+        // the NEXT codeword of this group: pull its rows (llr_e, ground truth) into L2 while this one is decoded
+        {
+            const long long nxt = cw0 + (long long)gridDim.x * kNqGroups + grp;
+            if (nxt < p.B) {
+                const int t = mem * 32 + lane;                      // 128 threads, one 128-byte line each per step
+                for (int i = t; i < EB; i += nq::kMembers * 32) {
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(p.llr + nxt * E + 32 * i));
+                    if (p.gt) asm volatile("prefetch.global.L2 [%0];" :: "l"(p.gt + nxt * E + 32 * i));
+                }
+            }
+        }
         // ---- load llr_e[cw]: coalesced 128-byte chunks -> [cell][lane] tile ----
         {
             const float* src = p.llr + cw * E + lane;
@@ -395,6 +412,18 @@ __global__ void __launch_bounds__(kNqThreads, 1) neural_qc_bwd_kernel(const Neur
     for (long long cw0 = (long long)blockIdx.x * kNqGroups; cw0 < p.B; cw0 += (long long)gridDim.x * kNqGroups) {
         const bool live = cw0 + grp < p.B;
         const long long cw = live ? cw0 + grp : p.B - 1;
+        // the NEXT codeword of this group: pull its saved activations (all levels) into L2 -- they stream from HBM otherwise
+        // and every row / column step would wait a full DRAM latency (first build: long_scoreboard 10 stalls per issue)
+        {
+            const long long nxt = cw0 + (long long)gridDim.x * kNqGroups + grp;
+            if (nxt < p.B) {
+                const int t = mem * 32 + lane;
+                for (int l = 0; l < p.iters; ++l) {
+                    const float* base = p.save_x + ((long long)l * p.B + nxt) * E;
+                    for (int i = t; i < EB; i += nq::kMembers * 32) asm volatile("prefetch.global.L2 [%0];" :: "l"(base + 32 * i));
+                }
+            }
+        }
         // ---- OutputLayer backward at the arg-max edge ----
         const int es = __ldg(p.argmax + cw);
         float gz;
@@ -418,24 +447,37 @@ __global__ void __launch_bounds__(kNqThreads, 1) neural_qc_bwd_kernel(const Neur
         }
         nq_group_sync(grp);
 
-        auto row_bwd = [&](auto ncc, auto nec, int row, const float* xl, bool last) {
+        // Saved activations stream from HBM / L2: every step keeps its loads in flight ahead of their use.  Rows: the 10 + 1
+        // values of the member's NEXT row (whatever its shape; unused slots re-read cell 0) are requested before the
+        // current row is worked on.
+        float pre[11];
+        auto row_prefetch = [&](int row, const float* xl) {
+            static_for<0, 10>([&](auto kc) {
+                constexpr int k = decltype(kc)::value;
+                pre[k] = __ldg(xl + 32 * (int)(nq::row_meta[row][k] & 0xff));
+            });
+            const int xr = nq::row_ext[row];
+            pre[10] = __ldg(xl + 32 * (EC + (xr < NX ? xr : 0)));                  // rows without a degree-1 edge re-read slot 0
+        };
+        auto row_bwd = [&](auto ncc, auto nec, int row, int next_row, const float* xl, bool last) {
             constexpr int NC = decltype(ncc)::value, NE = decltype(nec)::value, d = NC + NE;
             float v[d], g[d], old[NC];
             unsigned sb[d];
             int cell[NC], sft[NC];
+            static_for<0, NC>([&](auto kc) { v[decltype(kc)::value] = pre[decltype(kc)::value]; });
+            if constexpr (NE) v[NC] = pre[10];
+            row_prefetch(next_row, xl);
             static_for<0, NC>([&](auto kc) {
                 constexpr int k = decltype(kc)::value;
                 const unsigned meta = nq::row_meta[row][k];
                 cell[k] = meta & 0xff;
                 sft[k] = meta >> 8;
-                v[k] = __ldg(xl + 32 * cell[k]);
                 g[k] = gc[cell[k] * 32 + lane];
                 nq_ld1_issue(tA0 + cell[k], old[k]);
             });
             int xs = 0;
             if constexpr (NE) {
                 xs = nq::row_ext[row];
-                v[NC] = __ldg(xl + 32 * (EC + xs));
                 g[NC] = last ? gce[xs * 32 + lane] : 0.0f;      // a degree-1 variable consumes its check message only in `final`
             }
             static_for<0, NC>([&](auto kc) {
@@ -485,12 +527,14 @@ __global__ void __launch_bounds__(kNqThreads, 1) neural_qc_bwd_kernel(const Neur
         for (int l = p.iters - 1; l >= 1; --l) {
             const float* xl = p.save_x + ((long long)l * p.B + cw) * E + lane;
             const bool last = l == p.iters - 1;
+            row_prefetch((int)nq::sched_rows[mem][0], xl);
             static_for<0, nq::kRowClasses>([&](auto cc) {
                 constexpr int c = decltype(cc)::value;
                 const int t1 = nq::sched_row_ptr[mem][c + 1];
 #pragma unroll 1
                 for (int t = nq::sched_row_ptr[mem][c]; t < t1; ++t)
-                    row_bwd(IC<kNqRowNc[c]>{}, IC<kNqRowNe[c]>{}, (int)nq::sched_rows[mem][t], xl, last);
+                    row_bwd(IC<kNqRowNc[c]>{}, IC<kNqRowNe[c]>{}, (int)nq::sched_rows[mem][t],
+                            (int)nq::sched_rows[mem][t + 1 < nq::kRowsMax ? t + 1 : t], xl, last);
             });
             nq_group_sync(grp);
             // ---- Variable + Residual backward ----
@@ -498,55 +542,83 @@ __global__ void __launch_bounds__(kNqThreads, 1) neural_qc_bwd_kernel(const Neur
             const float* xm1 = p.save_x + ((long long)(l - 1) * p.B + cw) * E + lane;      // x_{l-1}: queue entry iff l-1 >= 1
             const float* xm2 = p.save_x + ((long long)(l >= 2 ? l - 2 : 0) * p.B + cw) * E + lane;
             const float w0 = l >= 2 ? wres0 : 0.0f, w1 = l >= 3 ? wres1 : 0.0f;
+            const float u0 = l >= 2 ? 1.0f : 0.0f, u1 = l >= 3 ? 1.0f : 0.0f;            // which w_res entries this level feeds
+            // column sums of gx (the member owns at most kColsMax columns; their sums stay in registers)
+            float S[nq::kColsMax];
             const int c1 = nq::sched_col_ptr[mem][nq::kColClasses];
+            static_for<0, nq::kColsMax>([&](auto sc) {
+                constexpr int sl = decltype(sc)::value;
+                S[sl] = 0.0f;
+                if (sl < c1) {
+                    const int j = nq::sched_cols[mem][sl], b0 = nq::col_b0[j], d = nq::col_d[j];
 #pragma unroll 1
-            for (int t = 0; t < c1; ++t) {
-                const int j = nq::sched_cols[mem][t], b0 = nq::col_b0[j], d = nq::col_d[j];
-                float S = 0.0f;
-#pragma unroll 1
-                for (int k0 = 0; k0 < d; k0 += 4) {
-                    float gx[4];
-                    static_for<0, 4>([&](auto ic) { nq_ld1_issue(tA0 + b0 + k0 + decltype(ic)::value, gx[decltype(ic)::value]); });
-                    nq_wait_ld();
-                    static_for<0, 4>([&](auto ic) {
-                        constexpr int i = decltype(ic)::value;
-                        nq_tie(gx[i]);
-                        S += (k0 + i < d) ? gx[i] : 0.0f;
-                    });
+                    for (int k0 = 0; k0 < d; k0 += 8) {
+                        float gx[8];
+                        static_for<0, 8>([&](auto ic) { nq_ld1_issue(tA0 + b0 + k0 + decltype(ic)::value, gx[decltype(ic)::value]); });
+                        nq_wait_ld();
+                        static_for<0, 8>([&](auto ic) {
+                            constexpr int i = decltype(ic)::value;
+                            nq_tie(gx[i]);
+                            S[sl] += (k0 + i < d) ? gx[i] : 0.0f;
+                        });
+                    }
                 }
+            });
+            // the member's cells, eight at a time: 24 global loads + 16 TMEM loads in flight per chunk
+            const int ncell = nq::sched_cell_cnt[mem];
 #pragma unroll 1
-                for (int k0 = 0; k0 < d; k0 += 4) {
-                    float gx[4], pa[4];
-                    static_for<0, 4>([&](auto ic) {
-                        nq_ld1_issue(tA0 + b0 + k0 + decltype(ic)::value, gx[decltype(ic)::value]);
-                        nq_ld1_issue(tA1 + b0 + k0 + decltype(ic)::value, pa[decltype(ic)::value]);
-                    });
-                    nq_wait_ld();
-                    static_for<0, 4>([&](auto ic) {
-                        constexpr int i = decltype(ic)::value;
-                        nq_tie(gx[i]); nq_tie(pa[i]);
-                        if (k0 + i < d) {
-                            const int m = b0 + k0 + i;
-                            gc[m * 32 + lane] = S - gx[i];
-                            atomicAdd(&gw[m * 32 + lane], gx[i] * __ldg(x0 + 32 * m));
-                            acc_wr0 += (l >= 2) ? gx[i] * __ldg(xm1 + 32 * m) : 0.0f;
-                            acc_wr1 += (l >= 3) ? gx[i] * __ldg(xm2 + 32 * m) : 0.0f;
-                            nq_st1(tA1 + m, __fadd_rn(pa[i], w0 * gx[i]));
-                            nq_st1(tA2 + m, w1 * gx[i]);
-                        }
-                    });
-                }
+            for (int c0 = 0; c0 < ncell; c0 += 8) {
+                float gx[8], pa[8], ll[8], y1[8], y2[8];
+                int cm[8];
+                static_for<0, 8>([&](auto ic) {
+                    constexpr int i = decltype(ic)::value;
+                    const int m = nq::sched_cells[mem][c0 + i];
+                    cm[i] = m < 255 ? m : 0;                                        // padding: reads cell 0, stores nothing
+                    ll[i] = __ldg(x0 + 32 * cm[i]);
+                    y1[i] = __ldg(xm1 + 32 * cm[i]);
+                    y2[i] = __ldg(xm2 + 32 * cm[i]);
+                    nq_ld1_issue(tA0 + cm[i], gx[i]);
+                    nq_ld1_issue(tA1 + cm[i], pa[i]);
+                });
+                nq_wait_ld();
+                static_for<0, 8>([&](auto ic) {
+                    constexpr int i = decltype(ic)::value;
+                    nq_tie(gx[i]); nq_tie(pa[i]);
+                    if (nq::sched_cells[mem][c0 + i] < 255) {
+                        const int sl = nq::sched_cell_slot[mem][c0 + i];
+                        const float Ss = sl == 0 ? S[0] : (sl == 1 ? S[1] : (sl == 2 ? S[2] : S[3]));
+                        gc[cm[i] * 32 + lane] = Ss - gx[i];
+                        atomicAdd(&gw[cm[i] * 32 + lane], gx[i] * ll[i]);
+                        acc_wr0 = fmaf(u0 * gx[i], y1[i], acc_wr0);
+                        acc_wr1 = fmaf(u1 * gx[i], y2[i], acc_wr1);
+                        nq_st1(tA1 + cm[i], __fadd_rn(pa[i], w0 * gx[i]));
+                        nq_st1(tA2 + cm[i], w1 * gx[i]);
+                    }
+                });
             }
             const int nx = nq::sched_ext_cnt[mem];
 #pragma unroll 1
-            for (int t = 0; t < nx; ++t) {
-                const int x = nq::sched_ext[mem][t], m = EC + x;
-                const float gx = ae[a0 + x * 32 + lane];
-                atomicAdd(&gw[m * 32 + lane], gx * __ldg(x0 + 32 * m));
-                acc_wr0 += (l >= 2) ? gx * __ldg(xm1 + 32 * m) : 0.0f;
-                acc_wr1 += (l >= 3) ? gx * __ldg(xm2 + 32 * m) : 0.0f;
-                ae[a1 + x * 32 + lane] += w0 * gx;
-                ae[a2 + x * 32 + lane] = w1 * gx;
+            for (int t = 0; t < nx; t += 4) {
+                float ll[4], y1[4], y2[4];
+                int xs[4];
+                static_for<0, 4>([&](auto ic) {
+                    constexpr int i = decltype(ic)::value;
+                    xs[i] = nq::sched_ext[mem][t + i < nx ? t + i : t];
+                    ll[i] = __ldg(x0 + 32 * (EC + xs[i]));
+                    y1[i] = __ldg(xm1 + 32 * (EC + xs[i]));
+                    y2[i] = __ldg(xm2 + 32 * (EC + xs[i]));
+                });
+                static_for<0, 4>([&](auto ic) {
+                    constexpr int i = decltype(ic)::value;
+                    if (t + i < nx) {
+                        const float gx = ae[a0 + xs[i] * 32 + lane];
+                        atomicAdd(&gw[(EC + xs[i]) * 32 + lane], gx * ll[i]);
+                        acc_wr0 = fmaf(u0 * gx, y1[i], acc_wr0);
+                        acc_wr1 = fmaf(u1 * gx, y2[i], acc_wr1);
+                        ae[a1 + xs[i] * 32 + lane] += w0 * gx;
+                        ae[a2 + xs[i] * 32 + lane] = w1 * gx;
+                    }
+                });
             }
             nq_group_sync(grp);
             { const uint32_t t = tA0; tA0 = tA1; tA1 = tA2; tA2 = t; }
