@@ -210,9 +210,14 @@ class LDPCNeuralDecoder(nn.Module):
         raise ValueError(f"tensor has {t.shape[1]} columns; expected {self.num_nodes} edges"
                          + ("" if self.edge_to_var is None else f" or {self.var_first_edge.numel()} variables"))
 
+    def _weights(self):
+        """(w_ch (E,), w_res (L,)) the iterations use; TiedNeuralLDPCDecoder expands its per-base-edge weights here."""
+        return self.residual_layer.w_ch, self.residual_layer.w_res
+
     def _messages(self, llr_e, check_index_tensor, var_index_tensor):
         """Last check-to-variable messages after num_iterations unrolled iterations."""
         res = self.residual_layer
+        w_ch_t, w_res_t = self._weights()
         queue = []                                            # most recent first
         x = llr_e
         c2v = None
@@ -222,10 +227,15 @@ class LDPCNeuralDecoder(nn.Module):
                 break
             prev = queue[:self.depth_L]
             if self.fused:
-                x = _NeuralVariableFn.apply(llr_e, c2v, var_index_tensor, res.w_ch, res.w_res[:len(prev)], *prev)
+                x = _NeuralVariableFn.apply(llr_e, c2v, var_index_tensor, w_ch_t, w_res_t[:len(prev)], *prev)
             else:
                 s = self.variable_layer(torch.zeros_like(c2v), c2v, var_index_tensor)
-                x = res(llr_e, s, prev)
+                if w_ch_t is res.w_ch:
+                    x = res(llr_e, s, prev)
+                else:                      # ResidualLayer.forward (layers.py:143-168) with the expanded weights
+                    x = llr_e * w_ch_t.unsqueeze(0) + s
+                    for i, pm in enumerate(prev):
+                        x = x + w_res_t[i] * pm
             queue.insert(0, x)
         return c2v
 
@@ -238,8 +248,9 @@ class LDPCNeuralDecoder(nn.Module):
         code = _qc_code_for(check_index_tensor, var_index_tensor, E) if (self.qc and self.depth_L <= 2) else None
         if code is not None:
             # the tables are create_LLR_mapping's for 5G BG2 Z=32: neighbours come from the base graph (no index loads)
-            w_ch = res.w_ch.detach().to(torch.float32).contiguous()
-            w_res = res.w_res.detach().to(torch.float32).contiguous()
+            w_ch_t, w_res_t = self._weights()
+            w_ch = w_ch_t.detach().to(torch.float32).contiguous()
+            w_res = w_res_t.detach().to(torch.float32).contiguous()
             y = gt_e.detach().to(torch.float32).contiguous() if gt_e is not None else None
             soft = torch.empty_like(llr_c)
             ml = torch.empty(B, dtype=torch.float32, device=llr_c.device) if y is not None else None
@@ -251,8 +262,9 @@ class LDPCNeuralDecoder(nn.Module):
             return soft, ml
         cp, cperm, ccnt = packed_index(check_index_tensor).sorted()
         vp, vperm, vcnt = packed_index(var_index_tensor).sorted()
-        w_ch = res.w_ch.detach().to(torch.float32).contiguous()
-        w_res = res.w_res.detach().to(torch.float32).contiguous()
+        w_ch_t, w_res_t = self._weights()
+        w_ch = w_ch_t.detach().to(torch.float32).contiguous()
+        w_res = w_res_t.detach().to(torch.float32).contiguous()
         y = gt_e.detach().to(torch.float32).contiguous() if gt_e is not None else None
         soft = torch.empty_like(llr_c)
         ml = torch.empty(B, dtype=torch.float32, device=llr_c.device) if y is not None else None
@@ -279,8 +291,8 @@ class LDPCNeuralDecoder(nn.Module):
             code = _qc_code_for(check_index_tensor, var_index_tensor, self.num_nodes)
         if code is not None:
             # training on the QC structure: one forward kernel that saves the CheckLayer inputs + one backward kernel
-            res = self.residual_layer
-            soft, max_loss = _NeuralQcTrainFn.apply(llr_e, gt_e, res.w_ch, res.w_res, code, self.num_iterations, self.depth_L)
+            w_ch_t, w_res_t = self._weights()
+            soft, max_loss = _NeuralQcTrainFn.apply(llr_e, gt_e, w_ch_t, w_res_t, code, self.num_iterations, self.depth_L)
         elif self.fused and not needs_grad and self.num_nodes < 0xFFFF and self.depth_L <= 4:
             soft, max_loss = self._forward_one_kernel(llr_e, check_index_tensor, var_index_tensor, gt_e)
         else:
@@ -294,5 +306,53 @@ class LDPCNeuralDecoder(nn.Module):
     @torch.no_grad()
     def decode(self, input_llr, check_index_tensor, var_index_tensor):
         """Hard decisions with the reference's rule `soft_bits > 0.5` (trainer.py:186)."""
+        soft, _ = self.forward(input_llr, check_index_tensor, var_index_tensor)
+        return (soft > 0.5).float()
+
+
+class TiedNeuralLDPCDecoder(LDPCNeuralDecoder):
+    """`TiedNeuralLDPCDecoder(base_graph, Z, num_iterations, depth_L)` -- the second class main.py:6,73-79 and
+    run_comparison_all.py:21 import from the reference's missing models/decoder.py.  No definition, prototype or test of it
+    exists in the reference; its constructor (a base graph and a lifting factor instead of an edge count) and the paper the
+    project follows (Deep Neural Network Based Decoding of Short 5G LDPC Codes: "the weights are tied over the Z copies of
+    a base-graph edge") fix what it must be: LDPCNeuralDecoder whose channel weights are ONE trainable value per base-graph
+    edge, shared by its Z lifted edges.  Everything else -- layers, composition, call shape -- is the parent's, so it
+    runs on the same kernels (the QC-structured ones at BG2 Z=32); the gradient of a tied weight is the sum over its Z
+    edges (autograd of the expansion).
+
+    The index tensors may be omitted in forward()/decode(): the decoder owns the code and builds create_LLR_mapping's
+    tables once (a reference-style caller passing its own tables gets the usual checks)."""
+
+    def __init__(self, base_graph, Z, num_iterations=5, depth_L=2, fused=True, qc=True):
+        from ..utils.ldpc_utils import QCCode, create_LLR_mapping
+        code = base_graph if isinstance(base_graph, QCCode) else QCCode.from_base_matrix(base_graph, Z)
+        _, cidx, vidx, oidx = create_LLR_mapping(code.dense().T)
+        super().__init__(code.E, num_iterations, depth_L, output_index_tensor=oidx, fused=fused, qc=qc)
+        self.code = code
+        # base edge (cell) of every lifted edge in the variable-major numbering: edges of variable j*Z + r are consecutive,
+        # in ascending base row, so the k-th edge of a variable of base column j is cell D_j + k
+        deg = (code.shifts >= 0).sum(axis=0)
+        d0 = [0]
+        for d in deg[:-1]:
+            d0.append(d0[-1] + int(d))
+        cell = torch.cat([torch.arange(int(deg[j])).repeat(code.Z) + d0[j] for j in range(code.cols)]).to(torch.int64)
+        self.register_buffer("edge_cell", cell, persistent=False)
+        self.register_buffer("check_index_tensor", cidx, persistent=False)
+        self.register_buffer("var_index_tensor", vidx, persistent=False)
+        # the parent's per-edge weight is replaced by the tied one (the parameter list holds the tied weights only)
+        del self.residual_layer.w_ch
+        self.residual_layer.w_ch = None
+        self.w_ch_tied = nn.Parameter(torch.ones(code.base_edges))
+
+    def _weights(self):
+        return self.w_ch_tied.index_select(0, self.edge_cell), self.residual_layer.w_res
+
+    def forward(self, input_llr, check_index_tensor=None, var_index_tensor=None, ground_truth=None):
+        c = self.check_index_tensor if check_index_tensor is None else check_index_tensor
+        v = self.var_index_tensor if var_index_tensor is None else var_index_tensor
+        return super().forward(input_llr, c, v, ground_truth)
+
+    @torch.no_grad()
+    def decode(self, input_llr, check_index_tensor=None, var_index_tensor=None):
         soft, _ = self.forward(input_llr, check_index_tensor, var_index_tensor)
         return (soft > 0.5).float()

@@ -293,3 +293,40 @@ def test_qc_structured_training_step_matches_the_per_layer_autograd(depth_L, ite
     assert float((gw_q - gw_t).abs().max()) <= 1e-4 * float(gw_t.abs().max())
     if depth_L:
         assert float((gr_q - gr_t).abs().max()) <= 1e-4 * max(float(gr_t.abs().max()), 1e-12), (gr_q, gr_t)
+
+
+@pytest.mark.parametrize("Z", [4, 32])
+def test_tied_decoder_equals_the_untied_one_with_expanded_weights(Z):
+    """TiedNeuralLDPCDecoder(base_graph, Z, iterations, depth_L) (main.py:73-79): one channel weight per base-graph edge.
+    Outputs equal LDPCNeuralDecoder with those weights copied to the Z lifted edges bit for bit; the gradient of a tied
+    weight is the sum of the gradients of its copies."""
+    from ldpc_b200.models import TiedNeuralLDPCDecoder
+    code = QCCode.nr_2_0(Z)
+    _, cidx, vidx, oidx = create_LLR_mapping(code.dense().T)
+    cidx, vidx = cidx.to(DEV), vidx.to(DEV)
+    rng = np.random.default_rng(Z)
+    B, iters, L = 37, 4, 2
+    tied = TiedNeuralLDPCDecoder(code.base_matrix(), Z, iters, L).to(DEV)
+    plain = LDPCNeuralDecoder(code.E, iters, L, output_index_tensor=oidx).to(DEV)
+    wt = torch.from_numpy((rng.random(code.base_edges) * 0.5 + 0.75).astype(np.float32)).to(DEV)
+    wr = torch.tensor([0.2, -0.1], device=DEV)
+    with torch.no_grad():
+        tied.w_ch_tied.copy_(wt)
+        tied.residual_layer.w_res.copy_(wr)
+        plain.residual_layer.w_ch.copy_(wt[tied.edge_cell])
+        plain.residual_layer.w_res.copy_(wr)
+    assert {n for n, _ in tied.named_parameters()} == {"w_ch_tied", "residual_layer.w_res"}
+    llr = torch.from_numpy((rng.normal(size=(B, code.N)) * 0.3 + 0.1).astype(np.float32)).to(DEV)     # variable-space input
+    gt = torch.from_numpy((rng.random((B, code.N)) < 0.6).astype(np.float32)).to(DEV)
+    s_t, m_t = tied(llr, ground_truth=gt)                       # tables owned by the decoder
+    s_p, m_p = plain(llr, cidx, vidx, gt)
+    assert s_t.shape == (B, code.N) and torch.equal(s_t.detach(), s_p.detach()) and torch.equal(m_t.detach(), m_p.detach())
+    m_t.mean().backward()
+    m_p.mean().backward()
+    want = torch.zeros(code.base_edges, device=DEV).index_add_(0, tied.edge_cell, plain.residual_layer.w_ch.grad)
+    assert float(want.abs().max()) > 0
+    assert float((tied.w_ch_tied.grad - want).abs().max()) <= 1e-5 * float(want.abs().max())
+    assert torch.allclose(tied.residual_layer.w_res.grad, plain.residual_layer.w_res.grad, rtol=1e-5, atol=1e-8)
+    with torch.no_grad():
+        assert torch.equal(tied.decode(llr), plain.decode(llr, cidx, vidx))
+        assert torch.equal(tied(llr, cidx, vidx)[0], s_p.detach())           # reference-style call with explicit tables

@@ -22,7 +22,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--frames4", type=float, default=1e9, help="total frames of config 4 (all SNR points)")
 ap.add_argument("--frames2", type=int, default=1 << 20)
 ap.add_argument("--gnn-batch", type=int, default=1 << 15)
-ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "r1_configs.json"))
+ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "r2_configs.json"))
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 res = {"gpu": torch.cuda.get_device_name(0), "host_cores": os.cpu_count()}
