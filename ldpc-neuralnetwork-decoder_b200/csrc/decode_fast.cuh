@@ -24,6 +24,8 @@ inline bool table_matches(const ldpc_code* c) {
 inline int detect_fast_kind(const ldpc_code* c) {
     if (table_matches<BG2Z32>(c)) return 1;
     if (table_matches<BG2Z4>(c)) return 2;
+    if (table_matches<BG2Z16>(c)) return 3;
+    if (table_matches<BG2Z8>(c)) return 4;
     return 0;
 }
 

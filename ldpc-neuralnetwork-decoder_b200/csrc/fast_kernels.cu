@@ -43,9 +43,13 @@ int launch_fast(const ldpc_code* c, int algo, const DecodeParams& p, cudaStream_
     if (algo == LDPC_ALGO_MINSUM) {
         if (c->fast_kind == 1) return launch_fast_inst<BG2Z32, LDPC_ALGO_MINSUM>(p, st);
         if (c->fast_kind == 2) return launch_fast_inst<BG2Z4, LDPC_ALGO_MINSUM>(p, st);
+        if (c->fast_kind == 3) return launch_fast_inst<BG2Z16, LDPC_ALGO_MINSUM>(p, st);
+        if (c->fast_kind == 4) return launch_fast_inst<BG2Z8, LDPC_ALGO_MINSUM>(p, st);
     } else {
         if (c->fast_kind == 1) return launch_fast_inst<BG2Z32, LDPC_ALGO_BP>(p, st);
         if (c->fast_kind == 2) return launch_fast_inst<BG2Z4, LDPC_ALGO_BP>(p, st);
+        if (c->fast_kind == 3) return launch_fast_inst<BG2Z16, LDPC_ALGO_BP>(p, st);
+        if (c->fast_kind == 4) return launch_fast_inst<BG2Z8, LDPC_ALGO_BP>(p, st);
     }
     return fail(LDPC_ERR_UNSUPPORTED, "fast path: code is not one of the compiled tables");
 }

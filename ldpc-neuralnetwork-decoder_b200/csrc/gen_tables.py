@@ -124,6 +124,8 @@ def main():
             "#pragma once", "", "namespace ldpc {", ""]
     text.append(emit("BG2Z32", rows, cols, cells, 32))
     text.append(emit("BG2Z4", rows, cols, cells, 4))
+    text.append(emit("BG2Z16", rows, cols, cells, 16))          # the reference's default --lifting_factor (main.py:38)
+    text.append(emit("BG2Z8", rows, cols, cells, 8))
     text.append("}  // namespace ldpc")
     new = "\n".join(text) + "\n"
     old = open(DST).read() if os.path.exists(DST) else None

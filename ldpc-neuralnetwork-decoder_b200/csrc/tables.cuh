@@ -60,7 +60,7 @@ struct ldpc_code {
     int slot = -1;                 // constant slot, -1 = global only
     uint32_t* d_tab = nullptr;     // global copy (always present)
     int tab_words = 0;
-    int fast_kind = 0;             // 0 none, 1 = 5G BG2 set 0 at Z=32 (the NR_2_0_32 table)
+    int fast_kind = 0;             // 0 none; 5G BG2 set 0 at Z = 32 (1, the NR_2_0_32 table), 4 (2), 16 (3), 8 (4)
     std::vector<uint32_t> h_tab;
     std::vector<int16_t> shifts;   // rows*cols
     mutable HostStage stage;

@@ -103,7 +103,8 @@ def test_reference_early_stopping_rule():
 
 # ---- seeded inputs against the oracle ------------------------------------------------------
 @pytest.mark.parametrize("Z,B,iters,snr_db,alpha", [(32, 97, 10, -2.0, 0.75), (32, 33, 3, -3.0, 0.8), (4, 1001, 5, 2.0, 0.75),
-                                                     (4, 5, 7, -4.0, 0.9), (32, 1, 1, 0.0, 0.75), (16, 40, 6, -1.0, 0.75)])
+                                                     (4, 5, 7, -4.0, 0.9), (32, 1, 1, 0.0, 0.75), (16, 40, 6, -1.0, 0.75),
+                                                     (16, 515, 10, -2.0, 0.75), (8, 129, 8, -1.5, 0.8), (2, 64, 5, 1.0, 0.75)])
 def test_minsum_paths_vs_oracle(Z, B, iters, snr_db, alpha):
     code = QCCode.nr_2_0(Z)
     llr = oracle.awgn_llr(None, B, code.N, snr_db, seed=Z * 1000 + B)
@@ -115,7 +116,18 @@ def test_minsum_paths_vs_oracle(Z, B, iters, snr_db, alpha):
         soft, hard = run(MinSumScaledDecoder(code, iters, alpha, early_stopping=False, path="fast"), llr)
         assert np.array_equal(soft, of["beliefs"]) and np.array_equal(hard, of["hard"])
     else:
-        assert Z == 16
+        assert Z == 2                                    # every other lifting size of BG2 set 0 (4, 8, 16, 32) is specialised
+    assert code.has_fast_path(dev()) == (Z in (4, 8, 16, 32))
+    if Z in (8, 16):                                     # sum-product on the new specialisations: decisions equal the oracle's
+        ob = oracle.decode(code.shifts, Z, llr, iters, "bp")
+        _, hb = run(BeliefPropagationDecoder(code, iters, early_stopping=False, path="fast"), llr)
+        assert (hb != ob["hard"]).mean() <= 1e-4
+        # and the fused simulation (on-chip channel) runs on them too
+        from ldpc_b200.sim import simulate_fer
+        pt = simulate_fer(code, [snr_db], 4096, iters=iters, alpha=alpha, seed=3, device=dev())[0]
+        llr2 = oracle.awgn_llr(None, 4096, code.N, snr_db, 3)
+        o2 = oracle.decode(code.shifts, Z, llr2, iters, "minsum", alpha, order="fast")
+        assert abs(pt["frame_errors"] - int((o2["hard"].sum(axis=1) > 0).sum())) <= max(2, 0.002 * 4096)
 
 
 def test_exact_zeros_ties_and_negative_zero():
