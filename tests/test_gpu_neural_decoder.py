@@ -330,3 +330,33 @@ def test_tied_decoder_equals_the_untied_one_with_expanded_weights(Z):
     with torch.no_grad():
         assert torch.equal(tied.decode(llr), plain.decode(llr, cidx, vidx))
         assert torch.equal(tied(llr, cidx, vidx)[0], s_p.detach())           # reference-style call with explicit tables
+
+
+def test_qc_structured_kernels_against_the_reference_layers_at_z32():
+    """tests/golden/neural_decoder_z32.npz: the reference's OWN CheckLayer / VariableLayer / ResidualLayer / OutputLayer objects in
+    the decoder's composition on BG2 Z=32 (5 iterations, L = 2; oracle/make_golden.py:neural_decoder), forward and autograd of
+    loss.mean().  The QC-structured forward and backward kernels against it: soft outputs and max loss to 1e-5, parameter
+    gradients to 1e-4 -- the same criteria the table-driven path meets on the Z=4 fixture."""
+    g = load_golden("neural_decoder_z32")
+    code = QCCode.nr_2_0(32)
+    _, cidx, vidx, _ = create_LLR_mapping(code.dense().T)
+    cidx, vidx = cidx.to(DEV), vidx.to(DEV)
+    dec = LDPCNeuralDecoder(code.E, int(g["iters"]), int(g["depth_L"])).to(DEV)
+    with torch.no_grad():
+        dec.residual_layer.w_ch.copy_(torch.from_numpy(g["w_ch"]))
+        dec.residual_layer.w_res.copy_(torch.from_numpy(g["w_res"]))
+    x = torch.from_numpy(g["llr_e"]).to(DEV)
+    y = torch.from_numpy(np.unpackbits(g["gt_e"], axis=1)[:, :code.E].astype(np.float32)).to(DEV)
+    n0 = ldpc_b200._native.lib().ldpc_launch_count()
+    soft, ml = dec(x, cidx, vidx, y)
+    ml.mean().backward()                                             # trainer.py:105-107
+    assert ldpc_b200._native.lib().ldpc_launch_count() - n0 == 2      # QC forward + QC backward, nothing else
+    np.testing.assert_allclose(soft.detach().cpu().numpy(), g["soft"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(ml.detach().cpu().numpy(), g["max_loss"], rtol=1e-5)
+    gw, gr = dec.residual_layer.w_ch.grad.cpu().numpy(), dec.residual_layer.w_res.grad.cpu().numpy()
+    assert np.count_nonzero(g["grad_wch"]) > 0
+    np.testing.assert_allclose(gw, g["grad_wch"], rtol=1e-4, atol=1e-4 * np.abs(g["grad_wch"]).max())
+    np.testing.assert_allclose(gr, g["grad_wres"], rtol=1e-4, atol=1e-4 * np.abs(g["grad_wres"]).max())
+    with torch.no_grad():                                            # inference launch of the same kernel
+        s2, m2 = dec(x, cidx, vidx, y)
+    assert torch.equal(s2, soft.detach()) and torch.equal(m2, ml.detach())
