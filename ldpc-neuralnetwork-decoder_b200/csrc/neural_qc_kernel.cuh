@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(kNqThreads, 1) neural_qc_kernel(const NeuralQc
         nq_group_sync(grp);
 
         // ---- phase A: CheckLayer on the current x; one body per row shape ----
-        auto row_body = [&](auto ncc, auto nec, int row, bool last) {
+        auto row_body = [&](auto ncc, auto nec, int row, bool last, float* save) {
             constexpr int NC = decltype(ncc)::value, NE = decltype(nec)::value, d = NC + NE;
             float v[d], a[d];
             unsigned sb[d];
@@ -152,15 +152,19 @@ __global__ void __launch_bounds__(kNqThreads, 1) neural_qc_kernel(const NeuralQc
                 nq_ld1_issue(tXc + cell[k], v[k]);
             });
             nq_wait_ld();
+            static_for<0, NC>([&](auto kc) { nq_tie(v[decltype(kc)::value]); });
+            // training forward: this CheckLayer's input as [cell][lane] (one coalesced 128-byte line per cell; every cell
+            // belongs to exactly one row) -- the layout the backward kernel reads back without a transposing tile
+            if (save) static_for<0, NC>([&](auto kc) { save[32 * cell[decltype(kc)::value]] = v[decltype(kc)::value]; });
             static_for<0, NC>([&](auto kc) {
                 constexpr int k = decltype(kc)::value;
-                nq_tie(v[k]);
                 v[k] = __shfl_sync(kFull, v[k], lane + sft[k]);           // variable (r + s) mod 32 -> check row r
             });
             int xs = 0;
             if constexpr (NE) {
                 xs = nq::row_ext[row];
                 v[NC] = xe0[xc_off + xs * 32 + lane];
+                if (save) save[32 * (EC + xs)] = v[NC];
             }
             unsigned nb = 0;
             int zc = 0;
@@ -197,13 +201,13 @@ __global__ void __launch_bounds__(kNqThreads, 1) neural_qc_kernel(const NeuralQc
                 }
             });
         };
-        auto phase_a = [&](bool last) {
+        auto phase_a = [&](bool last, float* save) {
             static_for<0, nq::kRowClasses>([&](auto cc) {
                 constexpr int c = decltype(cc)::value;
                 const int t1 = nq::sched_row_ptr[mem][c + 1];
 #pragma unroll 1
                 for (int t = nq::sched_row_ptr[mem][c]; t < t1; ++t)
-                    row_body(IC<kNqRowNc[c]>{}, IC<kNqRowNe[c]>{}, (int)nq::sched_rows[mem][t], last);
+                    row_body(IC<kNqRowNc[c]>{}, IC<kNqRowNe[c]>{}, (int)nq::sched_rows[mem][t], last, save);
             });
         };
 
@@ -282,23 +286,9 @@ __global__ void __launch_bounds__(kNqThreads, 1) neural_qc_kernel(const NeuralQc
         };
 
         for (int l = 0; l < p.iters; ++l) {
-            if (p.save_x && live) {
-                // training forward: the input of this CheckLayer as [cell][lane] (one coalesced 128-byte line per cell) --
-                // the layout the backward kernel reads back without a transposing tile
-                float* dst = p.save_x + ((long long)l * p.B + cw) * E + lane;
-                for (int m0 = mem * 4; m0 < EC; m0 += nq::kMembers * 4) {
-                    float xv[4];
-                    static_for<0, 4>([&](auto ic) { if (m0 + decltype(ic)::value < EC) nq_ld1_issue(tXc + m0 + decltype(ic)::value, xv[decltype(ic)::value]); });
-                    nq_wait_ld();
-                    static_for<0, 4>([&](auto ic) {
-                        constexpr int i = decltype(ic)::value;
-                        if (m0 + i < EC) { nq_tie(xv[i]); dst[32 * (m0 + i)] = xv[i]; }
-                    });
-                }
-                for (int x = mem; x < NX; x += nq::kMembers) dst[32 * (EC + x)] = xe0[xc_off + x * 32 + lane];
-            }
+            float* save = (p.save_x && live) ? p.save_x + ((long long)l * p.B + cw) * E + lane : nullptr;
             const bool last = l == p.iters - 1;
-            phase_a(last);
+            phase_a(last, save);
             nq_group_sync(grp);
             if (last) break;
             // queue of earlier outputs (models/decoder.py): x_0 is not an entry, so the first update has no residual term
