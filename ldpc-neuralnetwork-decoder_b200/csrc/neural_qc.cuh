@@ -20,6 +20,9 @@
 //     pitch-33 shared-memory tile.
 // The Python layer (models/decoder.py) takes this path only after checking that the caller's index tensors ARE
 // those tables; anything else runs the table-driven kernels.
+// One documented difference: a residual term that is not yet a queue entry (first one or two updates) is multiplied by a
+// zero weight here instead of being skipped, so +-inf / NaN channel LLRs turn into NaN one update earlier than in the
+// layer chain; finite inputs are unaffected (bit-identical).
 #pragma once
 #include <math_constants.h>
 

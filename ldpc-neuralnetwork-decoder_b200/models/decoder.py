@@ -103,7 +103,8 @@ class _NeuralVariableFn(torch.autograd.Function):
 # The kernel implies the neighbour tables from the base graph, so it may only run when the caller's tables ARE the ones
 # create_LLR_mapping produces for that code.  Checked once per (tensor, version); canonical tables built once per device.
 _QC_CANON = {}      # device index -> (QCCode, check table, var table)
-_QC_SEEN = {}       # (data_ptr, version, shape, data_ptr, version, shape) -> bool
+_QC_SEEN = []       # [(check tensor, its version, var tensor, its version, ok)], most recent first; the tensors are held so that
+                    # their addresses cannot be reused by other data while the verdict is cached
 
 
 def _qc_code_for(check_index_tensor, var_index_tensor, num_nodes):
@@ -116,13 +117,14 @@ def _qc_code_for(check_index_tensor, var_index_tensor, num_nodes):
         code = QCCode.nr_2_0(32)
         _, c, v, _ = create_LLR_mapping(code.dense().T)
         canon = _QC_CANON[dev.index] = (code, c.to(dev), v.to(dev))
-    key = (check_index_tensor.data_ptr(), check_index_tensor._version, var_index_tensor.data_ptr(), var_index_tensor._version)
-    ok = _QC_SEEN.get(key)
-    if ok is None:
-        ok = bool(torch.equal(check_index_tensor.to(torch.int64), canon[1]) and torch.equal(var_index_tensor.to(torch.int64), canon[2]))
-        if len(_QC_SEEN) > 64:
-            _QC_SEEN.clear()
-        _QC_SEEN[key] = ok
+    for i, (ct, cv, vt, vv, ok) in enumerate(_QC_SEEN):
+        if ct is check_index_tensor and vt is var_index_tensor and cv == ct._version and vv == vt._version:
+            if i:
+                _QC_SEEN.insert(0, _QC_SEEN.pop(i))
+            return canon[0] if ok else None
+    ok = bool(torch.equal(check_index_tensor.to(torch.int64), canon[1]) and torch.equal(var_index_tensor.to(torch.int64), canon[2]))
+    _QC_SEEN.insert(0, (check_index_tensor, check_index_tensor._version, var_index_tensor, var_index_tensor._version, ok))
+    del _QC_SEEN[8:]
     return canon[0] if ok else None
 
 
