@@ -45,6 +45,7 @@ struct ldpc_gnn {
     int* d_chk_ptr = nullptr;     // [M+1] (messages of a check are contiguous)
     float* d_packed = nullptr;    // per-call repacked weights (layers * kPackedPerLayer floats)
     float* d_emb = nullptr;       // per-call 16-byte aligned copy of the type embeddings [layers][types][h]
+    void* d_tc16 = nullptr;       // per-call fp16 hi/lo images of the edge kernel's weights (gnn_tc.cuh, kTc16PerLayer halves per layer)
     float* d_tc = nullptr;        // per-call tf32 hi/lo weight images in the tensor-core operand layout (gnn_tc.cuh)
     int* d_status = nullptr;      // set to 1 if a tensor-core kernel timed out waiting for its MMAs
     size_t params = 0;

@@ -24,6 +24,8 @@
 // Shared memory: W1A hi/lo 64 KB + W2 hi/lo 64 KB + A region hi/lo 64 KB + staging 32 KB = 224 KB, TMEM 256 columns.
 // The node kernel (Pv / Pc) has the same shape with a single GEMM per 128-node tile.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "gnn.cuh"
 
 namespace ldpc {
@@ -42,6 +44,10 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint
 // instruction descriptor: D = F32, A = B = TF32, both K-major, M = 128
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+// the same with A = B = F16 (format 0)
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -113,10 +119,23 @@ __device__ __forceinline__ void put_chunk(uint8_t* hi, uint8_t* lo, int r, int c
 constexpr int kTcW1A = 0, kTcW2 = kTcW1A + 2 * 128 * 64, kTcW1BV = kTcW2 + 2 * 64 * 128, kTcW1BC = kTcW1BV + 2 * 64 * 64,
               kTcW2T = kTcW1BC + 2 * 64 * 64, kTcW1AT = kTcW2T + 2 * 128 * 64, kTcW1BVT = kTcW1AT + 2 * 64 * 128,
               kTcW1BCT = kTcW1BVT + 2 * 64 * 64, kTcPerLayer = kTcW1BCT + 2 * 64 * 64;      // + W1B transposed (dm = dP . W1B)
-__global__ void gnn_pack_tc_kernel(const float* __restrict__ packed, float* __restrict__ tc) {
+// fp16 two-way split images of the edge kernel's weights (gnn_tc_pipe.cuh, kF16): w = hi + lo with hi = fp16(w), lo = fp16(w - hi);
+// canonical K-major layout for 16-bit elements: core matrix = 8 rows x 8 elements (16 B).  Per layer (halves):
+// W1A [128 x 64] hi, lo | W2 [64 x 128] hi, lo = 64 KB, half of the TF32 images.
+__host__ __device__ constexpr uint32_t canon_off16(int r, int k, int K) {
+    return (uint32_t)((r >> 3) * (K / 8) * 128 + (k >> 3) * 128 + (r & 7) * 16 + (k & 7) * 2);
+}
+constexpr int kTc16W1A = 0, kTc16W2 = 2 * 128 * 64, kTc16PerLayer = kTc16W2 + 2 * 64 * 128;
+__global__ void gnn_pack_tc_kernel(const float* __restrict__ packed, float* __restrict__ tc, __half* __restrict__ tc16) {
     const int l = blockIdx.y;
     const float* pk = packed + (size_t)l * kPackedPerLayer;
     float* o = tc + (size_t)l * kTcPerLayer;
+    __half* o16 = tc16 + (size_t)l * kTc16PerLayer;
+    auto put16 = [&](__half* base, int rows, int K, int r, int k, float w) {
+        const __half h = __float2half_rn(w);
+        base[canon_off16(r, k, K) / 2] = h;
+        base[rows * K + canon_off16(r, k, K) / 2] = __float2half_rn(w - __half2float(h));
+    };
     auto put = [&](float* base, int rows, int K, int r, int k, float w) {
         const float h = tf32_hi(w);
         base[canon_off(r, k, K) / 4] = h;
@@ -125,6 +144,8 @@ __global__ void gnn_pack_tc_kernel(const float* __restrict__ packed, float* __re
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < 128 * 64; t += gridDim.x * blockDim.x) {
         put(o + kTcW1A, 128, 64, t / 64, t % 64, pk[kPkW1A + t]);                   // W1A[n][k], n < 128
         put(o + kTcW2, 64, 128, t / 128, t % 128, pk[kPkW2 + t]);                    // W2[n][k], k < 128
+        put16(o16 + kTc16W1A, 128, 64, t / 64, t % 64, pk[kPkW1A + t]);
+        put16(o16 + kTc16W2, 64, 128, t / 128, t % 128, pk[kPkW2 + t]);
         put(o + kTcW2T, 128, 64, t % 128, t / 128, pk[kPkW2 + t]);                   // W2T[k][n] = W2[n][k]
         put(o + kTcW1AT, 64, 128, t % 64, t / 64, pk[kPkW1A + t]);                   // W1AT[k][n] = W1A[n][k]
         if (t < 64 * 64) {

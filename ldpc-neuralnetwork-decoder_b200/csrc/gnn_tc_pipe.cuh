@@ -46,6 +46,8 @@ constexpr int kPipeRowThreads = kPipeRowWarps * 32, kPipeLoaderThreads = kPipeLo
 constexpr size_t kPipeStage = 128 * 64 * sizeof(float);                        // 32 KB
 constexpr size_t kPipeSmem = (size_t)(2 * 128 * 64 + 2 * 64 * 128) * sizeof(float) + 3 * kPipeStage;   // 224 KB
 constexpr uint32_t kTmAcHi = 0, kTmAcLo = 64, kTmD1 = 128, kTmD2 = 128, kTmHHi = 256, kTmHLo = 384;
+// kF16 (fp16 two-way split operands, two k-values per 32-bit column): comb hi [0,32) lo [32,64), h hi [256,320) lo [320,384)
+constexpr uint32_t kTmAcLo16 = 32, kTmHLo16 = 320;
 
 enum PipeBar { kBarFullX = 0, kBarFreeX, kBarAReady, kBarD1Full, kBarFullP, kBarFreeP, kBarHReady, kBarD2Full, kBarFreeY,
                kBarD2Drained, kNumPipeBars };
@@ -90,6 +92,55 @@ __device__ __forceinline__ void umma_gemm3_ts(uint32_t d_tmem, uint32_t a_hi, ui
         acc = 1u;
     }
 }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+// fp16 two-way split (round 2): x = hi + lo, hi = fp16(x), lo = fp16(x - hi) -- 22 mantissa bits; hi.hi + hi.lo + lo.hi on
+// kind::f16 measured 4.3e-7 relative on the K = 64 product (3xTF32: 5.1e-7) at TWICE the tensor-pipe rate (773 vs 1 543
+// cycles for GEMM1, 1 079 vs 2 176 for GEMM2; tools/probe/umma_probe.cu), and the operands are half as wide.  Values must stay
+// below 65 504 (fp16 range); small values lose nothing that matters (lo becomes subnormal below |x| = 0.25: absolute 6e-8).
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "r"(a_tmem), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_gemm3_ts_f16(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, int K,
+                                                   uint32_t sbo_b, uint32_t idesc) {
+    uint32_t acc = 0u;
+    for (int ks = 0; ks < K / 16; ++ks) {
+        const uint32_t kb = (uint32_t)ks * 256u;                 // two 16-byte k-chunks (16 halves) of B per MMA; 8 TMEM columns of A
+        umma_f16_ts(d_tmem, a_lo + ks * 8, umma_desc(b_hi + kb, 128, sbo_b), idesc, acc);
+        umma_f16_ts(d_tmem, a_hi + ks * 8, umma_desc(b_lo + kb, 128, sbo_b), idesc, 1u);
+        umma_f16_ts(d_tmem, a_hi + ks * 8, umma_desc(b_hi + kb, 128, sbo_b), idesc, 1u);
+        acc = 1u;
+    }
+}
+// 16 consecutive k-values -> 8 packed columns of each image (k even in the low half)
+// hi is formed in fp32 with Veltkamp's splitting (t = x * (2^13 + 1); hi = t - (t - x): x rounded to 11 significant bits,
+// exactly representable in fp16 for |x| in the normal range), so that only the two packing conversions touch the
+// conversion pipe (cvt + unpack + cvt per pair made E1 slower than the TF32 truncation split: 2.5 k vs 1.4 k cycles per tile)
+#ifndef GNN_F16_VELTKAMP
+#define GNN_F16_VELTKAMP 1
+#endif
+__device__ __forceinline__ void split16_h(const float (&v)[16], uint32_t (&hi)[8], uint32_t (&lo)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+#if GNN_F16_VELTKAMP
+        const float a = v[2 * i], b = v[2 * i + 1];
+        const float ta = __fmul_rn(a, 8193.0f), tb = __fmul_rn(b, 8193.0f);
+        const float ha = __fsub_rn(ta, __fsub_rn(ta, a)), hb = __fsub_rn(tb, __fsub_rn(tb, b));
+        const __half2 h = __floats2half2_rn(ha, hb);
+        const __half2 l = __floats2half2_rn(__fsub_rn(a, ha), __fsub_rn(b, hb));
+#else
+        const __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+        const float2 hf = __half22float2(h);
+        const __half2 l = __floats2half2_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
+#endif
+        hi[i] = *reinterpret_cast<const uint32_t*>(&h);
+        lo[i] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+}
 // hi = x with the 13 low mantissa bits cleared (a TF32 value), lo = x - hi (exact; the tensor core reads its top 19
 // bits).  Truncation instead of cvt.rna costs 2 instructions per element instead of 8 (cvt.rna.tf32.f32 expands to
 // FSETP + VIADD + SEL + LOP3 on sm_100) and keeps the 3xTF32 product error at ~2^-20 relative.
@@ -120,7 +171,7 @@ __device__ __forceinline__ void split16(const float (&v)[16], uint32_t (&hi)[16]
 #define PIPE_TRACE_DUMP(role, nev)
 #endif
 
-template <bool kResidual>
+template <bool kResidual, bool kF16>
 __global__ void __launch_bounds__(kPipeThreads, 1) gnn_edge_pipe_kernel(
     const float* __restrict__ x, const float* __restrict__ emb_l, const float* __restrict__ packed_l, const float* __restrict__ tc_l,
     const int* __restrict__ edge_var, const int* __restrict__ edge_chk, const int* __restrict__ edge_type,
@@ -130,11 +181,16 @@ __global__ void __launch_bounds__(kPipeThreads, 1) gnn_edge_pipe_kernel(
     // message_gnn_decoder.py:46-47) is applied to the finished rows here -- dec_out[row] = <y_row, w_out> -- and y itself is
     // not written: saves the 256-byte row store and its re-read by the readout kernel.
     extern __shared__ __align__(1024) uint8_t tc_smem[];
-    uint8_t* W1Ahi = tc_smem;                               // [128 x 64]
-    uint8_t* W1Alo = W1Ahi + 128 * 64 * 4;
-    uint8_t* W2hi = W1Alo + 128 * 64 * 4;                   // [64 x 128]
-    uint8_t* W2lo = W2hi + 64 * 128 * 4;
-    uint8_t* Sx = W2lo + 64 * 128 * 4;
+    constexpr int kWb = kF16 ? 2 : 4;                       // bytes per weight element (fp16 split images are half as large;
+    uint8_t* W1Ahi = tc_smem;                               // [128 x 64]         the staging tiles keep their offsets)
+    uint8_t* W1Alo = W1Ahi + 128 * 64 * kWb;
+    uint8_t* W2hi = W1Alo + 128 * 64 * kWb;                 // [64 x 128]
+    uint8_t* W2lo = W2hi + 64 * 128 * kWb;
+    uint8_t* Sx = tc_smem + (size_t)(2 * 128 * 64 + 2 * 64 * 128) * 4;
+    // kF16: the half of the weight region the fp16 images leave free holds a staging tile of its OWN for the outputs, so that
+    // the loaders may publish x(t+2) while y(t) is still being stored (with 3xTF32 weights y shares Sx and the two serialise:
+    // clock64 trace, FullX wait 600-1700 cycles per tile)
+    uint8_t* Sy = kF16 ? tc_smem + (size_t)(2 * 128 * 64 + 2 * 64 * 128) * 2 : Sx;
     uint8_t* Sp0 = Sx + kPipeStage;
     uint8_t* Sp1 = Sp0 + kPipeStage;
     __shared__ uint64_t bars[kNumPipeBars];
@@ -153,9 +209,10 @@ __global__ void __launch_bounds__(kPipeThreads, 1) gnn_edge_pipe_kernel(
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     {   // weights: canonical hi/lo images, contiguous in global memory in the same order as in shared memory
-        const float4* src = reinterpret_cast<const float4*>(tc_l + kTcW1A);
+        // (kF16: tc_l points at the layer's fp16 images, kTc16PerLayer halves)
+        const float4* src = reinterpret_cast<const float4*>(kF16 ? tc_l : tc_l + kTcW1A);
         float4* dst = reinterpret_cast<float4*>(tc_smem);
-        for (int t = tid; t < (2 * 128 * 64 + 2 * 64 * 128) / 4; t += kPipeThreads) dst[t] = src[t];
+        for (int t = tid; t < (2 * 128 * 64 + 2 * 64 * 128) * kWb / 16; t += kPipeThreads) dst[t] = src[t];
         if (tid < kH) b2s[tid] = packed_l[kPkB2 + tid];
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -190,10 +247,17 @@ __global__ void __launch_bounds__(kPipeThreads, 1) gnn_edge_pipe_kernel(
                     const float4 t = *stage_ptr(Sx, rowi, (col >> 2) + q);
                     v[q * 4] = t.x; v[q * 4 + 1] = t.y; v[q * 4 + 2] = t.z; v[q * 4 + 3] = t.w;
                 }
-                uint32_t hi[16], lo[16];
-                split16(v, hi, lo);
-                tmem_st16(tmem + lane_base + kTmAcHi + col, hi);
-                tmem_st16(tmem + lane_base + kTmAcLo + col, lo);
+                if constexpr (kF16) {
+                    uint32_t hi[8], lo[8];
+                    split16_h(v, hi, lo);
+                    tmem_st8(tmem + lane_base + kTmAcHi + col / 2, hi);
+                    tmem_st8(tmem + lane_base + kTmAcLo16 + col / 2, lo);
+                } else {
+                    uint32_t hi[16], lo[16];
+                    split16(v, hi, lo);
+                    tmem_st16(tmem + lane_base + kTmAcHi + col, hi);
+                    tmem_st16(tmem + lane_base + kTmAcLo + col, lo);
+                }
             }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -222,6 +286,19 @@ __global__ void __launch_bounds__(kPipeThreads, 1) gnn_edge_pipe_kernel(
                     for (int q = 0; q < 4; ++q) { pa[q] = *stage_ptr(Sp, rowi, pch + q); pb[q] = *stage_ptr(Sp, rowi, pch + 4 + q); }
                     tmem_ld_wait(ha, hb);
                     auto finish = [&](uint32_t (&hh)[16], const float4 (&pp)[4], int cofs) {
+                        if constexpr (kF16) {
+                            float hv[16];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const float add[4] = {pp[q].x, pp[q].y, pp[q].z, pp[q].w};
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) hv[q * 4 + i] = fmaxf(__uint_as_float(hh[q * 4 + i]) + add[i], 0.f);
+                            }
+                            uint32_t hi[8], lo[8];
+                            split16_h(hv, hi, lo);
+                            tmem_st8(tmem + lane_base + kTmHHi + (col + cofs) / 2, hi);
+                            tmem_st8(tmem + lane_base + kTmHLo16 + (col + cofs) / 2, lo);
+                        } else {
                         uint32_t lo[16];
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
@@ -235,6 +312,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) gnn_edge_pipe_kernel(
                         }
                         tmem_st16(tmem + lane_base + kTmHHi + col + cofs, hh);
                         tmem_st16(tmem + lane_base + kTmHLo + col + cofs, lo);
+                        }
                     };
                     finish(ha, pa, 0);
                     finish(hb, pb, 16);
@@ -276,10 +354,10 @@ __global__ void __launch_bounds__(kPipeThreads, 1) gnn_edge_pipe_kernel(
                 tmem_ld_wait(oa, ob);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    *stage_ptr(Sx, rowi, (col >> 2) + q) = make_float4(__uint_as_float(oa[q * 4]), __uint_as_float(oa[q * 4 + 1]),
+                    *stage_ptr(Sy, rowi, (col >> 2) + q) = make_float4(__uint_as_float(oa[q * 4]), __uint_as_float(oa[q * 4 + 1]),
                                                                         __uint_as_float(oa[q * 4 + 2]), __uint_as_float(oa[q * 4 + 3]));
                     if constexpr (kPipeCw == 32)
-                        *stage_ptr(Sx, rowi, (col >> 2) + 4 + q) = make_float4(__uint_as_float(ob[q * 4]), __uint_as_float(ob[q * 4 + 1]),
+                        *stage_ptr(Sy, rowi, (col >> 2) + 4 + q) = make_float4(__uint_as_float(ob[q * 4]), __uint_as_float(ob[q * 4 + 1]),
                                                                                 __uint_as_float(ob[q * 4 + 2]), __uint_as_float(ob[q * 4 + 3]));
                 }
             }
@@ -291,7 +369,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) gnn_edge_pipe_kernel(
 #pragma unroll
             for (int it = 0; it < kStIters; ++it) {
                 const int rr = it * (kPipeRowThreads / 16) + cr0;
-                float4 r = *stage_ptr(Sx, rr, cc);
+                float4 r = *stage_ptr(Sy, rr, cc);
                 r.x += bias.x; r.y += bias.y; r.z += bias.z; r.w += bias.w;
                 if constexpr (kResidual) { r.x += xv[it].x; r.y += xv[it].y; r.z += xv[it].z; r.w += xv[it].w; }
                 if (dec_out) {                                           // warp-uniform
@@ -311,10 +389,11 @@ __global__ void __launch_bounds__(kPipeThreads, 1) gnn_edge_pipe_kernel(
     } else if (warp == kPipeMmaWarp) {
         // ================= MMA issue (one thread) =================
         if (lane == 0) {
-            constexpr uint32_t kIdesc128 = umma_idesc_tf32(128), kIdesc64 = umma_idesc_tf32(64);
+            constexpr uint32_t kIdesc128 = kF16 ? umma_idesc_f16(128) : umma_idesc_tf32(128), kIdesc64 = kF16 ? umma_idesc_f16(64) : umma_idesc_tf32(64);
             auto gemm1 = [&]() {
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                umma_gemm3_ts(tmem + kTmD1, tmem + kTmAcHi, tmem + kTmAcLo, smem_u32(W1Ahi), smem_u32(W1Alo), 64, 2048, kIdesc128);
+                if constexpr (kF16) umma_gemm3_ts_f16(tmem + kTmD1, tmem + kTmAcHi, tmem + kTmAcLo16, smem_u32(W1Ahi), smem_u32(W1Alo), 64, 1024, kIdesc128);
+                else umma_gemm3_ts(tmem + kTmD1, tmem + kTmAcHi, tmem + kTmAcLo, smem_u32(W1Ahi), smem_u32(W1Alo), 64, 2048, kIdesc128);
                 umma_commit(&bars[kBarD1Full]);
             };
             if (my_tiles > 0) { wait(kBarAReady, 0); if (ok) gemm1(); }
@@ -323,7 +402,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1) gnn_edge_pipe_kernel(
                 if (!ok) break;
                 PIPE_TRACE(0);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                umma_gemm3_ts(tmem + kTmD2, tmem + kTmHHi, tmem + kTmHLo, smem_u32(W2hi), smem_u32(W2lo), 128, 4096, kIdesc64);
+                if constexpr (kF16) umma_gemm3_ts_f16(tmem + kTmD2, tmem + kTmHHi, tmem + kTmHLo16, smem_u32(W2hi), smem_u32(W2lo), 128, 2048, kIdesc64);
+                else umma_gemm3_ts(tmem + kTmD2, tmem + kTmHHi, tmem + kTmHLo, smem_u32(W2hi), smem_u32(W2lo), 128, 4096, kIdesc64);
                 umma_commit(&bars[kBarD2Full]);
                 PIPE_TRACE(1);
                 if (k + 1 < my_tiles) {
@@ -417,7 +497,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1) gnn_edge_pipe_kernel(
             asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(smem_u32(&bars[kBarFullP])) : "memory");
             if (more) {
                 take_indices();                                               // of tile k+1, requested at the top
-                wait(kBarFreeX, (uint32_t)k); wait(kBarFreeY, (uint32_t)k + 1u);   // C(k) has read Sx and y(k-1) has left it
+                wait(kBarFreeX, (uint32_t)k);                                      // C(k) has read Sx ...
+                if constexpr (!kF16) wait(kBarFreeY, (uint32_t)k + 1u);             // ... and y(k-1) has left it (own tile with kF16)
                 if (!ok) break;
                 PIPE_TRACE(1);
                 publish_x();

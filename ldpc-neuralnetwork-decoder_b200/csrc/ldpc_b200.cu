@@ -726,6 +726,7 @@ int ldpc_gnn_create(const ldpc_code_t* code, int num_layers, int hidden, int num
               cudaMalloc(&g->d_packed, sizeof(float) * (size_t)num_layers * kPackedPerLayer) == cudaSuccess &&
               cudaMalloc(&g->d_emb, sizeof(float) * (size_t)num_layers * num_types * kH) == cudaSuccess &&
               cudaMalloc(&g->d_tc, sizeof(float) * (size_t)num_layers * kTcPerLayer) == cudaSuccess &&
+              cudaMalloc(&g->d_tc16, sizeof(__half) * (size_t)num_layers * kTc16PerLayer) == cudaSuccess &&
               cudaMalloc(&g->d_status, sizeof(int)) == cudaSuccess && cudaMemset(g->d_status, 0, sizeof(int)) == cudaSuccess;
     if (!ok) { ldpc_gnn_destroy(g); return fail(LDPC_ERR_CUDA, "gnn_create: device allocation failed: %s", cudaGetErrorString(cudaGetLastError())); }
     *out = g;
@@ -737,7 +738,7 @@ int ldpc_gnn_destroy(ldpc_gnn_t* g) {
     {
         DeviceGuard dg(g->device);
         cudaFree(g->d_edge_var); cudaFree(g->d_edge_chk); cudaFree(g->d_edge_type); cudaFree(g->d_var_ptr);
-        cudaFree(g->d_var_edge); cudaFree(g->d_chk_ptr); cudaFree(g->d_packed); cudaFree(g->d_emb); cudaFree(g->d_tc); cudaFree(g->d_status);
+        cudaFree(g->d_var_edge); cudaFree(g->d_chk_ptr); cudaFree(g->d_packed); cudaFree(g->d_emb); cudaFree(g->d_tc); cudaFree(g->d_tc16); cudaFree(g->d_status);
     }
     delete g;
     return LDPC_OK;
@@ -801,13 +802,15 @@ int ldpc_gnn_forward(const ldpc_gnn_t* g, const float* params, const float* llr,
     // LDPC_GNN_EDGE=serial selects the single-buffered edge kernel (gnn_tc.cuh) instead of the pipelined one (diagnostics)
     static const bool use_pipe = !(getenv("LDPC_GNN_EDGE") && getenv("LDPC_GNN_EDGE")[0] == 's');
     if (use_tc) {
-        gnn_pack_tc_kernel<<<dim3(16, g->layers), 256, 0, st>>>(g->d_packed, g->d_tc);
+        gnn_pack_tc_kernel<<<dim3(16, g->layers), 256, 0, st>>>(g->d_packed, g->d_tc, (__half*)g->d_tc16);
         LDPC_CHECK_LAUNCH("gnn_pack_tc_kernel");
         LDPC_CUDA(cudaFuncSetAttribute(gnn_edge_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEdgeTcSmem));
         LDPC_CUDA(cudaFuncSetAttribute(gnn_edge_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEdgeTcSmem));
         LDPC_CUDA(cudaFuncSetAttribute(gnn_node_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNodeTcSmem));
-        LDPC_CUDA(cudaFuncSetAttribute(gnn_edge_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmem));
-        LDPC_CUDA(cudaFuncSetAttribute(gnn_edge_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmem));
+        LDPC_CUDA(cudaFuncSetAttribute(gnn_edge_pipe_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmem));
+        LDPC_CUDA(cudaFuncSetAttribute(gnn_edge_pipe_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmem));
+        LDPC_CUDA(cudaFuncSetAttribute(gnn_edge_pipe_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmem));
+        LDPC_CUDA(cudaFuncSetAttribute(gnn_edge_pipe_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmem));
     }
     auto tc_grid = [](long long rows, int per_sm) {
         const long long tiles = (rows + 127) / 128, cap = (long long)kNumSMs * per_sm;
@@ -844,11 +847,23 @@ int ldpc_gnn_forward(const ldpc_gnn_t* g, const float* params, const float* llr,
                 fused_readout = use_pipe && !training && l == g->layers - 1;
                 const float* wo = fused_readout ? params + lay.out_w(l) : nullptr;
                 float* dec = fused_readout ? xb : nullptr;
-                if (use_pipe && l == 0)
-                    gnn_edge_pipe_kernel<false><<<tc_grid(bc * E, 1), kPipeThreads, kPipeSmem, st>>>(
+                // edge MLPs: 3xTF32 operands by default; LDPC_GNN_MMA=f16 selects the fp16 two-way split (gnn_tc_pipe.cuh: twice
+                // the tensor-pipe rate, half the operand footprint, 9.6e-6 instead of 1.8e-5 against the fp64 oracle -- and the
+                // SAME 28.0 ms per forward at B = 2048: the tile time is set by the row warps' instruction stream, not by the
+                // MMAs, so the range-safe form stays the default)
+                static const bool use_f16 = getenv("LDPC_GNN_MMA") && getenv("LDPC_GNN_MMA")[0] == 'f';
+                const float* tc16 = reinterpret_cast<const float*>((const __half*)g->d_tc16 + (size_t)l * kTc16PerLayer);
+                if (use_pipe && use_f16 && l == 0)
+                    gnn_edge_pipe_kernel<false, true><<<tc_grid(bc * E, 1), kPipeThreads, kPipeSmem, st>>>(
+                        xa, em, pk, tc16, g->d_edge_var, g->d_edge_chk, g->d_edge_type, pv, pc, bc, E, N, M, xb, wo, dec, g->d_status);
+                else if (use_pipe && use_f16)
+                    gnn_edge_pipe_kernel<true, true><<<tc_grid(bc * E, 1), kPipeThreads, kPipeSmem, st>>>(
+                        xa, em, pk, tc16, g->d_edge_var, g->d_edge_chk, g->d_edge_type, pv, pc, bc, E, N, M, xb, wo, dec, g->d_status);
+                else if (use_pipe && l == 0)
+                    gnn_edge_pipe_kernel<false, false><<<tc_grid(bc * E, 1), kPipeThreads, kPipeSmem, st>>>(
                         xa, em, pk, tcw, g->d_edge_var, g->d_edge_chk, g->d_edge_type, pv, pc, bc, E, N, M, xb, wo, dec, g->d_status);
                 else if (use_pipe)
-                    gnn_edge_pipe_kernel<true><<<tc_grid(bc * E, 1), kPipeThreads, kPipeSmem, st>>>(
+                    gnn_edge_pipe_kernel<true, false><<<tc_grid(bc * E, 1), kPipeThreads, kPipeSmem, st>>>(
                         xa, em, pk, tcw, g->d_edge_var, g->d_edge_chk, g->d_edge_type, pv, pc, bc, E, N, M, xb, wo, dec, g->d_status);
                 else if (l == 0)
                     gnn_edge_tc_kernel<false><<<tc_grid(bc * E, 1), kEdgeThreads, kEdgeTcSmem, st>>>(
@@ -916,7 +931,7 @@ int ldpc_gnn_backward(const ldpc_gnn_t* g, const float* params, const float* llr
     // launches).  A handle is still single-stream: d_packed / d_tc are shared scratch.
     gnn_pack_kernel<<<dim3(32, L), 256, 0, st>>>(params, lay, L, g->d_packed, g->d_emb);
     LDPC_CHECK_LAUNCH("gnn_pack_kernel");
-    gnn_pack_tc_kernel<<<dim3(16, L), 256, 0, st>>>(g->d_packed, g->d_tc);
+    gnn_pack_tc_kernel<<<dim3(16, L), 256, 0, st>>>(g->d_packed, g->d_tc, (__half*)g->d_tc16);
     LDPC_CHECK_LAUNCH("gnn_pack_tc_kernel");
     LDPC_CUDA(cudaMemsetAsync(PG, 0, sizeof(float) * (size_t)L * tw.pg_layer, st));
     LDPC_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), st));

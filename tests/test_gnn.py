@@ -224,3 +224,18 @@ def test_tiny_graph_tiles_span_many_codewords(B):
         p.reshape(-1)[0] += eps
     fd = (lp.item() - lm.item()) / (2 * eps)
     assert abs(fd - g) <= 2e-3 * max(1.0, abs(g)) + 2e-4
+
+
+@pytest.mark.gpu
+def test_fp16_split_edge_kernel_matches_the_oracle():
+    """LDPC_GNN_MMA=f16: the edge MLPs with fp16 two-way split operands on kind::f16 (gnn_tc_pipe.cuh).  Same tolerance as the
+    default 3xTF32 form (soft outputs within 1e-4 of the fp64-accumulated oracle; measured 9.6e-6).  Own process: the choice
+    is read once per process."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, LDPC_GNN_MMA="f16")
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "gnn_accuracy.py")], capture_output=True, text=True, timeout=600,
+                         env=env, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    err = float(out.stdout.strip().splitlines()[-1].split()[1])
+    assert err <= 1e-4, out.stdout

@@ -8,10 +8,10 @@ F="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo --expt-relax
 mkdir -p build_variants/obj
 if [ "${TU:-fast}" = "main" ]; then
   nvcc $F "$@" -c -o build_variants/obj/main_$N.o $P/csrc/ldpc_b200.cu
-  nvcc -shared -o build_variants/libldpc_b200_$N.so build_variants/obj/main_$N.o $P/build/fast_kernels.o
+  nvcc -shared -o build_variants/libldpc_b200_$N.so build_variants/obj/main_$N.o $P/build/fast_kernels.o $P/build/neural_qc.o
 else
   nvcc $F "$@" -c -o build_variants/obj/fast_$N.o $P/csrc/fast_kernels.cu
   [ -f $P/build/ldpc_b200.o ] || nvcc $F -c -o $P/build/ldpc_b200.o $P/csrc/ldpc_b200.cu
-  nvcc -shared -o build_variants/libldpc_b200_$N.so $P/build/ldpc_b200.o build_variants/obj/fast_$N.o
+  nvcc -shared -o build_variants/libldpc_b200_$N.so $P/build/ldpc_b200.o build_variants/obj/fast_$N.o $P/build/neural_qc.o
 fi
 echo built $N
