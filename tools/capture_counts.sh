@@ -6,5 +6,7 @@ P=ldpc-neuralnetwork-decoder_b200/libldpc_b200.so
 for algo in minsum bp; do
   python tools/kbench.py $P --algo $algo --batch 262144 --reps 2 || exit 1
   out=gpurun_out/$( [ $algo = minsum ] && echo minsum_r2 || echo bp_fast_r2 )
-  ncu --set full --clock-control none --import-source on -k regex:decode_fast_kernel -s 2 -c 1 -o $out -f python tools/kbench.py $P --algo $algo --batch 262144 --reps 1 > gpurun_out/ncu_$algo.log 2>&1
+  ncu --set full --clock-control none -k regex:decode_fast_kernel -s 2 -c 1 -o $out -f python tools/kbench.py $P --algo $algo --batch 262144 --reps 1 > gpurun_out/ncu_$algo.log 2>&1
+  # the reports of these 250 KB-SASS kernels are 40 MB each and gpurun brings back at most 64 MB: keep the raw-page CSV only
+  ncu -i $out.ncu-rep --page raw --csv > $out.csv 2>/dev/null && rm -f $out.ncu-rep
 done
