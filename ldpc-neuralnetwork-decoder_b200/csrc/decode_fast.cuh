@@ -29,12 +29,13 @@ inline int detect_fast_kind(const ldpc_code* c) {
     return 0;
 }
 
-// fixed iteration count: both compiled tables; per-codeword early exit: the Z = 32 table (one codeword per warp), hard
-// decisions / syndrome / iteration counts only (no soft output, no validity masks -- those stay on the exact kernel)
+// fixed iteration count: every compiled table; per-codeword early exit: min-sum on every table, sum-product at Z = 32 and 16;
+// hard decisions / syndrome / iteration counts only (no soft output, no validity masks -- those stay on the exact kernel)
 inline bool fast_path_supports(const ldpc_code* c, int algo, int stop_mode, bool want_mask, bool want_soft) {
     if (c->fast_kind == 0 || (algo != LDPC_ALGO_MINSUM && algo != LDPC_ALGO_BP) || want_mask) return false;
     if (stop_mode == LDPC_STOP_FIXED) return true;
-    return stop_mode == LDPC_STOP_PER_CODEWORD && c->fast_kind == 1 && !want_soft;
+    if (stop_mode != LDPC_STOP_PER_CODEWORD || want_soft) return false;
+    return algo == LDPC_ALGO_MINSUM || c->fast_kind == 1 || c->fast_kind == 3;
 }
 
 // defined in fast_kernels.cu

@@ -146,13 +146,13 @@ constexpr size_t fast_smem_bytes(int warps) {
     return (size_t)warps * ((LDPC_FAST_TMEM ? 0 : (BG::kCoreEdges + 3) / 4) + (BG::kCoreCols + 3) / 4) * 32 * sizeof(float4);
 }
 
-// kEarly: per-codeword early exit (LDPC_STOP_PER_CODEWORD; one codeword per warp, i.e. Z = 32).  Every iteration then also
+// kEarly: per-codeword early exit (LDPC_STOP_PER_CODEWORD).  With Z < 32 a warp carries 32/Z codewords: each FREEZES its
+// decisions and iteration count at its own first valid iteration, the warp runs until all of them have.  Every iteration then also
 // forms the hard decisions of the degree-1 columns and the syndrome of the new posteriors; a codeword stops after its
 // first valid iteration (traditional_decoders.py:102-106 / 255-258 applied per codeword, as the exact kernel does).
 // Outputs in this mode: hard decisions, syndrome_ok, iters_out (soft_out is served by the exact kernel).
 template <class BG, int kWarps, int kAlgo, bool kEarly = false>
 __global__ void __launch_bounds__(kWarps * 32, 1) decode_fast_kernel(const DecodeParams p) {
-    static_assert(!kEarly || BG::kZ == 32, "early exit needs one codeword per warp");
     constexpr int Z = BG::kZ, G = 32 / Z, NC = BG::kCoreCols, NX = BG::kExtCols, EC = BG::kCoreEdges;
     constexpr int EQ = (EC + 3) / 4;                      // message quads per lane
     constexpr int N = BG::kCols * Z, NW = (N + 31) / 32, NWR = (NW + Z - 1) / Z;
@@ -482,13 +482,28 @@ __global__ void __launch_bounds__(kWarps * 32, 1) decode_fast_kernel(const Decod
         };
         int iters_done = p.iters;
         bool early_ok = false;
+        unsigned tneg_fz = 0;                                  // kEarly: decisions of the core columns, frozen at the codeword's stop
         if constexpr (kEarly) {
-            for (iters_done = 1;; ++iters_done) {
+            bool frozen = false;
+            unsigned long long xneg_fz = 0;
+            for (int it = 1;; ++it) {
                 xneg_it = 0;
                 iteration(IC<2>{});
-                early_ok = all_checks_ok(xneg_it);
-                if (early_ok || iters_done >= p.iters) break;
+                const bool ok = all_checks_ok(xneg_it);        // of THIS lane's codeword
+                if (!frozen && (ok || it >= p.iters)) {
+                    frozen = true;
+                    early_ok = ok;
+                    iters_done = it;
+                    xneg_fz = xneg_it;
+                    static_for<0, NC>([&](auto kc) {
+                        constexpr int c = decltype(kc)::value;
+                        const float t = (kAlgo == LDPC_ALGO_BP) ? bp_resolve(Tc[c], Kc[c]) : Tc[c];
+                        tneg_fz |= t < 0.0f ? (1u << c) : 0u;
+                    });
+                }
+                if (__all_sync(kFull, frozen)) break;          // Z = 32: the one codeword of the warp
             }
+            xneg_it = xneg_fz;
 #if LDPC_FAST_TMEM == 2
             settle_group(IC<0>{});                             // the loads issued for an iteration that does not run
 #endif
@@ -508,8 +523,9 @@ __global__ void __launch_bounds__(kWarps * 32, 1) decode_fast_kernel(const Decod
         };
         auto neg_of = [&](auto jc) -> bool {                  // hard decision of column block j at this lane
             constexpr int j = decltype(jc)::value, sl = BG::col_slot[j];
-            if constexpr (BG::col_kind[j] == 0) return Tc[sl] < 0.0f;
+            if constexpr (kEarly && BG::col_kind[j] == 0) return ((tneg_fz >> sl) & 1u) != 0;
             else if constexpr (kEarly) return ((xneg_it >> sl) & 1ull) != 0;
+            else if constexpr (BG::col_kind[j] == 0) return Tc[sl] < 0.0f;
             else return Lx[sl] < 0.0f;
         };
         if (!kEarly && p.soft_out && live) {
@@ -560,7 +576,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) decode_fast_kernel(const Decod
             if (p.counters) {
                 // all-zero codeword was sent: every negative posterior is a bit error
                 unsigned e = __popcll(xneg);
-                static_for<0, NC>([&](auto kc) { e += Tc[decltype(kc)::value] < 0.0f ? 1u : 0u; });
+                if constexpr (kEarly) e += __popc(tneg_fz);
+                else static_for<0, NC>([&](auto kc) { e += Tc[decltype(kc)::value] < 0.0f ? 1u : 0u; });
 #pragma unroll
                 for (int o = Z / 2; o > 0; o >>= 1) e += __shfl_xor_sync(kFull, e, o, Z);
                 if (live && r == 0) {

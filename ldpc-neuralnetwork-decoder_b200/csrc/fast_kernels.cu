@@ -38,7 +38,11 @@ int launch_fast(const ldpc_code* c, int algo, const DecodeParams& p, cudaStream_
     if (p.stop_mode == LDPC_STOP_PER_CODEWORD) {
         if (c->fast_kind == 1 && algo == LDPC_ALGO_MINSUM) return launch_fast_inst<BG2Z32, LDPC_ALGO_MINSUM, true>(p, st);
         if (c->fast_kind == 1 && algo == LDPC_ALGO_BP) return launch_fast_inst<BG2Z32, LDPC_ALGO_BP, true>(p, st);
-        return fail(LDPC_ERR_UNSUPPORTED, "fast path: per-codeword early exit is compiled for the Z = 32 table only");
+        if (c->fast_kind == 2 && algo == LDPC_ALGO_MINSUM) return launch_fast_inst<BG2Z4, LDPC_ALGO_MINSUM, true>(p, st);
+        if (c->fast_kind == 3 && algo == LDPC_ALGO_MINSUM) return launch_fast_inst<BG2Z16, LDPC_ALGO_MINSUM, true>(p, st);
+        if (c->fast_kind == 3 && algo == LDPC_ALGO_BP) return launch_fast_inst<BG2Z16, LDPC_ALGO_BP, true>(p, st);
+        if (c->fast_kind == 4 && algo == LDPC_ALGO_MINSUM) return launch_fast_inst<BG2Z8, LDPC_ALGO_MINSUM, true>(p, st);
+        return fail(LDPC_ERR_UNSUPPORTED, "fast path: no per-codeword early-exit kernel for this table / algorithm");
     }
     if (algo == LDPC_ALGO_MINSUM) {
         if (c->fast_kind == 1) return launch_fast_inst<BG2Z32, LDPC_ALGO_MINSUM>(p, st);

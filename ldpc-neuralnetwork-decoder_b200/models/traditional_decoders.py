@@ -33,8 +33,12 @@ from ..utils.ldpc_utils import as_code
 class _FloodingDecoder:
     _ALGO = None
 
-    def __init__(self, H=None, max_iterations=50, early_stopping=True, base_graph=None, Z=None, path="auto"):
+    def __init__(self, H=None, max_iterations=50, early_stopping=True, base_graph=None, Z=None, path="auto", check_finite=True):
         self.code = as_code(H, base_graph, Z)
+        # check_finite: look for +-inf / NaN LLRs before every decode under path="auto" (one reduction over the batch and a
+        # host sync, ~0.1 ms) and send such batches to the reference-order kernel; False skips the look-up for callers
+        # that know their LLRs are finite (a demapper's clipped output)
+        self.check_finite = bool(check_finite)
         self.H = H
         self.max_iterations = int(max_iterations)
         self.early_stopping = bool(early_stopping)
@@ -62,7 +66,7 @@ class _FloodingDecoder:
         # +-inf channel LLRs (hard-decision inputs) that is inf - inf = NaN where the reference's sum over the OTHER
         # checks keeps inf (traditional_decoders.py:235-244).  Such batches take the reference-order kernel.
         self._route = self.path
-        if self.path == "auto" and llr_d.numel() and not bool(torch.isfinite(llr_d).all()):
+        if self.path == "auto" and self.check_finite and llr_d.numel() and not bool(torch.isfinite(llr_d).all()):
             self._route = "exact"
         return llr_d, dev
 
@@ -195,8 +199,8 @@ class MinSumScaledDecoder(_FloodingDecoder):
     _ALGO = _native.ALGO_MINSUM
 
     def __init__(self, H=None, max_iterations=50, scaling_factor=0.75, early_stopping=True, base_graph=None, Z=None,
-                 path="auto"):
-        super().__init__(H, max_iterations, early_stopping, base_graph, Z, path)
+                 path="auto", check_finite=True):
+        super().__init__(H, max_iterations, early_stopping, base_graph, Z, path, check_finite)
         self.scaling_factor = scaling_factor
 
     def _alpha(self):

@@ -365,21 +365,28 @@ def test_bench_line_contract_small_run():
     assert par["frames_over_1e-4_converged"] == 0 and par["frames_with_hard_mismatch"] <= par["nonconverged_frames"]
 
 
-@pytest.mark.parametrize("algo", ["minsum", "bp"])
-def test_fast_kernel_per_codeword_early_exit(algo):
-    """The specialised kernel's early-exit variant (Z = 32): every codeword stops after its first valid iteration.
-    Hard decisions, iteration counts and the syndrome flag equal the oracle run with the same stopping rule (min-sum:
-    in the fast kernel's operation order), on a batch that mixes early, late and never-converging codewords."""
-    code = QCCode.nr_2_0(32)
+@pytest.mark.parametrize("algo,Z", [("minsum", 32), ("bp", 32), ("minsum", 16), ("bp", 16), ("minsum", 8), ("minsum", 4)])
+def test_fast_kernel_per_codeword_early_exit(algo, Z):
+    """The specialised kernels' early-exit variant: every codeword stops after its first valid iteration (with Z < 32 the 32/Z
+    codewords of a warp freeze their decisions individually).  Hard decisions, iteration counts and the syndrome flag equal
+    the oracle run with the same stopping rule (min-sum: in the fast kernel's operation order), on a ragged batch that mixes
+    early, late and never-converging codewords.  Z = 16 with 50 iterations and early stopping is the reference's default."""
+    code = QCCode.nr_2_0(Z)
     B, iters = 301, 20
-    llr = np.concatenate([oracle.awgn_llr(None, 150, code.N, -3.6, seed=41), oracle.awgn_llr(None, 151, code.N, -1.0, seed=42)])
+    lo, hi = (-3.6, -1.0) if Z == 32 else ((-2.5, 0.5) if Z >= 8 else (-1.0, 3.0))
+    llr = np.concatenate([oracle.awgn_llr(None, 150, code.N, lo, seed=41), oracle.awgn_llr(None, 151, code.N, hi, seed=42)])
+    rng = np.random.default_rng(Z)
+    llr = llr[rng.permutation(B)]                       # early and late codewords share warps
     if algo == "minsum":
         dec = MinSumScaledDecoder(code, iters, 0.75, early_stopping=True)                  # auto -> specialised kernel
-        o = oracle.decode(code.shifts, 32, llr, iters, "minsum", 0.75, order="fast", stop_when_valid=True)
+        o = oracle.decode(code.shifts, Z, llr, iters, "minsum", 0.75, order="fast", stop_when_valid=True)
     else:
         dec = BeliefPropagationDecoder(code, iters, early_stopping=True, path="fast")
-        o = oracle.decode(code.shifts, 32, llr, iters, "bp", 1.0, stop_when_valid=True)
+        o = oracle.decode(code.shifts, Z, llr, iters, "bp", 1.0, stop_when_valid=True)
+    assert len(set(o["iters"].tolist())) > 2
+    n0 = _native.lib().ldpc_launch_count()
     bits, its, ok = dec.decode_with_iterations(torch.from_numpy(llr).to(dev()))
+    assert _native.lib().ldpc_launch_count() - n0 == 1                                   # ONE launch of the specialised kernel
     assert np.array_equal(its.cpu().numpy(), o["iters"])
     assert np.array_equal(bits.cpu().numpy().astype(np.uint8), o["hard"])
     valid = np.asarray(dec._check_valid_codeword(bits).cpu().numpy())
