@@ -105,6 +105,10 @@ int ldpc_bp_decode(const ldpc_code_t* code, const float* llr, int64_t B, int ite
                    float* soft_out, void* hard_out, int hard_dtype, uint8_t* syndrome_ok, int32_t* iters_out,
                    uint64_t* valid_mask, int mask_words, void* stream);
 
+/* flag[0] |= 1 if any of x[0..n) is +-inf or NaN (x 16-byte aligned; flag is a device int the caller zeroes).  One read-only
+ * pass; the drop-in classes use it to route non-finite LLR batches to LDPC_PATH_EXACT (see LDPC_PATH_AUTO above).            */
+int ldpc_nonfinite_flag(const float* x, int64_t n, int32_t* flag, void* stream);
+
 /* ldpc_syndrome_check replaces _check_valid_codeword (traditional_decoders.py:111-134,262-284):
  * syndrome_ok[b] = 1 iff every parity check of H is satisfied by hard[b] (per hard_dtype).    */
 int ldpc_syndrome_check(const ldpc_code_t* code, const void* hard, int hard_dtype, int64_t B, uint8_t* syndrome_ok,

@@ -31,6 +31,7 @@ PROTOTYPES = {
     "ldpc_code_has_fast_path": (_i, [_p, _i]),
     "ldpc_minsum_decode": (_i, [_p, _p, _i64, _i, _f, _i, _i, _p, _p, _i, _p, _p, _p, _i, _p]),
     "ldpc_bp_decode": (_i, [_p, _p, _i64, _i, _i, _i, _p, _p, _i, _p, _p, _p, _i, _p]),
+    "ldpc_nonfinite_flag": (_i, [_p, _i64, _p, _p]),
     "ldpc_syndrome_check": (_i, [_p, _p, _i, _i64, _p, _p]),
     "ldpc_encode": (_i, [_p, _p, _i64, _p, _i64, _p, _p, _p]),
     "ldpc_rate_match": (_i, [_p, _p, _i64, _i64, _i64, _p, _p]),

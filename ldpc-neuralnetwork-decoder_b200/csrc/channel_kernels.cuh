@@ -72,6 +72,19 @@ __global__ void __launch_bounds__(256) count_errors_kernel(const void* __restric
     }
 }
 
+// flag[0] |= 1 if any of x[0..n) is +-inf or NaN: one read-only pass (128-bit loads), one atomic per CTA at most
+__global__ void __launch_bounds__(256) nonfinite_flag_kernel(const float* __restrict__ x, long long n, int* __restrict__ flag) {
+    const long long n4 = n >> 2;
+    unsigned bad = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(x) + i);
+        bad |= ((v.x & 0x7f800000u) == 0x7f800000u) | ((v.y & 0x7f800000u) == 0x7f800000u) |
+               ((v.z & 0x7f800000u) == 0x7f800000u) | ((v.w & 0x7f800000u) == 0x7f800000u);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) bad |= (__float_as_uint(x[(n4 << 2) + threadIdx.x]) & 0x7f800000u) == 0x7f800000u;
+    if (__syncthreads_or((int)bad) && threadIdx.x == 0) atomicOr(flag, 1);
+}
+
 // quantised LLRs as transferred -> the fp32 values the decoder (and the reference) computes on
 template <typename T>
 __global__ void llr_dequant_kernel(const T* __restrict__ raw, float scale, long long n, float* __restrict__ out) {

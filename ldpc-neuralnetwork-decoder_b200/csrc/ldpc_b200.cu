@@ -366,6 +366,18 @@ int ldpc_qpsk_llr(const uint8_t* bits, int64_t B, int64_t N, float snr_db, int t
     return LDPC_OK;
 }
 
+int ldpc_nonfinite_flag(const float* x, int64_t n, int32_t* flag, void* stream) {
+    if (!x || !flag) return fail(LDPC_ERR_INVALID, "nonfinite_flag: null argument");
+    if (n < 0) return fail(LDPC_ERR_INVALID, "nonfinite_flag: negative length");
+    if ((reinterpret_cast<uintptr_t>(x) & 15u) != 0) return fail(LDPC_ERR_INVALID, "nonfinite_flag: x must be 16-byte aligned");
+    if (n == 0) return LDPC_OK;
+    const long long blocks = ((n >> 2) + 255) / 256;
+    nonfinite_flag_kernel<<<(int)(blocks < 1 ? 1 : (blocks < (long long)kNumSMs * 8 ? blocks : (long long)kNumSMs * 8)), 256, 0, (cudaStream_t)stream>>>(
+        x, (long long)n, flag);
+    LDPC_CHECK_LAUNCH("nonfinite_flag_kernel");
+    return LDPC_OK;
+}
+
 int ldpc_count_errors(const void* hard, int hard_dtype, const uint8_t* tx, int64_t B, int64_t N, uint64_t* counters,
                       void* stream) {
     if (!hard || !counters) return fail(LDPC_ERR_INVALID, "count_errors: null argument");

@@ -66,8 +66,17 @@ class _FloodingDecoder:
         # +-inf channel LLRs (hard-decision inputs) that is inf - inf = NaN where the reference's sum over the OTHER
         # checks keeps inf (traditional_decoders.py:235-244).  Such batches take the reference-order kernel.
         self._route = self.path
-        if self.path == "auto" and self.check_finite and llr_d.numel() and not bool(torch.isfinite(llr_d).all()):
-            self._route = "exact"
+        if self.path == "auto" and self.check_finite and llr_d.numel():
+            if llr_d.data_ptr() % 16 == 0:              # one read-only pass + a 4-byte read-back
+                flag = torch.zeros(1, dtype=torch.int32, device=dev)
+                with torch.cuda.device(dev):
+                    _native.check(_native.lib().ldpc_nonfinite_flag(_native.ptr(llr_d), llr_d.numel(), _native.ptr(flag),
+                                                                    _native.stream_ptr(dev)))
+                bad = bool(int(flag.item()))
+            else:                                       # odd view offsets (rows that are not a multiple of 16 bytes)
+                bad = not bool(torch.isfinite(llr_d).all())
+            if bad:
+                self._route = "exact"
         return llr_d, dev
 
     def _launch(self, llr_d, dev, iters, stop_mode=_native.STOP_FIXED, soft=True, hard_dtype=_native.HARD_F32,

@@ -378,7 +378,7 @@ def test_fast_kernel_per_codeword_early_exit(algo, Z):
     rng = np.random.default_rng(Z)
     llr = llr[rng.permutation(B)]                       # early and late codewords share warps
     if algo == "minsum":
-        dec = MinSumScaledDecoder(code, iters, 0.75, early_stopping=True)                  # auto -> specialised kernel
+        dec = MinSumScaledDecoder(code, iters, 0.75, early_stopping=True, check_finite=False)   # auto -> specialised kernel
         o = oracle.decode(code.shifts, Z, llr, iters, "minsum", 0.75, order="fast", stop_when_valid=True)
     else:
         dec = BeliefPropagationDecoder(code, iters, early_stopping=True, path="fast")
