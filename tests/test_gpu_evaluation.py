@@ -85,8 +85,13 @@ def test_device_channel_sweep_and_per_codeword_exit():
     # same frames through the oracle: per-codeword stop = first valid iteration of that codeword
     llr = oracle.qpsk_llr(None, 256, code.N, -4.0, seed=21)
     bits, its, ok = ev.ms_decoder.decode_with_iterations(torch.from_numpy(llr).to(DEV))
-    o = oracle.decode(code.shifts, Z, llr, 50, "minsum", 0.75, stop_when_valid=True)
+    # (path "auto": the specialised early-exit kernel, compiled for every lifting size since round 2 -> the kernel's operation order)
+    o = oracle.decode(code.shifts, Z, llr, 50, "minsum", 0.75, order="fast", stop_when_valid=True)
     assert np.array_equal(bits.cpu().numpy().astype(np.uint8), o["hard"]) and np.array_equal(its.cpu().numpy(), o["iters"])
+    # against the reference operation order: every codeword that converges does so at the same iteration with the same bits
+    r = oracle.decode(code.shifts, Z, llr, 50, "minsum", 0.75, stop_when_valid=True)
+    conv = ok.cpu().numpy().astype(bool)
+    assert conv.sum() > 10 and np.array_equal(o["iters"][conv], r["iters"][conv]) and np.array_equal(o["hard"][conv], r["hard"][conv])
 
 
 def test_neural_decoder_slot_takes_the_gnn():
