@@ -15,7 +15,6 @@ launches, max over ranks.  `e2e`: the same through ldpc_decode_host with pinned 
 Only this file's cpu_baseline / --impl reference legs execute oracle/.
 """
 import argparse
-import ctypes as C
 import json
 import os
 import subprocess
@@ -102,7 +101,6 @@ ALL_CPUS = os.sched_getaffinity(0)          # before any rank-local binding (bin
 def cpu_baseline(workload, seconds=12.0):
     """The oracle port (faithful O(d^2) restatement of the reference loops, OpenMP over
     codewords) on a bounded sample of the same workload."""
-    import numpy as np
     from oracle import oracle
     import ldpc_b200
     from ldpc_b200.utils import QCCode
@@ -192,7 +190,6 @@ def cpu_baseline_pytorch(L, h, code, dev, frames=32):
     """The UNMODIFIED reference (baseline/_ref = pip install of /root/reference) on this box's host cores:
     MinSumScaledDecoder(H, 10, 0.75, early_stopping=False).decode on `frames` BG2 Z=32 frames, and its hard bits
     compared with the engine's on the same LLRs (traditional_decoders.py:143-260)."""
-    import numpy as np
     import torch
     from ldpc_b200 import _native
     ref_dir = os.path.join(ROOT, "baseline", "_ref")

@@ -45,14 +45,7 @@ __device__ __forceinline__ void nq_tie(float& a) { asm volatile("" : "+f"(a)); }
 __device__ __forceinline__ void nq_st1(uint32_t taddr, float v) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" :: "r"(taddr), "r"(f2u(v)) : "memory");
 }
-// L1-allocating load: unlike ld.global.nc (__ldg) it hits the lines prefetch.global.L1 brought in
-__device__ __forceinline__ float nq_ldca(const float* p) {
-    float v;
-    asm volatile("ld.global.ca.f32 %0, [%1];" : "=f"(v) : "l"(p));
-    return v;
-}
 __device__ __forceinline__ void nq_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void nq_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // the members of a codeword meet: TMEM stores settled, ordered before / after the barrier, shared memory too
 __device__ __forceinline__ void nq_group_sync(int group) {
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");

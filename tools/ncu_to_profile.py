@@ -19,7 +19,6 @@ import io
 import json
 import os
 import subprocess
-import sys
 import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
