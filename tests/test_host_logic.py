@@ -296,3 +296,63 @@ def test_rate_match_tables_hand_computed_case_and_oracle():
         rate_match_tables(code, 11, payload_bits=16, Qm=2)
     with pytest.raises(ValueError):
         rate_match_tables(code, 10, payload_bits=3)
+
+
+def test_neural_qc_schedule_tables_cover_the_base_graph_exactly_once():
+    """csrc/nq_tables.h (generated by csrc/gen_tables.py:emit_nq) drives the rolled QC neural kernels: every base row, core
+    column, degree-1 cell and (member, cell) of the backward's flattened list must be owned exactly once, the row / column
+    classes must match the shapes the kernel bodies are compiled for, and the packed chunk table must decode to the
+    variable-major edge numbering of create_LLR_mapping."""
+    text = open(os.path.join(ROOT, "ldpc-neuralnetwork-decoder_b200", "csrc", "nq_tables.h")).read()
+
+    def arr(name):
+        m = re.search(r"\b%s(\[[^=]*)= \{([^}]*)\}" % name, text)
+        assert m, name
+        dims = [int(x) for x in re.findall(r"\[(\d+)\]", m.group(1))]
+        return np.array([int(x) for x in m.group(2).split(",")]).reshape(dims)
+    code = QCCode.nr_2_0(32)
+    deg_c = (code.shifts >= 0).sum(axis=0)
+    core = [j for j in range(code.cols) if deg_c[j] > 1]
+    row_meta, row_ext = arr("row_meta"), arr("row_ext")
+    sched_rows, row_ptr = arr("sched_rows"), arr("sched_row_ptr")
+    classes = [(2, 1), (3, 1), (4, 1), (5, 1), (8, 0), (10, 0)]
+    seen_rows = []
+    for m in range(4):
+        for c, (nc, ne) in enumerate(classes):
+            for t in range(row_ptr[m][c], row_ptr[m][c + 1]):
+                i = int(sched_rows[m][t])
+                seen_rows.append(i)
+                cols = np.nonzero(code.shifts[i] >= 0)[0]
+                assert sum(deg_c[j] > 1 for j in cols) == nc and sum(deg_c[j] == 1 for j in cols) == ne
+                assert (row_ext[i] != 255) == bool(ne)
+    assert sorted(seen_rows) == list(range(code.rows))
+    # every core cell appears in exactly one row's metadata with the right shift
+    vm0 = np.concatenate([[0], np.cumsum(deg_c)])[:-1]
+    cells = []
+    for i in range(code.rows):
+        k_in_col = {j: int((code.shifts[:i, j] >= 0).sum()) for j in range(code.cols)}
+        metas = [int(x) for x in row_meta[i][:sum(1 for j in np.nonzero(code.shifts[i] >= 0)[0] if deg_c[j] > 1)]]
+        want = [(vm0[j] + k_in_col[j]) | (int(code.shifts[i, j]) << 8) for j in np.nonzero(code.shifts[i] >= 0)[0] if deg_c[j] > 1]
+        assert metas == [int(w) for w in want]
+        cells += [w & 0xff for w in metas]
+    assert sorted(cells) == list(range(int(deg_c[core].sum())))
+    sched_cols, col_ptr, col_b0, col_d = arr("sched_cols"), arr("sched_col_ptr"), arr("col_b0"), arr("col_d")
+    cmax = [6, 8, 10, 13, 16, 23]
+    seen_cols = []
+    for m in range(4):
+        for c in range(6):
+            for t in range(col_ptr[m][c], col_ptr[m][c + 1]):
+                j = int(sched_cols[m][t])
+                seen_cols.append(j)
+                assert (cmax[c - 1] if c else 0) < col_d[j] <= cmax[c] and col_b0[j] == vm0[j] and col_d[j] == deg_c[j]
+    assert sorted(seen_cols) == core
+    sched_ext, ext_cnt = arr("sched_ext"), arr("sched_ext_cnt")
+    assert sorted(int(x) for m in range(4) for x in sched_ext[m][:ext_cnt[m]]) == list(range(code.cols - len(core)))
+    sc, scnt = arr("sched_cells"), arr("sched_cell_cnt")
+    assert sorted(int(x) for m in range(4) for x in sc[m][:scnt[m]] if x != 255) == list(range(int(deg_c[core].sum())))
+    chunk = arr("chunk_meta")
+    for m, w in enumerate(chunk):
+        D, d, inv = int(w) & 0xff, (int(w) >> 8) & 0x1f, int(w) >> 13
+        j = int(np.searchsorted(vm0, m, side="right") - 1)
+        assert D == vm0[j] and d == deg_c[j]
+        assert all(((off * inv) >> 16) == off // d for off in range(32 * d))
