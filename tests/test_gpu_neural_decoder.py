@@ -248,6 +248,9 @@ def test_qc_structured_kernel_is_bit_identical_to_the_table_driven_kernels(depth
         s_tb, m_tb = make(False)(x, cidx, vidx, y)
         s_n, _ = make(True)(x, cidx, vidx)                                            # without ground truth
     assert torch.equal(s_qc, s_tb) and torch.equal(m_qc, m_tb) and torch.equal(s_n, s_qc)
+    with torch.no_grad():                                            # soft targets: the two-logarithm form of the loss
+        ysoft = torch.from_numpy(rng.random((64, code.E)).astype(np.float32)).to(DEV)
+        assert torch.equal(make(True)(x[:64], cidx, vidx, ysoft)[1], make(False)(x[:64], cidx, vidx, ysoft)[1])
     chain = make(False, fused=False)
     s_ch, m_ch = chain(x[:64], cidx, vidx, y[:64])                                  # literal four-layer composition
     assert torch.equal(s_ch.detach(), s_qc[:64]) and torch.equal(m_ch.detach(), m_qc[:64])
