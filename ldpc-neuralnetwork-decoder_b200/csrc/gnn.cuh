@@ -43,6 +43,8 @@ struct ldpc_gnn {
     int* d_var_ptr = nullptr;     // [N+1]
     int* d_var_edge = nullptr;    // [E] messages of each variable, ascending check
     int* d_chk_ptr = nullptr;     // [M+1] (messages of a check are contiguous)
+    int* d_var_list2 = nullptr;   // [E] message | type << 20 in variable-list order (gnn_node_pipe.cuh; null if E or types too large)
+    int* d_chk_list2 = nullptr;   // [E] the same in check-list (= message) order
     float* d_packed = nullptr;    // per-call repacked weights (layers * kPackedPerLayer floats)
     float* d_emb = nullptr;       // per-call 16-byte aligned copy of the type embeddings [layers][types][h]
     void* d_tc16 = nullptr;       // per-call fp16 hi/lo images of the edge kernel's weights (gnn_tc.cuh, kTc16PerLayer halves per layer)

@@ -16,6 +16,7 @@
 #include "rate_match.cuh"
 #include "gnn_tc.cuh"
 #include "gnn_tc_pipe.cuh"
+#include "gnn_node_pipe.cuh"
 #include "gnn_bwd_tc.cuh"
 #include <cstdlib>
 
@@ -727,6 +728,13 @@ int ldpc_gnn_create(const ldpc_code_t* code, int num_layers, int hidden, int num
     for (int v = 0; v < g->N; ++v) vptr[v + 1] += vptr[v];
     std::vector<int> fill(g->N, 0);
     for (int x = 0; x < g->E; ++x) vedge[vptr[ev[x]] + fill[ev[x]]++] = x;
+    // packed lists of the pipelined node kernel: message index and message type in one entry
+    const bool node_pipe = g->E < (1 << kNpListShift) && num_types <= kNpMaxTypes && g->N % 4 == 0 && g->M % 4 == 0;
+    std::vector<int> vlist2(node_pipe ? g->E : 0), clist2(node_pipe ? g->E : 0);
+    for (int x = 0; node_pipe && x < g->E; ++x) {
+        vlist2[x] = vedge[x] | (et[vedge[x]] << kNpListShift);
+        clist2[x] = x | (et[x] << kNpListShift);
+    }
     DeviceGuard dg(g->device);
     if (!dg.ok) { delete g; return fail(LDPC_ERR_CUDA, "gnn_create: cannot select device"); }
     auto up = [&](int** dst, const std::vector<int>& src) -> bool {
@@ -734,7 +742,7 @@ int ldpc_gnn_create(const ldpc_code_t* code, int num_layers, int hidden, int num
         return cudaMemcpy(*dst, src.data(), sizeof(int) * src.size(), cudaMemcpyHostToDevice) == cudaSuccess;
     };
     bool ok = up(&g->d_edge_var, ev) && up(&g->d_edge_chk, ec) && up(&g->d_edge_type, et) && up(&g->d_var_ptr, vptr) &&
-              up(&g->d_var_edge, vedge) && up(&g->d_chk_ptr, cptr) &&
+              up(&g->d_var_edge, vedge) && up(&g->d_chk_ptr, cptr) && (!node_pipe || (up(&g->d_var_list2, vlist2) && up(&g->d_chk_list2, clist2))) &&
               cudaMalloc(&g->d_packed, sizeof(float) * (size_t)num_layers * kPackedPerLayer) == cudaSuccess &&
               cudaMalloc(&g->d_emb, sizeof(float) * (size_t)num_layers * num_types * kH) == cudaSuccess &&
               cudaMalloc(&g->d_tc, sizeof(float) * (size_t)num_layers * kTcPerLayer) == cudaSuccess &&
@@ -750,7 +758,7 @@ int ldpc_gnn_destroy(ldpc_gnn_t* g) {
     {
         DeviceGuard dg(g->device);
         cudaFree(g->d_edge_var); cudaFree(g->d_edge_chk); cudaFree(g->d_edge_type); cudaFree(g->d_var_ptr);
-        cudaFree(g->d_var_edge); cudaFree(g->d_chk_ptr); cudaFree(g->d_packed); cudaFree(g->d_emb); cudaFree(g->d_tc); cudaFree(g->d_tc16); cudaFree(g->d_status);
+        cudaFree(g->d_var_edge); cudaFree(g->d_chk_ptr); cudaFree(g->d_var_list2); cudaFree(g->d_chk_list2); cudaFree(g->d_packed); cudaFree(g->d_emb); cudaFree(g->d_tc); cudaFree(g->d_tc16); cudaFree(g->d_status);
     }
     delete g;
     return LDPC_OK;
@@ -819,6 +827,8 @@ int ldpc_gnn_forward(const ldpc_gnn_t* g, const float* params, const float* llr,
         LDPC_CUDA(cudaFuncSetAttribute(gnn_edge_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEdgeTcSmem));
         LDPC_CUDA(cudaFuncSetAttribute(gnn_edge_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEdgeTcSmem));
         LDPC_CUDA(cudaFuncSetAttribute(gnn_node_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNodeTcSmem));
+        if (g->d_var_list2)
+            LDPC_CUDA(cudaFuncSetAttribute(gnn_node_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)node_pipe_smem(g->types)));
         LDPC_CUDA(cudaFuncSetAttribute(gnn_edge_pipe_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmem));
         LDPC_CUDA(cudaFuncSetAttribute(gnn_edge_pipe_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmem));
         LDPC_CUDA(cudaFuncSetAttribute(gnn_edge_pipe_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmem));
@@ -847,14 +857,27 @@ int ldpc_gnn_forward(const ldpc_gnn_t* g, const float* params, const float* llr,
             const float* em = g->d_emb + (size_t)l * g->types * kH;
             if (use_tc) {
                 const float* tcw = g->d_tc + (size_t)l * kTcPerLayer;
-                gnn_node_tc_kernel<<<tc_grid(bc * N, 2), kNodeThreads, kNodeTcSmem, st>>>(
-                    xa, em, pk, tcw, 0, g->d_var_ptr, g->d_var_edge, g->d_edge_type, bc, E, N, pv,
-                    training ? base + tw.MVS + (size_t)l * tw.pvs : nullptr, g->d_status);
-                LDPC_CHECK_LAUNCH("gnn_node_tc_kernel(var)");
-                gnn_node_tc_kernel<<<tc_grid(bc * M, 2), kNodeThreads, kNodeTcSmem, st>>>(
-                    xa, em, pk, tcw, 1, g->d_chk_ptr, nullptr, g->d_edge_type, bc, E, M, pc,
-                    training ? base + tw.MCS + (size_t)l * tw.pcs : nullptr, g->d_status);
-                LDPC_CHECK_LAUNCH("gnn_node_tc_kernel(chk)");
+                float* mvs = training ? base + tw.MVS + (size_t)l * tw.pvs : nullptr;
+                float* mcs = training ? base + tw.MCS + (size_t)l * tw.pcs : nullptr;
+                // node terms: the warp-specialised gather pipeline (gnn_node_pipe.cuh); LDPC_GNN_NODE=serial selects the
+                // phase-by-phase kernel it replaced (bit-identical, kept for codes whose tables do not fit the packed lists)
+                static const bool node_serial = getenv("LDPC_GNN_NODE") && getenv("LDPC_GNN_NODE")[0] == 's';
+                if (g->d_var_list2 && !node_serial) {
+                    const size_t nsm = node_pipe_smem(g->types);
+                    gnn_node_pipe_kernel<<<tc_grid(bc * N, 1), kNpThreads, nsm, st>>>(
+                        xa, em, pk, tcw, 0, g->d_var_ptr, g->d_var_list2, g->types, bc, E, N, pv, mvs, g->d_status);
+                    LDPC_CHECK_LAUNCH("gnn_node_pipe_kernel(var)");
+                    gnn_node_pipe_kernel<<<tc_grid(bc * M, 1), kNpThreads, nsm, st>>>(
+                        xa, em, pk, tcw, 1, g->d_chk_ptr, g->d_chk_list2, g->types, bc, E, M, pc, mcs, g->d_status);
+                    LDPC_CHECK_LAUNCH("gnn_node_pipe_kernel(chk)");
+                } else {
+                    gnn_node_tc_kernel<<<tc_grid(bc * N, 2), kNodeThreads, kNodeTcSmem, st>>>(
+                        xa, em, pk, tcw, 0, g->d_var_ptr, g->d_var_edge, g->d_edge_type, bc, E, N, pv, mvs, g->d_status);
+                    LDPC_CHECK_LAUNCH("gnn_node_tc_kernel(var)");
+                    gnn_node_tc_kernel<<<tc_grid(bc * M, 2), kNodeThreads, kNodeTcSmem, st>>>(
+                        xa, em, pk, tcw, 1, g->d_chk_ptr, nullptr, g->d_edge_type, bc, E, M, pc, mcs, g->d_status);
+                    LDPC_CHECK_LAUNCH("gnn_node_tc_kernel(chk)");
+                }
                 // inference: the last layer applies the readout projection itself and writes one float per message into xb
                 fused_readout = use_pipe && !training && l == g->layers - 1;
                 const float* wo = fused_readout ? params + lay.out_w(l) : nullptr;

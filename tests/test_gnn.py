@@ -194,6 +194,30 @@ def test_tensor_core_and_ffma_paths_agree(tmp_path):
 
 
 @pytest.mark.gpu
+def test_pipelined_and_serial_node_kernels_are_bit_identical(tmp_path):
+    """gnn_node_pipe_kernel (loader warps gathering ahead of the tensor-pipe warps, gnn_node_pipe.cuh) against the
+    phase-by-phase gnn_node_tc_kernel it replaced (LDPC_GNN_NODE=serial, read once per process): the sums are formed in
+    the same order, so the probabilities must be EQUAL on the ragged batch of the script (loss and gradients to rounding)."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "run.py"
+    script.write_text(_PATH_SCRIPT)
+    res = {}
+    for tag, env in (("pipe", {}), ("serial", {"LDPC_GNN_NODE": "serial"})):
+        out = tmp_path / f"{tag}.npz"
+        p = subprocess.run([sys.executable, str(script), root, str(out)], capture_output=True, text=True, timeout=600,
+                           env=dict(os.environ, **env))
+        assert p.returncode == 0, p.stderr[-3000:]
+        res[tag] = np.load(out)
+    a, b = res["pipe"], res["serial"]
+    assert np.array_equal(a["probs"], b["probs"]), float(np.max(np.abs(a["probs"] - b["probs"])))
+    # the loss reduction and the weight gradients are accumulated with atomics: compare to rounding, not bit for bit
+    assert abs(float(a["loss"]) - float(b["loss"])) <= 2e-6 * abs(float(b["loss"]))
+    scale = np.max(np.abs(b["grad"]))
+    assert np.max(np.abs(a["grad"] - b["grad"])) <= 1e-5 * scale
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("B", [1, 3, 40])
 def test_tiny_graph_tiles_span_many_codewords(B):
     """The notebook's 3x4 toy matrix has 7 messages, so a 128-row tile of the tensor-core kernels covers up to 18
