@@ -250,6 +250,18 @@ int ldpc_neural_decode_qc(const ldpc_code_t* code, const float* llr_e, const flo
 int ldpc_neural_backward_qc(const ldpc_code_t* code, const float* save_x, const float* soft, const float* gt_e, const int32_t* argmax,
                             const float* g_ml, const float* w_res, int L, int iters, int64_t B, float* g_wch, float* g_wres,
                             void* stream);
+/* The same two kernels with PER-VARIABLE input and output -- the trainer's own call shape (training/trainer.py:95-110,180-187:
+ * LLRs and targets per code bit, expanded with llr[:, edge_to_var] before the layers run): llr_v / gt_v / soft_v are [B, N]
+ * (N = 1664); every edge of a variable takes its variable's LLR and target, soft_v holds the output at each variable's
+ * first edge, max_loss / argmax range over all E edges exactly as in ldpc_neural_decode_qc (bit-identical to it on the
+ * expanded arrays).  star [B, 2] receives (soft, target) at the arg-max edge, which is all ldpc_neural_backward_qc_var
+ * needs of the two arrays: no [B, E] tensor exists anywhere on this path.                                             */
+int ldpc_neural_decode_qc_var(const ldpc_code_t* code, const float* llr_v, const float* w_ch, const float* w_res, int L, int iters,
+                              int64_t B, const float* gt_v, float* soft_v, float* max_loss, float* save_x, int32_t* argmax,
+                              float* star, void* stream);
+int ldpc_neural_backward_qc_var(const ldpc_code_t* code, const float* save_x, const float* star, const int32_t* argmax,
+                                const float* g_ml, const float* w_res, int L, int iters, int64_t B, float* g_wch, float* g_wres,
+                                void* stream);
 /* OutputLayer.forward, layers.py:180-210: soft = sigmoid(final+llr); if gt: per-row max of
  * BCE(soft, gt) -> max_loss [B], argmax [B] int32 (for the backward).                    */
 int ldpc_output_layer_fwd(const float* final_llr, const float* llr, const float* gt, int64_t B, int64_t E,

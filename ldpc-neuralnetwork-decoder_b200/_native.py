@@ -51,6 +51,8 @@ PROTOTYPES = {
     "ldpc_neural_decode": (_i, [_p, _p, _i, _p, _p, _p, _i, _p, _p, _p, _p, _i, _i, _i64, _i64, _p, _p, _p, _p]),
     "ldpc_neural_decode_qc": (_i, [_p, _p, _p, _p, _i, _i, _i64, _p, _p, _p, _p, _p, _p]),
     "ldpc_neural_backward_qc": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i64, _p, _p, _p]),
+    "ldpc_neural_decode_qc_var": (_i, [_p, _p, _p, _p, _i, _i, _i64, _p, _p, _p, _p, _p, _p, _p]),
+    "ldpc_neural_backward_qc_var": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i64, _p, _p, _p]),
     "ldpc_check_layer_fwd_sorted": (_i, [_p, _p, _i, _p, _p, _i64, _i64, _p, _p, _p]),
     "ldpc_variable_layer_fwd_sorted": (_i, [_p, _p, _p, _i, _p, _p, _p, _p, C.POINTER(_p), _i, _i64, _i64, _p, _p]),
     "ldpc_check_layer_bwd_nstar": (_i, [_p, _p, _p, _p, _i64, _i64, _p, _p]),

@@ -211,6 +211,7 @@ def emit_nq(rows, cols, cells, Z, dst):
         sslots.append(sl)
     ncell = max(len(l) for l in scells)
     chunk = []
+    cell_col = []
     for m in range(vm0[-1] + coldeg[-1]):
         j = max(jj for jj in range(cols) if vm0[jj] <= m)
         d = coldeg[j]
@@ -218,6 +219,7 @@ def emit_nq(rows, cols, cells, Z, dst):
         for off in range(32 * d):
             assert (off * inv) >> 16 == off // d
         chunk.append((vm0[j], d, inv))
+        cell_col.append(j)
 
     def arr(ctype, nm, vals, dims):
         flat = ", ".join(str(v) for v in vals)
@@ -261,6 +263,7 @@ def emit_nq(rows, cols, cells, Z, dst):
             arr("unsigned char", "sched_ext_cnt", [len(l) for l in sext], f"[{NQ_MEMBERS}]"),
             arr("unsigned int", "chunk_meta", [D | (d << 8) | (inv << 13) for D, d, inv in chunk], f"[{len(chunk)}]") +
             "   // per 32-edge chunk of a row: first cell of its column | degree << 8 | (65536 / degree + 1) << 13",
+            arr("unsigned char", "cell_col", cell_col, f"[{len(cell_col)}]") + "   // base column of a cell (per-variable I/O)",
             "", "}  // namespace nq", "}  // namespace ldpc", ""]
     new = "\n".join(text)
     old = open(dst).read() if os.path.exists(dst) else None

@@ -672,6 +672,39 @@ int ldpc_neural_backward_qc(const ldpc_code_t* code, const float* save_x, const 
     return launch_neural_qc_bwd(code, p, (cudaStream_t)stream);
 }
 
+int ldpc_neural_decode_qc_var(const ldpc_code_t* code, const float* llr_v, const float* w_ch, const float* w_res, int L, int iters,
+                              int64_t B, const float* gt_v, float* soft_v, float* max_loss, float* save_x, int32_t* argmax,
+                              float* star, void* stream) {
+    if (!code || !llr_v || !w_ch || !soft_v || (L > 0 && !w_res)) return fail(LDPC_ERR_INVALID, "neural_decode_qc_var: null argument");
+    if (gt_v && !max_loss) return fail(LDPC_ERR_INVALID, "neural_decode_qc_var: ground truth given without max_loss buffer");
+    if ((argmax || star) && !gt_v) return fail(LDPC_ERR_INVALID, "neural_decode_qc_var: argmax / star need the ground truth");
+    if (L < 0 || L > 2) return fail(LDPC_ERR_UNSUPPORTED, "neural_decode_qc_var: residual depth %d outside 0..2 (two ring slots in Tensor Memory)", L);
+    if (iters < 1 || B < 0) return fail(LDPC_ERR_INVALID, "neural_decode_qc_var: bad shape");
+    if (B == 0) return LDPC_OK;
+    DeviceGuard g(code->device);
+    if (!g.ok) return fail(LDPC_ERR_CUDA, "neural_decode_qc_var: cannot select device %d", code->device);
+    NeuralQcParams p{};
+    p.llr = llr_v; p.w_ch = w_ch; p.w_res = w_res; p.L = L; p.iters = iters; p.B = B; p.gt = gt_v; p.soft = soft_v;
+    p.max_loss = max_loss; p.save_x = save_x; p.argmax = argmax; p.per_var = 1; p.star = star;
+    return launch_neural_qc(code, p, (cudaStream_t)stream);
+}
+
+int ldpc_neural_backward_qc_var(const ldpc_code_t* code, const float* save_x, const float* star, const int32_t* argmax,
+                                const float* g_ml, const float* w_res, int L, int iters, int64_t B, float* g_wch, float* g_wres,
+                                void* stream) {
+    if (!code || !save_x || !star || !argmax || !g_ml || !g_wch || (L > 0 && (!w_res || !g_wres)))
+        return fail(LDPC_ERR_INVALID, "neural_backward_qc_var: null argument");
+    if (L < 0 || L > 2) return fail(LDPC_ERR_UNSUPPORTED, "neural_backward_qc_var: residual depth %d outside 0..2", L);
+    if (iters < 1 || B < 0) return fail(LDPC_ERR_INVALID, "neural_backward_qc_var: bad shape");
+    if (B == 0) return LDPC_OK;
+    DeviceGuard g(code->device);
+    if (!g.ok) return fail(LDPC_ERR_CUDA, "neural_backward_qc_var: cannot select device %d", code->device);
+    NeuralQcBwdParams p{};
+    p.save_x = save_x; p.star = star; p.argmax = argmax; p.g_ml = g_ml; p.w_res = w_res; p.L = L; p.iters = iters;
+    p.B = B; p.g_wch = g_wch; p.g_wres = g_wres;
+    return launch_neural_qc_bwd(code, p, (cudaStream_t)stream);
+}
+
 int ldpc_output_layer_fwd(const float* final_llr, const float* llr, const float* gt, int64_t B, int64_t E, float* soft,
                           float* max_loss, int32_t* argmax, void* stream) {
     if (!final_llr || !llr || !soft) return fail(LDPC_ERR_INVALID, "output_layer_fwd: null argument");

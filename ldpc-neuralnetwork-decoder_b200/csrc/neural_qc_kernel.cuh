@@ -30,7 +30,7 @@ constexpr int kNqColMax[nq::kColClasses] = {6, 8, 10, 13, 16, 23};
 constexpr int kNqColMin[nq::kColClasses] = {5, 7, 9, 12, 14, 22};   // smallest degree that uses the class (no masking below it)
 
 template <class BG>
-constexpr int nq_group_floats() { return BG::kEdges * kNqPitch + 3 * BG::kExtCols * 32 + 8; }
+constexpr int nq_group_floats() { return BG::kEdges * kNqPitch + 3 * BG::kExtCols * 32 + 16; }
 template <class BG>
 constexpr size_t neural_qc_smem_bytes() {      // w_ch tile | per-codeword state | tile addresses of the row chunks (uint16)
     return sizeof(float) * ((size_t)BG::kEdges * 32 + (size_t)kNqGroups * nq_group_floats<BG>()) + sizeof(unsigned short) * BG::kEdges * 32;
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(kNqThreads, 1) neural_qc_kernel(const NeuralQc
     float* lls = nq_smem + EB * 32 + grp * nq_group_floats<BG>();         // [EB][33]  llr_e, later the soft outputs
     float* xe0 = lls + EB * kNqPitch;                                      // [2][NX][32] ring of the degree-1 cells
     float* ces = xe0 + 2 * NX * 32;                                        // [NX][32]  their last check message
-    float* red = ces + NX * 32;                                            // [4] per-member loss maxima
+    float* red = ces + NX * 32;                                            // [4][4] per-member loss maximum, its edge, soft and target
     // where element `lane` of the m-th 32-edge chunk of a row sits in the tile: (D + k) * 33 + r (the same for every codeword)
     unsigned short* tile_addr = reinterpret_cast<unsigned short*>(nq_smem + EB * 32 + kNqGroups * nq_group_floats<BG>());
 
@@ -107,14 +107,33 @@ __global__ void __launch_bounds__(kNqThreads, 1) neural_qc_kernel(const NeuralQc
             const long long nxt = cw0 + (long long)gridDim.x * kNqGroups + grp;
             if (nxt < p.B) {
                 const int t = mem * 32 + lane;                      // 128 threads, one 128-byte line each per step
-                for (int i = t; i < EB; i += nq::kMembers * 32) {
-                    asm volatile("prefetch.global.L2 [%0];" :: "l"(p.llr + nxt * E + 32 * i));
-                    if (p.gt) asm volatile("prefetch.global.L2 [%0];" :: "l"(p.gt + nxt * E + 32 * i));
+                const int lines = p.per_var ? BG::kCols : EB;
+                const long long rowlen = p.per_var ? BG::kCols * 32 : E;
+                for (int i = t; i < lines; i += nq::kMembers * 32) {
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(p.llr + nxt * rowlen + 32 * i));
+                    if (p.gt) asm volatile("prefetch.global.L2 [%0];" :: "l"(p.gt + nxt * rowlen + 32 * i));
                 }
             }
         }
         // ---- load llr_e[cw]: coalesced 128-byte chunks -> [cell][lane] tile ----
-        {
+        if (p.per_var) {
+            // one line per base column, copied to each of the column's cells (the value llr[:, edge_to_var] gives its edges);
+            // a member's 13 lines are requested together
+            const float* src = p.llr + cw * (BG::kCols * 32) + lane;
+            constexpr int kPer = BG::kCols / nq::kMembers;
+            static_assert(kPer * nq::kMembers == BG::kCols, "columns split evenly over the members");
+            float v[kPer];
+#pragma unroll
+            for (int i = 0; i < kPer; ++i) v[i] = __ldg(src + 32 * (mem + i * nq::kMembers));
+#pragma unroll
+            for (int i = 0; i < kPer; ++i) {
+                const int j = mem + i * nq::kMembers;
+                const int D = j < BG::kCoreCols ? (int)nq::col_b0[j] : EC + (j - BG::kCoreCols);
+                const int d = j < BG::kCoreCols ? (int)nq::col_d[j] : 1;
+#pragma unroll 1
+                for (int k = 0; k < d; ++k) lls[(D + k) * kNqPitch + lane] = v[i];
+            }
+        } else {
             const float* src = p.llr + cw * E + lane;
 #pragma unroll 8
             for (int m = mem; m < EB; m += nq::kMembers) lls[tile_addr[m * 32 + lane]] = __ldg(src + 32 * m);
@@ -293,11 +312,45 @@ __global__ void __launch_bounds__(kNqThreads, 1) neural_qc_kernel(const NeuralQc
         // ---- final = VariableLayer(c2v, c2v); OutputLayer: soft = sigmoid(final + llr), staged in the tile ----
         phase_cols(IC<1>{}, 0.0f, 0.0f);
         nq_group_sync(grp);
-        {
+        float best = -CUDART_INF_F, best_s = 0.0f, best_y = 0.0f;
+        int besti = 0x7fffffff;
+        if (p.per_var) {
+            // cell by cell as below, in the tile's own [cell][lane] order: the output of a column's FIRST cell is the variables'
+            // output line; every cell's loss is taken against the column's target line (L1 hits after the first cell);
+            // edge (cell m of the column starting at D with degree d, variable `lane`) = 32 D + lane d + (m - D)
+            float* dst = p.soft + cw * (BG::kCols * 32) + lane;
+            const float* gts = p.gt ? p.gt + cw * (BG::kCols * 32) + lane : nullptr;
+#pragma unroll 1
+            for (int m0 = mem; m0 < EB; m0 += 4 * nq::kMembers) {
+                float sv[4], yv[4];
+                int col[4];
+                static_for<0, 4>([&](auto ic) {
+                    constexpr int i = decltype(ic)::value;
+                    const int m = m0 + i * nq::kMembers;
+                    col[i] = m < EB ? (int)nq::cell_col[m] : 0;
+                    sv[i] = m < EB ? lls[m * kNqPitch + lane] : 0.5f;
+                    yv[i] = (gts && m < EB) ? __ldg(gts + 32 * col[i]) : 0.0f;
+                });
+                static_for<0, 4>([&](auto ic) {
+                    constexpr int i = decltype(ic)::value;
+                    const int m = m0 + i * nq::kMembers;
+                    if (m < EB) {
+                        const unsigned cmeta = nq::chunk_meta[m];
+                        const int D = cmeta & 0xff, d = (cmeta >> 8) & 0x1f;
+                        const float s = sv[i];
+                        if (live && m == D) dst[32 * col[i]] = s;
+                        if (gts) {
+                            const float y = yv[i];
+                            const float l1 = fmaxf(logf(s), -100.0f), l0 = fmaxf(logf(1.0f - s), -100.0f);
+                            const float loss = -(y * l1 + (1.0f - y) * l0);
+                            if (loss > best) { best = loss; besti = 32 * D + lane * d + (m - D); best_s = s; best_y = y; }   // ascending per thread
+                        }
+                    }
+                });
+            }
+        } else {
             float* dst = p.soft + cw * E + lane;
             const float* gts = p.gt ? p.gt + cw * E + lane : nullptr;
-            float best = -CUDART_INF_F;
-            int besti = 0x7fffffff;
             // four chunks at a time: their staged values and ground-truth lines are requested before the first logarithm
             // (training step 9.4 -> 8.5 ms per 32 768 codewords; a separate plain store loop for the no-ground-truth case
             // measured slower for both cases -- the kernel is sensitive to the code layout of its hot loops)
@@ -322,33 +375,34 @@ __global__ void __launch_bounds__(kNqThreads, 1) neural_qc_kernel(const NeuralQc
                             const float y = yv[i];
                             const float l1 = fmaxf(logf(s), -100.0f), l0 = fmaxf(logf(1.0f - s), -100.0f);
                             const float loss = -(y * l1 + (1.0f - y) * l0);
-                            if (loss > best) { best = loss; besti = 32 * m + lane; }      // first (lowest) edge among equal maxima
+                            if (loss > best) { best = loss; besti = 32 * m + lane; best_s = s; best_y = y; }   // first (lowest) edge among equal maxima
                         }
                     }
                 });
             }
-            if (gts) {
+        }
+        if (p.gt) {
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const float ob = __shfl_xor_sync(kFull, best, o);
-                    const int oi = __shfl_xor_sync(kFull, besti, o);
-                    if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
-                }
-                if (lane == 0) { red[mem] = best; red[4 + mem] = __int_as_float(besti); }
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ob = __shfl_xor_sync(kFull, best, o);
+                const int oi = __shfl_xor_sync(kFull, besti, o);
+                const float os = __shfl_xor_sync(kFull, best_s, o), oy = __shfl_xor_sync(kFull, best_y, o);
+                if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; best_s = os; best_y = oy; }
             }
+            if (lane == 0) { red[mem] = best; red[4 + mem] = __int_as_float(besti); red[8 + mem] = best_s; red[12 + mem] = best_y; }
         }
         nq_group_sync(grp);                                  // tile and `red` are complete; the next codeword may overwrite the tile
         if (p.gt && live && mem == 0 && lane == 0) {
-            float best = red[0];
-            int besti = __float_as_int(red[4]);
+            int q = 0;
 #pragma unroll
-            for (int q = 1; q < nq::kMembers; ++q) {
-                const float ob = red[q];
-                const int oi = __float_as_int(red[4 + q]);
-                if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+            for (int t = 1; t < nq::kMembers; ++t) {
+                const float ob = red[t], cb = red[q];
+                const int oi = __float_as_int(red[4 + t]), ci = __float_as_int(red[4 + q]);
+                if (ob > cb || (ob == cb && oi < ci)) q = t;
             }
-            p.max_loss[cw] = best;
-            if (p.argmax) p.argmax[cw] = besti;
+            p.max_loss[cw] = red[q];
+            if (p.argmax) p.argmax[cw] = __float_as_int(red[4 + q]);
+            if (p.star) { p.star[2 * cw] = red[8 + q]; p.star[2 * cw + 1] = red[12 + q]; }
         }
         nq_group_sync(grp);
     }
@@ -429,7 +483,8 @@ __global__ void __launch_bounds__(kNqThreads, 1) neural_qc_bwd_kernel(const Neur
         const int es = __ldg(p.argmax + cw);
         float gz;
         {
-            const float s = __ldg(p.soft + cw * E + es), y = __ldg(p.gt + cw * E + es);
+            const float s = p.star ? __ldg(p.star + 2 * cw) : __ldg(p.soft + cw * E + es);
+            const float y = p.star ? __ldg(p.star + 2 * cw + 1) : __ldg(p.gt + cw * E + es);
             gz = __ldg(p.g_ml + cw) * (s - y) / fmaxf((1.0f - s) * s, 1e-12f) * (s * (1.0f - s));
             if (!live) gz = 0.0f;                                          // a group past the end of the batch contributes nothing
         }

@@ -115,8 +115,8 @@ def _qc_code_for(check_index_tensor, var_index_tensor, num_nodes):
     canon = _QC_CANON.get(dev.index)
     if canon is None:
         code = QCCode.nr_2_0(32)
-        _, c, v, _ = create_LLR_mapping(code.dense().T)
-        canon = _QC_CANON[dev.index] = (code, c.to(dev), v.to(dev))
+        _, c, v, o = create_LLR_mapping(code.dense().T)
+        canon = _QC_CANON[dev.index] = (code, c.to(dev), v.to(dev), torch.as_tensor(o).reshape(-1).to(torch.int64).to(dev))
     for i, (ct, cv, vt, vv, ok) in enumerate(_QC_SEEN):
         if ct is check_index_tensor and vt is var_index_tensor and cv == ct._version and vv == vt._version:
             if i:
@@ -170,6 +170,49 @@ class _NeuralQcTrainFn(torch.autograd.Function):
         return None, None, g_wch, g_wres[:ctx.depth_L], None, None, None
 
 
+class _NeuralQcVarTrainFn(torch.autograd.Function):
+    """_NeuralQcTrainFn with per-variable LLRs and targets, the shape the trainer holds them in (trainer.py:95-110): the kernels
+    expand a variable's value to its edges on chip (ldpc_neural_decode_qc_var), so no (B, E) tensor is built -- neither the two
+    index_select expansions nor the (B, E) soft output.  Bit-identical to the edge-space function on the expanded arrays."""
+
+    @staticmethod
+    def forward(ctx, llr_v, gt_v, w_ch, w_res, code, iters, depth_L):
+        llr_c = llr_v.detach().to(torch.float32).contiguous()
+        y = gt_v.detach().to(torch.float32).contiguous()
+        wch = w_ch.detach().to(torch.float32).contiguous()
+        wres = w_res.detach().to(torch.float32).contiguous()
+        B = llr_c.shape[0]
+        E = wch.numel()
+        dev = llr_c.device
+        soft = torch.empty_like(llr_c)
+        ml = torch.empty(B, dtype=torch.float32, device=dev)
+        am = torch.empty(B, dtype=torch.int32, device=dev)
+        star = torch.empty((B, 2), dtype=torch.float32, device=dev)
+        save_x = torch.empty((iters, B, E), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _native.check(_native.lib().ldpc_neural_decode_qc_var(
+                code.handle(dev), _native.ptr(llr_c), _native.ptr(wch), _native.ptr(wres), depth_L, iters, B, _native.ptr(y),
+                _native.ptr(soft), _native.ptr(ml), _native.ptr(save_x), _native.ptr(am), _native.ptr(star), _native.stream_ptr(dev)))
+        ctx.save_for_backward(save_x, star, am, wres)
+        ctx.code, ctx.iters, ctx.depth_L, ctx.E = code, iters, depth_L, E
+        ctx.mark_non_differentiable(soft)
+        return soft, ml
+
+    @staticmethod
+    def backward(ctx, _g_soft, g_ml):
+        save_x, star, am, wres = ctx.saved_tensors
+        dev = star.device
+        B = star.shape[0]
+        g = (g_ml if g_ml is not None else torch.zeros(B, device=dev)).to(torch.float32).contiguous()
+        g_wch = torch.zeros(ctx.E, dtype=torch.float32, device=dev)
+        g_wres = torch.zeros(max(ctx.depth_L, 1), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _native.check(_native.lib().ldpc_neural_backward_qc_var(
+                ctx.code.handle(dev), _native.ptr(save_x), _native.ptr(star), _native.ptr(am), _native.ptr(g),
+                _native.ptr(wres), ctx.depth_L, ctx.iters, B, _native.ptr(g_wch), _native.ptr(g_wres), _native.stream_ptr(dev)))
+        return None, None, g_wch, g_wres[:ctx.depth_L], None, None, None
+
+
 class LDPCNeuralDecoder(nn.Module):
     def __init__(self, num_nodes, num_iterations=5, depth_L=2, output_index_tensor=None, fused=True, qc=True):
         super().__init__()
@@ -195,9 +238,14 @@ class LDPCNeuralDecoder(nn.Module):
                 raise ValueError("output_index_tensor leaves a variable without an edge")
             self.register_buffer("edge_to_var", m, persistent=False)
             self.register_buffer("var_first_edge", first, persistent=False)
+            # create_LLR_mapping's numbering (edges of a variable consecutive, variables ascending): the QC kernels can then
+            # take (B, N) LLRs / targets and expand them on chip
+            self._var_major = bool(torch.equal(m, torch.sort(m).values))
         else:
             self.edge_to_var = None
             self.var_first_edge = None
+            self._var_major = False
+        self._etv_canonical = None      # edge_to_var equals the 5G BG2 Z=32 mapping (checked once, on the first per-variable call)
 
     # -- helpers ---------------------------------------------------------------------------
     def _to_edges(self, t):
@@ -278,11 +326,53 @@ class LDPCNeuralDecoder(nn.Module):
                 _native.ptr(ml), _native.stream_ptr(llr_c.device)))
         return soft, ml
 
+    def _forward_per_variable(self, llr_v, check_index_tensor, var_index_tensor, gt_v):
+        """(B, N) LLRs (and targets) straight into the QC-structured kernels; None when this call cannot take that path (tables
+        that are not the 5G BG2 Z=32 ones, targets in edge space, gradients w.r.t. the LLRs, no targets while training)."""
+        n_var = self.var_first_edge.numel()
+        if llr_v.dim() != 2 or llr_v.shape[1] != n_var or n_var != 52 * 32:
+            return None
+        if gt_v is not None and tuple(gt_v.shape) != tuple(llr_v.shape):
+            return None
+        if check_index_tensor.shape[0] != self.num_nodes or var_index_tensor.shape[0] != self.num_nodes:
+            return None
+        needs_grad = torch.is_grad_enabled() and (llr_v.requires_grad or any(p.requires_grad for p in self.parameters()))
+        if needs_grad and (gt_v is None or llr_v.requires_grad):
+            return None
+        code = _qc_code_for(check_index_tensor, var_index_tensor, self.num_nodes)
+        if code is None:
+            return None
+        if self._etv_canonical is None:
+            dev = check_index_tensor.device
+            self._etv_canonical = bool(torch.equal(self.edge_to_var.to(dev), _QC_CANON[dev.index][3]))
+        if not self._etv_canonical:
+            return None
+        w_ch_t, w_res_t = self._weights()
+        if needs_grad:
+            return _NeuralQcVarTrainFn.apply(llr_v, gt_v, w_ch_t, w_res_t, code, self.num_iterations, self.depth_L)
+        llr_c = llr_v.detach().to(torch.float32).contiguous()
+        w_ch = w_ch_t.detach().to(torch.float32).contiguous()
+        w_res = w_res_t.detach().to(torch.float32).contiguous()
+        y = gt_v.detach().to(torch.float32).contiguous() if gt_v is not None else None
+        B = llr_c.shape[0]
+        soft = torch.empty_like(llr_c)
+        ml = torch.empty(B, dtype=torch.float32, device=llr_c.device) if y is not None else None
+        with torch.cuda.device(llr_c.device):
+            _native.check(_native.lib().ldpc_neural_decode_qc_var(
+                code.handle(llr_c.device), _native.ptr(llr_c), _native.ptr(w_ch), _native.ptr(w_res), self.depth_L,
+                self.num_iterations, B, _native.ptr(y), _native.ptr(soft), _native.ptr(ml), None, None, None,
+                _native.stream_ptr(llr_c.device)))
+        return soft, ml
+
     # -- reference-shaped API ----------------------------------------------------------------
     def forward(self, input_llr, check_index_tensor, var_index_tensor, ground_truth=None):
         """-> (soft_bits, max_loss | None); trainer.py:102,180 call shape."""
         _need_cuda(input_llr, check_index_tensor, var_index_tensor, ground_truth)
         per_variable = self.edge_to_var is not None and input_llr.shape[1] != self.num_nodes
+        if per_variable and self._var_major and self.fused and self.qc and self.depth_L <= 2:
+            out = self._forward_per_variable(input_llr, check_index_tensor, var_index_tensor, ground_truth)
+            if out is not None:
+                return out
         llr_e = self._to_edges(input_llr).to(torch.float32)
         gt_e = self._to_edges(ground_truth)
         needs_grad = torch.is_grad_enabled() and (llr_e.requires_grad or any(

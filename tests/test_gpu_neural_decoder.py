@@ -363,3 +363,61 @@ def test_qc_structured_kernels_against_the_reference_layers_at_z32():
     with torch.no_grad():                                            # inference launch of the same kernel
         s2, m2 = dec(x, cidx, vidx, y)
     assert torch.equal(s2, soft.detach()) and torch.equal(m2, ml.detach())
+
+
+@pytest.mark.parametrize("depth_L,iters", [(2, 5), (1, 3), (0, 2)])
+def test_per_variable_qc_path_is_bit_identical_to_the_expanded_edge_space_path(depth_L, iters):
+    """The trainer's call shape (trainer.py:95-110,180-187): (B, N) LLRs and targets.  ldpc_neural_decode_qc_var /
+    ldpc_neural_backward_qc_var expand a variable's value to its edges on chip; against the edge-space kernels fed with
+    llr[:, edge_to_var] / gt[:, edge_to_var]: soft outputs (at each variable's first edge) and max_loss EQUAL, in inference
+    and in training, gradients within rounding of the accumulation order (atomics), and exactly two kernel launches per
+    training step with no index_select expansion."""
+    code = QCCode.nr_2_0(32)
+    _, cidx, vidx, oidx = create_LLR_mapping(code.dense().T)
+    cidx, vidx = cidx.to(DEV), vidx.to(DEV)
+    etv = torch.as_tensor(oidx).reshape(-1).to(torch.int64)
+    rng = np.random.default_rng(31 + depth_L)
+    B = 4 * 148 + 3
+    llr = torch.from_numpy(((rng.normal(size=(B, code.N)) * 0.3 + 0.2) * 0.5).astype(np.float32)).to(DEV)
+    gt = torch.from_numpy((rng.random((B, code.N)) < 0.7).astype(np.float32)).to(DEV)
+    w_ch = torch.from_numpy((rng.random(code.E) * 0.5 + 0.75).astype(np.float32))
+    w_res = torch.tensor([0.2, -0.1][:depth_L])
+
+    def make(with_map):
+        d = LDPCNeuralDecoder(code.E, iters, depth_L, output_index_tensor=oidx if with_map else None).to(DEV)
+        with torch.no_grad():
+            d.residual_layer.w_ch.copy_(w_ch)
+            d.residual_layer.w_res.copy_(w_res)
+        return d
+    dv, de = make(True), make(False)
+    llr_e, gt_e = llr[:, etv.to(DEV)].contiguous(), gt[:, etv.to(DEV)].contiguous()
+    first = dv.var_first_edge.to(DEV)
+    lib = ldpc_b200._native.lib()
+    # inference, without and with targets
+    with torch.no_grad():
+        n0 = lib.ldpc_launch_count()
+        s_v, none = dv(llr, cidx, vidx)
+        assert lib.ldpc_launch_count() - n0 == 1 and none is None and s_v.shape == llr.shape
+        s_e, _ = de(llr_e, cidx, vidx)
+        assert torch.equal(s_v, s_e[:, first])
+        s_v, m_v = dv(llr, cidx, vidx, gt)
+        s_e, m_e = de(llr_e, cidx, vidx, gt_e)
+        assert torch.equal(s_v, s_e[:, first]) and torch.equal(m_v, m_e)
+    # training step
+    up = torch.linspace(0.5, 1.5, B, device=DEV)
+    n0 = lib.ldpc_launch_count()
+    s_v, m_v = dv(llr, cidx, vidx, gt)
+    (m_v * up).mean().backward()
+    assert lib.ldpc_launch_count() - n0 == 2
+    s_e, m_e = de(llr_e, cidx, vidx, gt_e)
+    (m_e * up).mean().backward()
+    assert torch.equal(s_v.detach(), s_e.detach()[:, first]) and torch.equal(m_v.detach(), m_e.detach())
+    gv, ge = dv.residual_layer.w_ch.grad, de.residual_layer.w_ch.grad
+    assert float(ge.abs().max()) > 0 and float((gv - ge).abs().max()) <= 1e-5 * float(ge.abs().max())
+    if depth_L:
+        rv, re_ = dv.residual_layer.w_res.grad, de.residual_layer.w_res.grad
+        assert float((rv - re_).abs().max()) <= 1e-5 * max(float(re_.abs().max()), 1e-12)
+    # targets in edge space with LLRs per variable: not this path's shape -> the expansion path, same numbers
+    with torch.no_grad():
+        s_m, m_m = dv(llr, cidx, vidx, gt_e)
+    assert torch.equal(s_m, s_v.detach()) and torch.equal(m_m, m_v.detach())

@@ -49,18 +49,26 @@ def main():
     llr_e = llr[:, oidx[0].to(dev)].contiguous()
     gt = torch.ones_like(llr_e)
     out = {"batch": args.batch, "iters": args.iters, "Z": args.z, "E": code.E, "lib": args.lib}
-    for tag, fused, qc in (("qc", True, True), ("fused", True, False), ("composed", False, False)):
-        if tag == "qc" and args.z != 32:
+    gt_v = torch.ones_like(llr)
+    # qc_var: the trainer's call shape, (B, N) LLRs and targets straight into the QC kernels; qc_var_expand: the same call
+    # through index_select expansions to (B, E) (what that shape cost before the per-variable kernels existed)
+    for tag, fused, qc in (("qc", True, True), ("qc_var", True, True), ("qc_var_expand", True, True), ("fused", True, False),
+                           ("composed", False, False)):
+        if tag.startswith("qc") and args.z != 32:
             continue
-        dec = LDPCNeuralDecoder(code.E, args.iters, 2, fused=fused, qc=qc).to(dev)
+        var_shape = tag.startswith("qc_var")
+        dec = LDPCNeuralDecoder(code.E, args.iters, 2, output_index_tensor=oidx if var_shape else None, fused=fused, qc=qc).to(dev)
+        if tag == "qc_var_expand":
+            dec._var_major = False
+        xin, yin = (llr, gt_v) if var_shape else (llr_e, gt)
 
         def infer():
             with torch.no_grad():
-                dec(llr_e, cidx, vidx)
+                dec(xin, cidx, vidx)
 
         def train():
             dec.zero_grad(set_to_none=True)
-            _, ml = dec(llr_e, cidx, vidx, gt)
+            _, ml = dec(xin, cidx, vidx, yin)
             ml.mean().backward()
 
         ms_i, ms_t = timed(infer, args.reps), timed(train, args.reps)
