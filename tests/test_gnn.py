@@ -173,7 +173,7 @@ np.savez(sys.argv[2], probs=probs.detach().cpu().numpy(), loss=float(loss), grad
 def test_tensor_core_and_ffma_paths_agree(tmp_path):
     """The tcgen05 kernels (forward pipeline, node kernel, data and weight gradients) against the fp32 FFMA kernels
     (LDPC_GNN_FFMA=1, read once per process -> two subprocesses) on a ragged batch with random targets: probabilities
-    to 2e-5, loss to 1e-6 relative, every gradient entry to 2e-4 of the gradient's scale."""
+    to 2e-5, loss to 5e-6 relative, every gradient entry to 2e-4 of the gradient's scale."""
     import os, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     script = tmp_path / "run.py"
@@ -187,7 +187,9 @@ def test_tensor_core_and_ffma_paths_agree(tmp_path):
         res[tag] = np.load(out)
     a, b = res["tc"], res["ffma"]
     assert np.max(np.abs(a["probs"] - b["probs"])) <= 2e-5
-    assert abs(float(a["loss"]) - float(b["loss"])) <= 1e-6 * abs(float(b["loss"]))
+    # the mean loss is an fp32 atomicAdd over ~2 000 warp partials in arrival order: a few 1e-6 relative between ANY two runs
+    # (measured 0.3e-6 .. 1.4e-6 between runs of the same path), so 1e-6 was inside the noise; 5e-6 is not
+    assert abs(float(a["loss"]) - float(b["loss"])) <= 5e-6 * abs(float(b["loss"]))
     scale = np.max(np.abs(b["grad"]))
     assert scale > 0 and np.max(np.abs(a["grad"] - b["grad"])) <= 2e-4 * scale
     assert np.array_equal(a["grad"] == 0, b["grad"] == 0)           # same parameters without gradient
@@ -212,7 +214,7 @@ def test_pipelined_and_serial_node_kernels_are_bit_identical(tmp_path):
     a, b = res["pipe"], res["serial"]
     assert np.array_equal(a["probs"], b["probs"]), float(np.max(np.abs(a["probs"] - b["probs"])))
     # the loss reduction and the weight gradients are accumulated with atomics: compare to rounding, not bit for bit
-    assert abs(float(a["loss"]) - float(b["loss"])) <= 2e-6 * abs(float(b["loss"]))
+    assert abs(float(a["loss"]) - float(b["loss"])) <= 5e-6 * abs(float(b["loss"]))
     scale = np.max(np.abs(b["grad"]))
     assert np.max(np.abs(a["grad"] - b["grad"])) <= 1e-5 * scale
 
