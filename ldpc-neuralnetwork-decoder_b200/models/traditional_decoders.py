@@ -34,7 +34,8 @@ class _FloodingDecoder:
     _ALGO = None
 
     def __init__(self, H=None, max_iterations=50, early_stopping=True, base_graph=None, Z=None, path="auto", check_finite=True):
-        self.code = as_code(H, base_graph, Z)
+        self.code = as_code(H, base_graph, Z, allow_split=True)     # Z > 32: held as an equivalent code with Z <= 32, renumbered
+        self._perm = {}                                              # device -> (engine <- natural, natural <- engine) index tensors
         # check_finite: look for +-inf / NaN LLRs before every decode under path="auto" (one reduction over the batch and a
         # host sync, ~0.1 ms) and send such batches to the reference-order kernel; False skips the look-up for callers
         # that know their LLRs are finite (a demapper's clipped output)
@@ -62,6 +63,8 @@ class _FloodingDecoder:
                 raise RuntimeError("the LDPC engine needs a CUDA device (no CPU fallback)")
             dev = torch.device("cuda", torch.cuda.current_device())
         llr_d = llr.detach().to(device=dev, dtype=torch.float32).contiguous()
+        if self.code.var_old_of_new is not None:
+            llr_d = llr_d.index_select(1, self._perms(dev)[0])
         # path "auto" sends min-sum to the specialised kernel, whose variable update is posterior - own message: with
         # +-inf channel LLRs (hard-decision inputs) that is inf - inf = NaN where the reference's sum over the OTHER
         # checks keeps inf (traditional_decoders.py:235-244).  Such batches take the reference-order kernel.
@@ -78,6 +81,19 @@ class _FloodingDecoder:
             if bad:
                 self._route = "exact"
         return llr_d, dev
+
+    def _perms(self, dev):
+        """Index tensors of a renumbered (Z > 32) code on `dev`: engine order <- natural order, and back."""
+        key = (dev.type, dev.index)
+        if key not in self._perm:
+            self._perm[key] = (torch.from_numpy(self.code.var_old_of_new).to(dev), torch.from_numpy(self.code.var_new_of_old).to(dev))
+        return self._perm[key]
+
+    def _natural(self, t, dev):
+        """(B, N) engine-order output -> the caller's variable order."""
+        if t is None or self.code.var_old_of_new is None or t.dim() != 2 or t.shape[1] != self.code.N:
+            return t
+        return t.index_select(1, self._perms(dev)[1])
 
     def _launch(self, llr_d, dev, iters, stop_mode=_native.STOP_FIXED, soft=True, hard_dtype=_native.HARD_F32,
                 syndrome=False, iters_out=False, mask=False, path=None):
@@ -109,7 +125,9 @@ class _FloodingDecoder:
                                       _native.ptr(hard_t), hard_dtype, _native.ptr(syn_t), _native.ptr(it_t),
                                       _native.ptr(mask_t), words, st)
         _native.check(rc)
-        return soft_t, hard_t, syn_t, it_t, mask_t
+        if hard_dtype != _native.HARD_PACKED:                   # packed words are only used internally (validity probes)
+            hard_t = self._natural(hard_t, dev)
+        return self._natural(soft_t, dev), hard_t, syn_t, it_t, mask_t
 
     @staticmethod
     def _first_all_valid(mask_t, iters):
@@ -195,6 +213,8 @@ class _FloodingDecoder:
             hard, dtype = bits.to(dev).contiguous(), _native.HARD_U8
         else:
             hard, dtype = bits.to(device=dev, dtype=torch.float32).contiguous(), _native.HARD_F32
+        if self.code.var_old_of_new is not None:
+            hard = hard.index_select(1, self._perms(dev)[0])
         ok = torch.empty(bits.shape[0], dtype=torch.uint8, device=dev)
         if bits.shape[0]:
             with torch.cuda.device(dev):

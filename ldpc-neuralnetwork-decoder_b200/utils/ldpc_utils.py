@@ -112,15 +112,57 @@ class QCCode:
         self.E = self.base_edges * Z
         self.K = self.N - self.M
         self._handles = {}
+        # set by from_base_matrix(..., allow_split=True) for a lifting factor above MAX_Z: the code is held as an equivalent
+        # QC code with a smaller lifting factor and its variables / checks renumbered (see _split_lifting)
+        self.lift_Z = None              # the caller's lifting factor
+        self.lift_shifts = None         # the caller's base graph (shifts mod lift_Z)
+        self.var_old_of_new = None      # (N,) int64: caller's variable index of each engine variable
+        self.var_new_of_old = None      # (N,) int64: the inverse
 
     # ---- constructors ----
     @classmethod
-    def from_base_matrix(cls, base_matrix, Z):
+    def from_base_matrix(cls, base_matrix, Z, allow_split=False):
         """Base graph as the reference's files hold it: non-negative shifts are taken mod Z, exactly what
         expand_base_matrix's roll does (ldpc_utils.py:121-123), so `NR_2_0_32.txt` lifted with Z=16 works as it
-        does upstream.  The raw constructor keeps the strict [0, Z) check."""
+        does upstream.  The raw constructor keeps the strict [0, Z) check.
+
+        Z > 32 (the reference accepts any --lifting_factor, main.py:38): with allow_split the code is rewritten as an
+        equivalent QC code with lifting factor Zs = the largest divisor of Z that is <= 32 (_split_lifting) and a
+        renumbering of its variables; the classic decoders apply the renumbering to their inputs and outputs, so the
+        caller sees the natural order.  Other consumers (GNN, encoder, simulation) do not take such codes."""
         s = np.rint(np.asarray(torch.as_tensor(base_matrix).cpu().numpy(), dtype=np.float64)).astype(np.int64)
-        return cls(np.where(s >= 0, s % int(Z), -1), Z)
+        Z = int(Z)
+        if Z <= cls.MAX_Z or not allow_split:
+            return cls(np.where(s >= 0, s % Z, -1), Z)
+        nat = np.where(s >= 0, s % Z, -1)
+        Zs = max(z for z in range(1, cls.MAX_Z + 1) if Z % z == 0)
+        code = cls(cls._split_lifting(nat, Z, Zs), Zs)
+        m = Z // Zs
+        new = np.arange(code.N, dtype=np.int64)
+        jb, a = np.divmod(new, Zs)
+        j, b = np.divmod(jb, m)
+        code.var_old_of_new = j * Z + m * a + b
+        code.var_new_of_old = np.empty_like(code.var_old_of_new)
+        code.var_new_of_old[code.var_old_of_new] = new
+        code.lift_Z, code.lift_shifts = Z, nat.astype(np.int64)
+        return code
+
+    @staticmethod
+    def _split_lifting(shifts, Z, Zs):
+        """A Z x Z circulant with Z = m * Zs becomes an m x m block pattern of Zs x Zs circulants once rows and columns
+        are renumbered r = m * a + b  ->  (b, a): row (b, a) of the shift-s circulant (s = m * q + t) meets column
+        (b', a') with b' = (b + t) mod m and a' = a + q + carry, carry = (b + t) div m, i.e. block (b, b') is the
+        circulant with shift (q + carry) mod Zs.  Base row i / column j and, inside them, the order of the cells are
+        kept, so every check still meets its variables in ascending order and every variable its checks: the decoders'
+        operation order -- and with it every bit of their output -- is that of the natural numbering."""
+        m = Z // Zs
+        rows, cols = shifts.shape
+        out = np.full((rows * m, cols * m), -1, dtype=np.int64)
+        for i, j in zip(*np.nonzero(shifts >= 0)):
+            q, t = divmod(int(shifts[i, j]), m)
+            for b in range(m):
+                out[i * m + b, j * m + (b + t) % m] = (q + (b + t) // m) % Zs
+        return out
 
     @classmethod
     def from_file(cls, path, Z):
@@ -189,10 +231,12 @@ class QCCode:
 
     # ---- views ----
     def base_matrix(self):
-        return torch.from_numpy(self.shifts.astype(np.float32))
+        """The base graph in the caller's terms (for a split code: the one it was built from, to be lifted with lift_Z)."""
+        src = self.shifts if self.lift_shifts is None else self.lift_shifts
+        return torch.from_numpy(src.astype(np.float32))
 
     def dense(self):
-        return expand_base_matrix(self.base_matrix(), self.Z)
+        return expand_base_matrix(self.base_matrix(), self.Z if self.lift_Z is None else self.lift_Z)
 
     def edges(self):
         """(check, variable) arrays of all E Tanner edges in check-major, ascending-variable
@@ -247,14 +291,16 @@ class _Handle:
             pass
 
 
-def as_code(H=None, base_graph=None, Z=None):
-    """Resolve the constructor arguments of the drop-in decoders to a QCCode."""
+def as_code(H=None, base_graph=None, Z=None, allow_split=False):
+    """Resolve the constructor arguments of the drop-in decoders to a QCCode (allow_split: see QCCode.from_base_matrix)."""
     if isinstance(H, QCCode):
+        if H.lift_Z is not None and not allow_split:
+            raise ValueError(f"a code with lifting factor {H.lift_Z} > {QCCode.MAX_Z} is supported by the classic decoders only")
         return H
     if base_graph is not None:
         if Z is None:
             raise ValueError("base_graph given without Z")
-        return QCCode.from_base_matrix(base_graph, Z)
+        return QCCode.from_base_matrix(base_graph, Z, allow_split=allow_split)
     if H is None:
         raise ValueError("need a parity-check matrix H, a QCCode, or (base_graph, Z)")
     return QCCode.from_dense(H, Z)

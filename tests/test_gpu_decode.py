@@ -484,3 +484,46 @@ def test_auto_path_routes_non_finite_llrs_to_the_reference_order_kernel():
     fin = oracle.awgn_llr(None, 64, code.N, -2.0, seed=13)
     sf, _ = run(auto, fin)
     assert np.array_equal(sf, oracle.decode(code.shifts, 32, fin, 10, "minsum", 0.75, order="fast")["beliefs"])
+
+
+@pytest.mark.parametrize("Z,B,iters", [(64, 37, 6), (96, 9, 4), (48, 50, 5)])
+def test_lifting_factors_above_32_decode_like_the_oracle(Z, B, iters):
+    """Z > 32 through the classic decoders' (base_graph, Z) constructor: the code is held as an equivalent code with a smaller lifting
+    factor (tests/test_host_logic.py) and inputs / outputs are renumbered, so beliefs, decisions and validity must equal the
+    oracle's run on the natural code -- bit for bit for min-sum (the operation order is preserved), decisions for BP."""
+    rng = np.random.default_rng(Z)
+    support = QCCode.nr_2_0(32).shifts >= 0
+    base = np.where(support, rng.integers(0, Z, size=support.shape), -1)
+    llr = oracle.awgn_llr(None, B, 52 * Z, 1.0, seed=Z)
+    o = oracle.decode(base, Z, llr, iters, "minsum", 0.75)
+    dec = MinSumScaledDecoder(base_graph=torch.from_numpy(base.astype(np.float32)), Z=Z, max_iterations=iters, scaling_factor=0.75,
+                              early_stopping=False)
+    soft, hard = run(dec, llr)
+    assert np.array_equal(soft, o["beliefs"]) and np.array_equal(hard, o["hard"])
+    ok = dec._check_valid_codeword(torch.from_numpy(o["hard"]).to(dev())).cpu().numpy()
+    H = dec.code.dense().numpy()
+    assert np.array_equal(ok, ((o["hard"].astype(np.int64) @ H.T) % 2 == 0).all(axis=1))
+    bits, its, syn = dec.decode_with_iterations(torch.from_numpy(llr).to(dev()))
+    assert np.array_equal(bits.cpu().numpy(), o["hard"]) and np.array_equal(syn.cpu().numpy(), ok)
+    ob = oracle.decode(base, Z, llr, iters, "bp")
+    _, hb = run(BeliefPropagationDecoder(base_graph=torch.from_numpy(base.astype(np.float32)), Z=Z, max_iterations=iters,
+                                         early_stopping=False), llr)
+    assert np.array_equal(hb, ob["hard"])
+    # early stopping: the reference's batch-global rule on a batch that converges
+    llr_hi = oracle.awgn_llr(None, 8, 52 * Z, 6.0, seed=Z + 1)
+    oe = oracle.decode(base, Z, llr_hi, 20, "minsum", 0.75, want_mask=True)
+    t = oracle.first_all_valid(oe["valid_mask"], 20)
+    hard_e, n_it = MinSumScaledDecoder(base_graph=torch.from_numpy(base.astype(np.float32)), Z=Z, max_iterations=20).decode(
+        torch.from_numpy(llr_hi).to(dev()))
+    assert t is not None and n_it == t + 1
+    assert np.array_equal(hard_e.cpu().numpy(), oracle.decode(base, Z, llr_hi, t + 1, "minsum", 0.75)["hard"])
+
+
+def test_lifting_factor_too_large_for_the_generic_kernel_fails_loudly():
+    """Z = 384 = 12 x 32: 2 364 + 2 x 624 cell rows of 128 bytes do not fit one SM's shared memory; the call must say so."""
+    from ldpc_b200 import _native
+    base = np.where(QCCode.nr_2_0(32).shifts >= 0, 1, -1)
+    dec = MinSumScaledDecoder(base_graph=torch.from_numpy(base.astype(np.float32)), Z=384, max_iterations=2, early_stopping=False)
+    with pytest.raises(_native.LdpcError) as e:
+        dec.decode(torch.zeros((1, 52 * 384), device=dev()))
+    assert e.value.code == _native.ERR_UNSUPPORTED

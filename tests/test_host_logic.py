@@ -356,3 +356,32 @@ def test_neural_qc_schedule_tables_cover_the_base_graph_exactly_once():
         j = int(np.searchsorted(vm0, m, side="right") - 1)
         assert D == vm0[j] and d == deg_c[j]
         assert all(((off * inv) >> 16) == off // d for off in range(32 * d))
+
+
+@pytest.mark.parametrize("Z", [33, 36, 48, 64, 96, 384])
+def test_lifting_factors_above_32_are_rewritten_as_an_equivalent_code(Z):
+    """The reference lifts with any --lifting_factor (main.py:38, expand_base_matrix).  QCCode.from_base_matrix(..., allow_split=True)
+    holds Z > 32 as an equivalent QC code with Zs = the largest divisor of Z <= 32 and renumbered variables / checks: its expanded
+    H must be the reference's expanded H with rows and columns permuted by exactly that renumbering, and cell order inside a
+    base row / column must be preserved (so the decoders keep the reference's operation order)."""
+    import torch
+    from ldpc_b200.utils import QCCode
+    from ldpc_b200.utils.ldpc_utils import expand_base_matrix
+    rng = np.random.default_rng(Z)
+    support = QCCode.nr_2_0(32).shifts >= 0
+    base = np.where(support, rng.integers(0, 4 * Z, size=support.shape), -1)          # raw shifts beyond Z: taken mod Z as upstream
+    code = QCCode.from_base_matrix(base, Z, allow_split=True)
+    assert code.lift_Z == Z and code.Z <= 32 and Z % code.Z == 0 and code.N == 52 * Z and code.M == 42 * Z
+    m = Z // code.Z
+    H_nat = expand_base_matrix(torch.from_numpy(base.astype(np.float32)), Z).numpy()
+    H_eng = expand_base_matrix(torch.from_numpy(code.shifts.astype(np.float32)), code.Z).numpy()
+    ib, a = np.divmod(np.arange(code.M), code.Z)
+    i, b = np.divmod(ib, m)
+    chk_old = i * Z + m * a + b
+    assert np.array_equal(H_eng, H_nat[np.ix_(chk_old, code.var_old_of_new)])
+    assert np.array_equal(code.var_new_of_old[code.var_old_of_new], np.arange(code.N))
+    assert np.array_equal(code.dense().numpy(), H_nat)                                # dense() speaks the caller's numbering
+    # base row / column majority of the renumbering: the engine index of a variable grows with its base column, of a check with its base row
+    assert np.array_equal(code.var_old_of_new // Z, np.arange(code.N) // Z)
+    with pytest.raises(ValueError):
+        QCCode.from_base_matrix(base, Z)                                              # other consumers: Z <= 32 only
