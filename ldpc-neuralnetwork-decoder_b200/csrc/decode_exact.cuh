@@ -49,13 +49,15 @@ __device__ __forceinline__ bool syndrome_bad(const Tab<kConst>& tab, const float
 }
 
 template <int kAlgo, int kMaxDc, int kMaxDv, bool kConst>
-__global__ void __launch_bounds__(256) decode_exact_kernel(const DecodeParams p) {
+__global__ void __launch_bounds__(256) decode_exact_kernel(const DecodeParams p, float* __restrict__ scratch) {
+    // scratch != nullptr: the per-warp state (messages, posteriors, LLRs) does not fit shared memory (large lifting factors
+    // held as many small circulants, large Z = 1 codes) and lives in a global workspace instead -- same code, L2 speed
     extern __shared__ float smem[];
     const Tab<kConst> tab{p.gtab, p.slot};
     const int rows = tab[0], cols = tab[1], Z = tab[2], E = tab[3], G = tab[4];
     const int off_rowptr = tab[7], off_colptr = tab[8], off_redge = tab[9], off_cedge = tab[10];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
-    float* msg = smem + (size_t)warp * p.floats_per_warp;
+    float* msg = scratch ? scratch + ((size_t)blockIdx.x * W + warp) * p.floats_per_warp : smem + (size_t)warp * p.floats_per_warp;
     float* T = msg + E * 32;
     float* L = T + cols * 32;
     const bool active = lane < G * Z;
@@ -283,12 +285,12 @@ __global__ void __launch_bounds__(256) decode_exact_kernel(const DecodeParams p)
 template <bool kConst>
 __global__ void __launch_bounds__(256) syndrome_kernel(const uint32_t* gtab, int slot, const void* __restrict__ hard,
                                                         int hard_dtype, long long B, long long ngroups,
-                                                        uint8_t* __restrict__ ok_out) {
+                                                        uint8_t* __restrict__ ok_out, float* __restrict__ scratch) {
     extern __shared__ float smem[];
     const Tab<kConst> tab{gtab, slot};
     const int rows = tab[0], cols = tab[1], Z = tab[2], G = tab[4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
-    float* T = smem + (size_t)warp * cols * 32;
+    float* T = scratch ? scratch + ((size_t)blockIdx.x * W + warp) * cols * 32 : smem + (size_t)warp * cols * 32;
     const bool active = lane < G * Z;
     const int cwi = active ? lane / Z : 0, r = active ? lane - cwi * Z : 0, base = cwi * Z, N = cols * Z;
     const unsigned gmask = (Z == 32) ? 0xffffffffu : (((1u << Z) - 1u) << base);
@@ -316,21 +318,48 @@ __global__ void __launch_bounds__(256) syndrome_kernel(const uint32_t* gtab, int
     }
 }
 
+// Global workspace for codes whose per-warp state exceeds shared memory: at most ~1 GB, stream-ordered allocation
+struct ExactScratch {
+    float* ptr = nullptr;
+    int W = 0;
+    long long blocks = 0;
+    cudaStream_t st = nullptr;
+    int init(size_t per_warp, long long ngroups, cudaStream_t stream, const char* who) {
+        st = stream;
+        long long warps = (long long)((size_t)1 << 30) / (long long)per_warp;
+        if (warps < 1) return fail(LDPC_ERR_UNSUPPORTED, "%s: %zu bytes of state per warp", who, per_warp);
+        if (warps > (long long)kNumSMs * 8) warps = (long long)kNumSMs * 8;
+        if (warps > ngroups) warps = ngroups;
+        W = warps < 8 ? (int)warps : 8;
+        blocks = warps / W;
+        LDPC_CUDA(cudaMallocAsync((void**)&ptr, per_warp * (size_t)W * (size_t)blocks, st));
+        return LDPC_OK;
+    }
+    ~ExactScratch() { if (ptr) cudaFreeAsync(ptr, st); }
+};
+
 inline int launch_syndrome(const ldpc_code* c, const void* hard, int hard_dtype, long long B, uint8_t* ok, cudaStream_t st) {
     const size_t per_warp = (size_t)c->cols * 32 * sizeof(float);
     int W = (int)(kMaxSmemPerBlock / per_warp);
-    if (W < 1) return fail(LDPC_ERR_UNSUPPORTED, "syndrome_check: code too large for shared memory");
-    if (W > 8) W = 8;
     const long long ngroups = (B + c->G - 1) / c->G;
-    long long blocks = (ngroups + W - 1) / W;
-    if (blocks > (long long)kNumSMs * 4) blocks = (long long)kNumSMs * 4;
-    const size_t smem = per_warp * W;
+    ExactScratch sc;
+    long long blocks;
+    size_t smem = 0;
+    if (W < 1) {
+        if (int rc = sc.init(per_warp, ngroups, st, "syndrome_check")) return rc;
+        W = sc.W; blocks = sc.blocks;
+    } else {
+        if (W > 8) W = 8;
+        blocks = (ngroups + W - 1) / W;
+        if (blocks > (long long)kNumSMs * 4) blocks = (long long)kNumSMs * 4;
+        smem = per_warp * W;
+    }
     if (c->slot >= 0) {
         LDPC_CUDA(cudaFuncSetAttribute(syndrome_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        syndrome_kernel<true><<<(int)blocks, W * 32, smem, st>>>(c->d_tab, c->slot, hard, hard_dtype, B, ngroups, ok);
+        syndrome_kernel<true><<<(int)blocks, W * 32, smem, st>>>(c->d_tab, c->slot, hard, hard_dtype, B, ngroups, ok, sc.ptr);
     } else {
         LDPC_CUDA(cudaFuncSetAttribute(syndrome_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        syndrome_kernel<false><<<(int)blocks, W * 32, smem, st>>>(c->d_tab, 0, hard, hard_dtype, B, ngroups, ok);
+        syndrome_kernel<false><<<(int)blocks, W * 32, smem, st>>>(c->d_tab, 0, hard, hard_dtype, B, ngroups, ok, sc.ptr);
     }
     LDPC_CHECK_LAUNCH("syndrome_kernel");
     return LDPC_OK;
@@ -338,10 +367,10 @@ inline int launch_syndrome(const ldpc_code* c, const void* hard, int hard_dtype,
 
 // ---- host launcher ----------------------------------------------------------------------
 template <int kAlgo, int kMaxDc, int kMaxDv, bool kConst>
-inline int launch_exact_inst(const DecodeParams& p, int W, int grid, size_t smem, cudaStream_t st) {
+inline int launch_exact_inst(const DecodeParams& p, int W, int grid, size_t smem, float* scratch, cudaStream_t st) {
     auto kern = decode_exact_kernel<kAlgo, kMaxDc, kMaxDv, kConst>;
     LDPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, W * 32, smem, st>>>(p);
+    kern<<<grid, W * 32, smem, st>>>(p, scratch);
     LDPC_CHECK_LAUNCH("decode_exact_kernel");
     return LDPC_OK;
 }
@@ -351,23 +380,30 @@ inline int launch_exact(const ldpc_code* c, int algo, DecodeParams p, cudaStream
         return fail(LDPC_ERR_UNSUPPORTED, "exact path: node degree above 32 (row %d, col %d)", c->maxdc, c->maxdv);
     const size_t per_warp = (size_t)(c->E + 2 * c->cols) * 32 * sizeof(float);
     int W = (int)(kMaxSmemPerBlock / per_warp);
-    if (W < 1)
-        return fail(LDPC_ERR_UNSUPPORTED, "exact path: %zu bytes of messages per warp exceed shared memory", per_warp);
-    if (W > 8) W = 8;
     const long long ngroups = (p.B + c->G - 1) / c->G;
-    if ((long long)W > ngroups) W = (int)ngroups;
-    int per_sm = (int)(kMaxSmemPerBlock / (per_warp * W));
-    per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
-    long long blocks = (ngroups + W - 1) / W;
-    if (blocks > (long long)kNumSMs * per_sm) blocks = (long long)kNumSMs * per_sm;
+    ExactScratch sc;
+    long long blocks;
+    size_t smem = 0;
+    if (W < 1) {
+        // messages of one warp exceed shared memory: global workspace (BG2 above Z = 192 as 32-circulants, large Z = 1 codes)
+        if (int rc = sc.init(per_warp, ngroups, st, "exact path")) return rc;
+        W = sc.W; blocks = sc.blocks;
+    } else {
+        if (W > 8) W = 8;
+        if ((long long)W > ngroups) W = (int)ngroups;
+        int per_sm = (int)(kMaxSmemPerBlock / (per_warp * W));
+        per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
+        blocks = (ngroups + W - 1) / W;
+        if (blocks > (long long)kNumSMs * per_sm) blocks = (long long)kNumSMs * per_sm;
+        smem = per_warp * W;
+    }
     p.floats_per_warp = (int)(per_warp / sizeof(float));
     p.ngroups = ngroups;
     p.gtab = c->d_tab;
     p.slot = c->slot < 0 ? 0 : c->slot;
     const bool small = c->maxdc <= 10 && c->maxdv <= 24;
     const bool cst = c->slot >= 0;
-    const size_t smem = per_warp * W;
-#define LDPC_EXACT_CASE(A, DC, DV, CST) return launch_exact_inst<A, DC, DV, CST>(p, W, (int)blocks, smem, st)
+#define LDPC_EXACT_CASE(A, DC, DV, CST) return launch_exact_inst<A, DC, DV, CST>(p, W, (int)blocks, smem, sc.ptr, st)
     if (algo == LDPC_ALGO_MINSUM) {
         if (small) { if (cst) LDPC_EXACT_CASE(LDPC_ALGO_MINSUM, 10, 24, true); else LDPC_EXACT_CASE(LDPC_ALGO_MINSUM, 10, 24, false); }
         else       { if (cst) LDPC_EXACT_CASE(LDPC_ALGO_MINSUM, 32, 32, true); else LDPC_EXACT_CASE(LDPC_ALGO_MINSUM, 32, 32, false); }

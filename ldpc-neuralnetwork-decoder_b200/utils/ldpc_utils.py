@@ -93,6 +93,7 @@ class QCCode:
     """Quasi-cyclic LDPC code as a base-graph shift table (host copy + per-device handles)."""
 
     MAX_Z = 32
+    MAX_SPLIT_Z = 512           # largest lifting factor looked for in a dense H (5G NR: 384)
 
     def __init__(self, shifts, Z):
         shifts = np.asarray(shifts)
@@ -190,11 +191,15 @@ class QCCode:
         return cls(s, Z)
 
     @classmethod
-    def from_dense(cls, H, Z=None):
+    def from_dense(cls, H, Z=None, allow_split=False):
         """Factor a dense 0/1 parity-check matrix into circulant shifts.  Tries the given Z,
         else the largest Z <= 32 dividing both dimensions for which every block is empty or a
         cyclic permutation; Z = 1 always succeeds.  Raises ValueError if `Z` was given and
-        H is not quasi-cyclic with that lifting factor."""
+        H is not quasi-cyclic with that lifting factor.
+
+        allow_split (classic decoders): lifting factors above 32 are looked for first, largest first -- the reference's
+        scripts hand the decoders `expand_base_matrix(base, --lifting_factor)` (main.py:92,152,215) -- and held as an
+        equivalent renumbered code (from_base_matrix)."""
         Hn = torch.as_tensor(H).detach().cpu().numpy()
         if Hn.ndim != 2:
             raise ValueError("H must be 2-D")
@@ -202,6 +207,17 @@ class QCCode:
             raise ValueError("H must be binary")
         Hb = Hn.astype(np.uint8)
         M, N = Hb.shape
+        if allow_split and (Z is None or int(Z) > cls.MAX_Z):
+            g = int(np.gcd(M, N))
+            big = [int(Z)] if Z is not None else [z for z in range(min(g, cls.MAX_SPLIT_Z), cls.MAX_Z, -1) if g % z == 0]
+            for z in big:
+                if M % z or N % z:
+                    raise ValueError(f"H of shape {Hb.shape} cannot be lifted with Z={z}")
+                s = cls._factor(Hb, z)
+                if s is not None:
+                    return cls.from_base_matrix(s, z, allow_split=True)
+            if Z is not None:
+                raise ValueError(f"H is not quasi-cyclic with Z={Z}")
         cand = [int(Z)] if Z is not None else [z for z in range(cls.MAX_Z, 0, -1) if M % z == 0 and N % z == 0]
         for z in cand:
             if z < 1 or z > cls.MAX_Z or M % z or N % z:
@@ -303,4 +319,4 @@ def as_code(H=None, base_graph=None, Z=None, allow_split=False):
         return QCCode.from_base_matrix(base_graph, Z, allow_split=allow_split)
     if H is None:
         raise ValueError("need a parity-check matrix H, a QCCode, or (base_graph, Z)")
-    return QCCode.from_dense(H, Z)
+    return QCCode.from_dense(H, Z, allow_split=allow_split)

@@ -519,11 +519,40 @@ def test_lifting_factors_above_32_decode_like_the_oracle(Z, B, iters):
     assert np.array_equal(hard_e.cpu().numpy(), oracle.decode(base, Z, llr_hi, t + 1, "minsum", 0.75)["hard"])
 
 
-def test_lifting_factor_too_large_for_the_generic_kernel_fails_loudly():
-    """Z = 384 = 12 x 32: 2 364 + 2 x 624 cell rows of 128 bytes do not fit one SM's shared memory; the call must say so."""
-    from ldpc_b200 import _native
-    base = np.where(QCCode.nr_2_0(32).shifts >= 0, 1, -1)
-    dec = MinSumScaledDecoder(base_graph=torch.from_numpy(base.astype(np.float32)), Z=384, max_iterations=2, early_stopping=False)
-    with pytest.raises(_native.LdpcError) as e:
-        dec.decode(torch.zeros((1, 52 * 384), device=dev()))
-    assert e.value.code == _native.ERR_UNSUPPORTED
+def test_codes_too_large_for_shared_memory_use_the_global_workspace():
+    """Z = 384 = 12 x 32 (2 364 + 2 x 624 cell rows of 128 bytes per codeword) and a 3 328-bit code without quasi-cyclic structure
+    (Z = 1: 12 608 + 2 x 3 328 rows per warp of 32 codewords) do not fit an SM's shared memory: the table-driven kernel then
+    keeps its per-warp state in a global workspace.  Same code, same operation order: beliefs bit-identical to the oracle.
+    The second case is also the reference's own call shape -- a dense H handed to the constructor (main.py:92,152)."""
+    rng = np.random.default_rng(5)
+    support = QCCode.nr_2_0(32).shifts >= 0
+    base = np.where(support, rng.integers(0, 384, size=support.shape), -1)
+    llr = oracle.awgn_llr(None, 5, 52 * 384, 1.0, seed=9)
+    o = oracle.decode(base, 384, llr, 3, "minsum", 0.75)
+    dec = MinSumScaledDecoder(base_graph=torch.from_numpy(base.astype(np.float32)), Z=384, max_iterations=3, early_stopping=False)
+    soft, hard = run(dec, llr)
+    assert np.array_equal(soft, o["beliefs"]) and np.array_equal(hard, o["hard"])
+    ok = dec._check_valid_codeword(torch.from_numpy(o["hard"]).to(dev())).cpu().numpy()
+    assert np.array_equal(ok, (oracle.decode(base, 384, llr, 3, "minsum", 0.75, want_mask=True)["valid_mask"][:, 0] >> np.uint64(2)) & np.uint64(1) == 1)
+    # dense H = BG2 lifted with Z = 64: recognised as such (renumbered 32-circulants, shared memory)
+    from ldpc_b200.utils.ldpc_utils import expand_base_matrix
+    base64 = np.where(support, rng.integers(0, 64, size=support.shape), -1)
+    H = expand_base_matrix(torch.from_numpy(base64.astype(np.float32)), 64)
+    llr = oracle.awgn_llr(None, 33, 52 * 64, 0.5, seed=10)
+    o = oracle.decode(base64, 64, llr, 4, "minsum", 0.75)
+    dec = MinSumScaledDecoder(H, max_iterations=4, early_stopping=False)
+    assert dec.code.lift_Z == 64 and dec.code.Z == 32
+    soft, hard = run(dec, llr)
+    assert np.array_equal(soft, o["beliefs"]) and np.array_equal(hard, o["hard"])
+    # the same H with its columns shuffled: no quasi-cyclic structure left, Z = 1, global workspace; BP too
+    perm = rng.permutation(H.shape[1])
+    Hp = H[:, perm]
+    dec = MinSumScaledDecoder(Hp, max_iterations=4, early_stopping=False)
+    assert dec.code.Z == 1 and dec.code.lift_Z is None
+    shifts1 = np.where(Hp.numpy() > 0, 0, -1)
+    o = oracle.decode(shifts1, 1, llr[:, perm], 4, "minsum", 0.75)
+    soft, hard = run(dec, llr[:, perm])
+    assert np.array_equal(soft, o["beliefs"]) and np.array_equal(hard, o["hard"])
+    ob = oracle.decode(shifts1, 1, llr[:, perm], 4, "bp")
+    _, hb = run(BeliefPropagationDecoder(Hp, max_iterations=4, early_stopping=False), llr[:, perm])
+    assert np.array_equal(hb, ob["hard"])
