@@ -332,6 +332,16 @@ struct ExactScratch {
         if (warps > ngroups) warps = ngroups;
         W = warps < 8 ? (int)warps : 8;
         blocks = warps / W;
+        {   // keep the workspace in the device's pool between calls: with the default release threshold (0) every
+            // synchronisation hands the memory back to the driver and the next call pays for a fresh allocation
+            int dev = 0;
+            cudaMemPool_t pool;
+            LDPC_CUDA(cudaGetDevice(&dev));
+            LDPC_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+            uint64_t cur = 0, keep = (uint64_t)2 << 30;
+            LDPC_CUDA(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &cur));
+            if (cur < keep) LDPC_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        }
         LDPC_CUDA(cudaMallocAsync((void**)&ptr, per_warp * (size_t)W * (size_t)blocks, st));
         return LDPC_OK;
     }
@@ -384,8 +394,10 @@ inline int launch_exact(const ldpc_code* c, int algo, DecodeParams p, cudaStream
     ExactScratch sc;
     long long blocks;
     size_t smem = 0;
-    if (W < 1) {
-        // messages of one warp exceed shared memory: global workspace (BG2 above Z = 192 as 32-circulants, large Z = 1 codes)
+    if (W < 4) {
+        // the state of a warp exceeds a quarter of shared memory: global workspace (BG2 from Z = 64 up as 32-circulants, large
+        // Z = 1 codes).  Fewer than four warps per SM cannot hide the kernel's latencies: BG2 at Z = 128 ran 34.7 k cw/s with
+        // one warp per SM from shared memory and 175 k cw/s from the workspace with 8 warps per block (L2-resident)
         if (int rc = sc.init(per_warp, ngroups, st, "exact path")) return rc;
         W = sc.W; blocks = sc.blocks;
     } else {
