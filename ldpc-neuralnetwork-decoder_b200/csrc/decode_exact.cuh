@@ -94,19 +94,22 @@ __global__ void __launch_bounds__(256) decode_exact_kernel(const DecodeParams p,
         int my_iters = p.iters;
         unsigned long long vm = 0;
         for (int it = 0; it < p.iters; ++it) {
+            // Both updates are written once for a compile-time bound on the node degree and instantiated for a ladder of
+            // bounds; a row / column runs the smallest instance that holds it (warp-uniform choice).  The operations and their
+            // order are those of the full-width loops -- the padded slots only ever contributed predicated-off instructions,
+            // which at kMaxDv = 24 were 276 additions per base column whatever its degree (38 of BG2's 52 columns have degree 1).
             // ---------------- check-node update ----------------
-            for (int i = 0; i < rows; ++i) {
-                const int e0 = tab[off_rowptr + i];
-                const int d = (int)tab[off_rowptr + i + 1] - e0;
-                float v[kMaxDc];
+            auto check_row = [&](auto dcc, int e0, int d) {
+                constexpr int DC = decltype(dcc)::value;
+                float v[DC];
 #pragma unroll
-                for (int k = 0; k < kMaxDc; ++k) v[k] = (k < d) ? msg[(e0 + k) * 32 + lane] : 0.0f;
+                for (int k = 0; k < DC; ++k) v[k] = (k < d) ? msg[(e0 + k) * 32 + lane] : 0.0f;
                 if constexpr (kAlgo == LDPC_ALGO_MINSUM) {
                     float m1 = CUDART_INF_F, m2 = CUDART_INF_F;
                     uint32_t sg = 0;
                     int nn = 0;                    // NaN inputs (only reachable from non-finite channel LLRs)
 #pragma unroll
-                    for (int k = 0; k < kMaxDc; ++k)
+                    for (int k = 0; k < DC; ++k)
                         if (k < d) {
                             // reference :216-222: `mag < min_mag` is false for a NaN magnitude, i.e. a NaN never becomes a
                             // minimum: it takes part as +inf here
@@ -119,7 +122,7 @@ __global__ void __launch_bounds__(256) decode_exact_kernel(const DecodeParams p,
                         }
                     const float s1 = __fmul_rn(p.alpha, m1), s2 = __fmul_rn(p.alpha, m2);
 #pragma unroll
-                    for (int k = 0; k < kMaxDc; ++k)
+                    for (int k = 0; k < DC; ++k)
                         if (k < d) {
                             // torch.sign(NaN) = 0 (:213), so a NaN among the OTHER inputs zeroes the sign product: the
                             // message is 0 * scaled_min = 0, or NaN when that minimum is infinite
@@ -129,19 +132,19 @@ __global__ void __launch_bounds__(256) decode_exact_kernel(const DecodeParams p,
                             v[k] = other_nan ? __fmul_rn(0.0f, mag) : out;
                         }
                 } else {
-                    float t[kMaxDc];
+                    float t[DC];
 #pragma unroll
-                    for (int k = 0; k < kMaxDc; ++k) {
+                    for (int k = 0; k < DC; ++k) {
                         t[k] = 1.0f;
-                        if (k < d) t[k] = tanh_half_ref(v[k]);        // warp-uniform branch: degree-3..5 rows skip the rest
+                        if (k < d) t[k] = tanh_half_ref(v[k]);
                     }
                     float pre = 1.0f;
 #pragma unroll
-                    for (int k = 0; k < kMaxDc; ++k)
+                    for (int k = 0; k < DC; ++k)
                         if (k < d) {
                             float pr = pre;
 #pragma unroll
-                            for (int k2 = k + 1; k2 < kMaxDc; ++k2)
+                            for (int k2 = k + 1; k2 < DC; ++k2)
                                 if (k2 < d) pr = __fmul_rn(pr, t[k2]);
                             v[k] = two_atanh_ref(pr);
                             pre = __fmul_rn(pre, t[k]);
@@ -149,19 +152,30 @@ __global__ void __launch_bounds__(256) decode_exact_kernel(const DecodeParams p,
                 }
                 if (!done) {
 #pragma unroll
-                    for (int k = 0; k < kMaxDc; ++k)
+                    for (int k = 0; k < DC; ++k)
                         if (k < d) msg[(e0 + k) * 32 + lane] = v[k];
                 }
+            };
+            for (int i = 0; i < rows; ++i) {
+                const int e0 = tab[off_rowptr + i];
+                const int d = (int)tab[off_rowptr + i + 1] - e0;
+                if (d <= 3) check_row(IC<3>{}, e0, d);
+                else if (d <= 4) check_row(IC<4>{}, e0, d);
+                else if (d <= 5) check_row(IC<5>{}, e0, d);
+                else if (d <= 6) check_row(IC<(kMaxDc < 6 ? kMaxDc : 6)>{}, e0, d);
+                else if (d <= 8) check_row(IC<(kMaxDc < 8 ? kMaxDc : 8)>{}, e0, d);
+                else if (d <= 10) check_row(IC<(kMaxDc < 10 ? kMaxDc : 10)>{}, e0, d);
+                else if (d <= 16) check_row(IC<(kMaxDc < 16 ? kMaxDc : 16)>{}, e0, d);
+                else check_row(IC<kMaxDc>{}, e0, d);
             }
             __syncwarp();
             // ---------------- variable-node update + posterior ----------------
-            for (int j = 0; j < cols; ++j) {
-                const int k0 = tab[off_colptr + j];
-                const int d = (int)tab[off_colptr + j + 1] - k0;
-                float c[kMaxDv];
-                int addr[kMaxDv];
+            auto var_col = [&](auto dvc, int j, int k0, int d) {
+                constexpr int DV = decltype(dvc)::value;
+                float c[DV];
+                int addr[DV];
 #pragma unroll
-                for (int k = 0; k < kMaxDv; ++k) {
+                for (int k = 0; k < DV; ++k) {
                     if (k < d) {
                         const uint32_t w = tab[off_cedge + k0 + k];
                         int rr = r - (int)((w >> 16) & 0xff);
@@ -175,21 +189,35 @@ __global__ void __launch_bounds__(256) decode_exact_kernel(const DecodeParams p,
                 }
                 float pre = L[j * 32 + lane];
 #pragma unroll
-                for (int k = 0; k < kMaxDv; ++k)
+                for (int k = 0; k < DV; ++k)
                     if (k < d) {
                         float s = pre;
 #pragma unroll
-                        for (int k2 = k + 1; k2 < kMaxDv; ++k2)
+                        for (int k2 = k + 1; k2 < DV; ++k2)
                             if (k2 < d) s = __fadd_rn(s, c[k2]);
                         pre = __fadd_rn(pre, c[k]);
                         c[k] = s;
                     }
                 if (!done) {
 #pragma unroll
-                    for (int k = 0; k < kMaxDv; ++k)
+                    for (int k = 0; k < DV; ++k)
                         if (k < d) msg[addr[k]] = c[k];
                     T[j * 32 + lane] = pre;
                 }
+            };
+            for (int j = 0; j < cols; ++j) {
+                const int k0 = tab[off_colptr + j];
+                const int d = (int)tab[off_colptr + j + 1] - k0;
+                if (d <= 1) var_col(IC<1>{}, j, k0, d);
+                else if (d <= 2) var_col(IC<2>{}, j, k0, d);
+                else if (d <= 3) var_col(IC<3>{}, j, k0, d);
+                else if (d <= 4) var_col(IC<4>{}, j, k0, d);
+                else if (d <= 6) var_col(IC<6>{}, j, k0, d);
+                else if (d <= 8) var_col(IC<8>{}, j, k0, d);
+                else if (d <= 12) var_col(IC<12>{}, j, k0, d);
+                else if (d <= 16) var_col(IC<16>{}, j, k0, d);
+                else if (d <= 24) var_col(IC<(kMaxDv < 24 ? kMaxDv : 24)>{}, j, k0, d);
+                else var_col(IC<kMaxDv>{}, j, k0, d);
             }
             __syncwarp();
             if (track) {
