@@ -347,6 +347,12 @@ __global__ void __launch_bounds__(256) syndrome_kernel(const uint32_t* gtab, int
 }
 
 // Global workspace for codes whose per-warp state exceeds shared memory: at most ~1 GB, stream-ordered allocation
+#ifndef LDPC_EXACT_WS_WARPS
+#define LDPC_EXACT_WS_WARPS 16         // warps per SM when the state lives in the global workspace (2 blocks of 8: the register file's limit)
+#endif
+#ifndef LDPC_EXACT_WS_BELOW
+#define LDPC_EXACT_WS_BELOW 4          // min-sum: use the workspace when fewer warps than this fit an SM's shared memory (sum-product: 8)
+#endif
 struct ExactScratch {
     float* ptr = nullptr;
     int W = 0;
@@ -356,7 +362,7 @@ struct ExactScratch {
         st = stream;
         long long warps = (long long)((size_t)1 << 30) / (long long)per_warp;
         if (warps < 1) return fail(LDPC_ERR_UNSUPPORTED, "%s: %zu bytes of state per warp", who, per_warp);
-        if (warps > (long long)kNumSMs * 8) warps = (long long)kNumSMs * 8;
+        if (warps > (long long)kNumSMs * LDPC_EXACT_WS_WARPS) warps = (long long)kNumSMs * LDPC_EXACT_WS_WARPS;
         if (warps > ngroups) warps = ngroups;
         W = warps < 8 ? (int)warps : 8;
         blocks = warps / W;
@@ -422,10 +428,12 @@ inline int launch_exact(const ldpc_code* c, int algo, DecodeParams p, cudaStream
     ExactScratch sc;
     long long blocks;
     size_t smem = 0;
-    if (W < 4) {
-        // the state of a warp exceeds a quarter of shared memory: global workspace (BG2 from Z = 64 up as 32-circulants, large
-        // Z = 1 codes).  Fewer than four warps per SM cannot hide the kernel's latencies: BG2 at Z = 128 ran 34.7 k cw/s with
-        // one warp per SM from shared memory and 175 k cw/s from the workspace with 8 warps per block (L2-resident)
+    if (W < (algo == LDPC_ALGO_BP ? 2 * LDPC_EXACT_WS_BELOW : LDPC_EXACT_WS_BELOW)) {
+        // too few warps fit an SM's shared memory to hide the kernel's latencies: global workspace, 16 warps per SM (BG2 from
+        // Z = 64 up as 32-circulants, large Z = 1 codes; sum-product, whose double-precision tanh / atanh chains are longer,
+        // already at BG2 Z = 32 where five warps fit).  Measured, k cw/s, shared memory with what fits / workspace with 8 / with
+        // 16 warps per SM: min-sum BG2 Z = 32 3288 / 2934 / 2794; sum-product 561 / 699 / 991; min-sum Z = 64 (2 warps fit)
+        // 208 / 930 / 1138; Z = 128 (1 warp) 35 / 351 / 559; Z = 384 (none) - / 92 / 157
         if (int rc = sc.init(per_warp, ngroups, st, "exact path")) return rc;
         W = sc.W; blocks = sc.blocks;
     } else {

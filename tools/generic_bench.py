@@ -5,6 +5,9 @@ import json, os, sys, time
 import numpy as np, torch
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import ldpc_b200  # noqa: E402,F401
+if os.environ.get("LDPC_LIB"):
+    from ldpc_b200 import _native as _n
+    _n.LIB_PATH = os.environ["LDPC_LIB"]
 from ldpc_b200.models import MinSumScaledDecoder, BeliefPropagationDecoder  # noqa: E402
 from ldpc_b200.utils import QCCode  # noqa: E402
 
