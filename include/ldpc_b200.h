@@ -77,7 +77,13 @@ uint64_t ldpc_launch_count(void);
  * adjacency scans traditional_decoders.py:26-40,161-175 / message_gnn_decoder.py:382-408.
  * shifts: [rows*cols] row-major, -1 = zero block, otherwise 0 <= shift < Z.
  * Lifting convention (ldpc_utils.py:121-123): check i*Z+r  <->  variable j*Z+((r+s) mod Z).
- * 1 <= Z <= 32.  Tables go to __constant__ memory when they fit a slot, else to global. */
+ * 1 <= Z <= 32.  Tables go to __constant__ memory when they fit a slot, else to global.
+ * A lifting factor above 32 is passed as the equivalent code with Zs = a divisor of Z that is <= 32: a Z x Z circulant
+ * with Z = m*Zs and shift s = m*q + t becomes, after renumbering r = m*a + b -> (b, a), the m blocks
+ * (i*m + b, j*m + (b+t) mod m) with shift (q + (b+t) div m) mod Zs; the caller permutes LLRs / outputs accordingly
+ * (utils/ldpc_utils.py: QCCode._split_lifting does both for the Python classes; output bit-identical to the natural code).
+ * The table-driven decoder keeps a warp's messages in shared memory when enough warps fit, else in a stream-ordered
+ * global workspace (cudaMallocAsync on the caller's stream), so code size is bounded by node degree <= 32 only.        */
 int ldpc_code_create(const int16_t* shifts, int rows, int cols, int Z, int device, ldpc_code_t** out);
 int ldpc_code_destroy(ldpc_code_t* code);
 /* info[0..7] = rows, cols, Z, base edges, N=cols*Z, M=rows*Z, max row degree, max col degree */
