@@ -265,3 +265,25 @@ def test_fp16_split_edge_kernel_matches_the_oracle():
     assert out.returncode == 0, out.stderr[-2000:]
     err = float(out.stdout.strip().splitlines()[-1].split()[1])
     assert err <= 1e-4, out.stdout
+
+
+@pytest.mark.gpu
+def test_dense_h_of_a_large_lifting_factor():
+    """The reference's scripts build the GNN from `expand_base_matrix(base, --lifting_factor)` (main.py:92, run_comparison.py:70) with
+    any lifting factor: BG2's support lifted with Z = 64 (3 328 variables, 12 608 messages) as a dense H -- held with Z = 1 tables, the
+    message list in the reference's order -- forward against the oracle."""
+    from ldpc_b200.utils.ldpc_utils import expand_base_matrix
+    rng = np.random.default_rng(0)
+    support = QCCode.nr_2_0(32).shifts >= 0
+    base = np.where(support, rng.integers(0, 64, size=support.shape), -1)
+    H = expand_base_matrix(torch.from_numpy(base.astype(np.float32)), 64)
+    torch.manual_seed(1)
+    dec, conv = create_message_gnn_decoder(H, 2, 64)
+    assert conv.message_var_index.numel() == 197 * 64
+    llr = rng.normal(1.0, 2.0, size=(3, H.shape[1])).astype(np.float32)
+    sd = {k: v.detach().numpy() for k, v in dec.state_dict().items()}
+    soft_ref, _ = oracle.gnn_forward(sd, llr, conv.message_var_index.numpy(), conv.message_check_index.numpy(),
+                                     dec._expanded_types(), 2)
+    dec = dec.cuda()
+    soft, _ = dec(torch.from_numpy(llr).cuda())
+    assert np.all(np.abs(soft.cpu().numpy() - soft_ref) <= 1e-4 * np.maximum(np.abs(soft_ref), 1.0))
