@@ -34,7 +34,7 @@ def main():
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--reps", type=int, default=5)
-    ap.add_argument("--z", type=int, default=32, choices=[4, 32], help="lifting size of the BG2 code")
+    ap.add_argument("--z", type=int, default=32, choices=[4, 8, 16, 32], help="lifting size of the BG2 code")
     ap.add_argument("--lib", default=None, help="alternative libldpc_b200.so (tools/build_variant.sh)")
     args = ap.parse_args()
     if args.lib:
