@@ -48,7 +48,7 @@ __device__ __forceinline__ bool syndrome_bad(const Tab<kConst>& tab, const float
     return bad != 0;
 }
 
-template <int kAlgo, int kMaxDc, int kMaxDv, bool kConst>
+template <int kAlgo, int kMaxDc, int kMaxDv, bool kConst, bool kScratch>
 __global__ void __launch_bounds__(256) decode_exact_kernel(const DecodeParams p, float* __restrict__ scratch) {
     // scratch != nullptr: the per-warp state (messages, posteriors, LLRs) does not fit shared memory (large lifting factors
     // held as many small circulants, large Z = 1 codes) and lives in a global workspace instead -- same code, L2 speed
@@ -57,7 +57,11 @@ __global__ void __launch_bounds__(256) decode_exact_kernel(const DecodeParams p,
     const int rows = tab[0], cols = tab[1], Z = tab[2], E = tab[3], G = tab[4];
     const int off_rowptr = tab[7], off_colptr = tab[8], off_redge = tab[9], off_cedge = tab[10];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
-    float* msg = scratch ? scratch + ((size_t)blockIdx.x * W + warp) * p.floats_per_warp : smem + (size_t)warp * p.floats_per_warp;
+    // (a template parameter, not a run-time choice: with one pointer for both address spaces every access became a generic
+    // LD / ST instead of LDS / STS)
+    float* msg;
+    if constexpr (kScratch) msg = scratch + ((size_t)blockIdx.x * W + warp) * p.floats_per_warp;
+    else msg = smem + (size_t)warp * p.floats_per_warp;
     float* T = msg + E * 32;
     float* L = T + cols * 32;
     const bool active = lane < G * Z;
@@ -410,9 +414,9 @@ inline int launch_syndrome(const ldpc_code* c, const void* hard, int hard_dtype,
 }
 
 // ---- host launcher ----------------------------------------------------------------------
-template <int kAlgo, int kMaxDc, int kMaxDv, bool kConst>
+template <int kAlgo, int kMaxDc, int kMaxDv, bool kConst, bool kScratch>
 inline int launch_exact_inst(const DecodeParams& p, int W, int grid, size_t smem, float* scratch, cudaStream_t st) {
-    auto kern = decode_exact_kernel<kAlgo, kMaxDc, kMaxDv, kConst>;
+    auto kern = decode_exact_kernel<kAlgo, kMaxDc, kMaxDv, kConst, kScratch>;
     LDPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, W * 32, smem, st>>>(p, scratch);
     LDPC_CHECK_LAUNCH("decode_exact_kernel");
@@ -451,7 +455,8 @@ inline int launch_exact(const ldpc_code* c, int algo, DecodeParams p, cudaStream
     p.slot = c->slot < 0 ? 0 : c->slot;
     const bool small = c->maxdc <= 10 && c->maxdv <= 24;
     const bool cst = c->slot >= 0;
-#define LDPC_EXACT_CASE(A, DC, DV, CST) return launch_exact_inst<A, DC, DV, CST>(p, W, (int)blocks, smem, sc.ptr, st)
+#define LDPC_EXACT_CASE(A, DC, DV, CST) do { if (sc.ptr) return launch_exact_inst<A, DC, DV, CST, true>(p, W, (int)blocks, smem, sc.ptr, st); \
+                                              return launch_exact_inst<A, DC, DV, CST, false>(p, W, (int)blocks, smem, nullptr, st); } while (0)
     if (algo == LDPC_ALGO_MINSUM) {
         if (small) { if (cst) LDPC_EXACT_CASE(LDPC_ALGO_MINSUM, 10, 24, true); else LDPC_EXACT_CASE(LDPC_ALGO_MINSUM, 10, 24, false); }
         else       { if (cst) LDPC_EXACT_CASE(LDPC_ALGO_MINSUM, 32, 32, true); else LDPC_EXACT_CASE(LDPC_ALGO_MINSUM, 32, 32, false); }
@@ -460,6 +465,7 @@ inline int launch_exact(const ldpc_code* c, int algo, DecodeParams p, cudaStream
         else       { if (cst) LDPC_EXACT_CASE(LDPC_ALGO_BP, 32, 32, true); else LDPC_EXACT_CASE(LDPC_ALGO_BP, 32, 32, false); }
     }
 #undef LDPC_EXACT_CASE
+    return LDPC_OK;                          // not reached: every case returns
 }
 
 }  // namespace ldpc
