@@ -30,7 +30,7 @@ constexpr int kNqColMax[nq::kColClasses] = {6, 8, 10, 13, 16, 23};
 constexpr int kNqColMin[nq::kColClasses] = {5, 7, 9, 12, 14, 22};   // smallest degree that uses the class (no masking below it)
 
 template <class BG>
-constexpr int nq_group_floats() { return BG::kEdges * kNqPitch + 3 * BG::kExtCols * 32 + 16; }
+constexpr int nq_group_floats() { return BG::kEdges * kNqPitch + 3 * BG::kExtCols * 32 + 128; }
 template <class BG>
 constexpr size_t neural_qc_smem_bytes() {      // w_ch tile | per-codeword state | tile addresses of the row chunks (uint16)
     return sizeof(float) * ((size_t)BG::kEdges * 32 + (size_t)kNqGroups * nq_group_floats<BG>()) + sizeof(unsigned short) * BG::kEdges * 32;
@@ -56,10 +56,14 @@ __device__ __forceinline__ void nq_group_sync(int group) {
 
 template <class BG>
 __global__ void __launch_bounds__(kNqThreads, 1) neural_qc_kernel(const NeuralQcParams p) {
-    static_assert(BG::kZ == 32, "one codeword per warp-wide lane set");
+    // Z < 32: a warp holds G = 32 / Z codewords side by side (lane = Z * sub + r); every per-lane structure (Tensor Memory
+    // columns, tile columns) then carries G codewords at once, rotations stay inside a codeword's Z lanes, and only the global
+    // addressing, the rotations and the per-codeword reductions know about it.  Z = 32 compiles to the code it always was.
+    constexpr int Z = BG::kZ, G = 32 / Z;
+    static_assert(Z == 32 || Z == 16 || Z == 8 || Z == 4, "lifting sizes with a whole number of codewords per warp");
     constexpr int EB = BG::kEdges, EC = BG::kCoreEdges, NX = BG::kExtCols;
     constexpr int ECP = (EC + 3) / 4 * 4;
-    constexpr int E = EB * 32;
+    constexpr int E = EB * Z, NV = BG::kCols * Z;
     static_assert(EB == nq::kCells && 3 * ECP <= 512, "schedule tables / TMEM budget");
     extern __shared__ float nq_smem[];
     // the warp index is broadcast from lane 0 so that the compiler KNOWS it is warp-uniform: schedule-table indices,
@@ -67,11 +71,21 @@ __global__ void __launch_bounds__(kNqThreads, 1) neural_qc_kernel(const NeuralQc
     // moving per-access TMEM addresses into them)
     const int lane = threadIdx.x & 31, warp = __shfl_sync(kFull, (int)(threadIdx.x >> 5), 0);
     const int grp = warp & (kNqGroups - 1), mem = warp / kNqGroups;       // TMEM lane quarter = codeword slot; member in it
+    const int r = lane & (Z - 1), sub = lane / Z, lbase = lane & ~(Z - 1); // circulant row, codeword of the warp, its first lane
+    // rotation by s inside the codeword's lanes: lane r reads row (r + s) mod Z
+    auto rot = [&](float v, int s) {
+        if constexpr (Z == 32) return __shfl_sync(kFull, v, lane + s);
+        else return __shfl_sync(kFull, v, lbase | ((lane + s) & (Z - 1)));
+    };
+    auto rot_back = [&](float v, int s) {                                  // the inverse: lane r reads row (r - s) mod Z
+        if constexpr (Z == 32) return __shfl_sync(kFull, v, lane - s);
+        else return __shfl_sync(kFull, v, lbase | ((lane - s) & (Z - 1)));
+    };
     float* wsm = nq_smem;                                                  // [EB][32]  w_ch per (cell, lane)
     float* lls = nq_smem + EB * 32 + grp * nq_group_floats<BG>();         // [EB][33]  llr_e, later the soft outputs
     float* xe0 = lls + EB * kNqPitch;                                      // [2][NX][32] ring of the degree-1 cells
     float* ces = xe0 + 2 * NX * 32;                                        // [NX][32]  their last check message
-    float* red = ces + NX * 32;                                            // [4][4] per-member loss maximum, its edge, soft and target
+    float* red = ces + NX * 32;                                            // [G][4][4] per codeword: per-member loss maximum, its edge, soft and target
     // where element `lane` of the m-th 32-edge chunk of a row sits in the tile: (D + k) * 33 + r (the same for every codeword)
     unsigned short* tile_addr = reinterpret_cast<unsigned short*>(nq_smem + EB * 32 + kNqGroups * nq_group_floats<BG>());
 
@@ -85,9 +99,9 @@ __global__ void __launch_bounds__(kNqThreads, 1) neural_qc_kernel(const NeuralQc
     for (int m = warp; m < EB; m += kNqThreads / 32) {
         const unsigned cmeta = nq::chunk_meta[m];
         const int D = cmeta & 0xff, d = (cmeta >> 8) & 0x1f;
-        wsm[m * 32 + lane] = __ldg(p.w_ch + 32 * D + lane * d + (m - D));
-        const int inv = cmeta >> 13, off = 32 * (m - D) + lane, r = (off * inv) >> 16, k = off - r * d;
-        tile_addr[m * 32 + lane] = (unsigned short)((D + k) * kNqPitch + r);
+        wsm[m * 32 + lane] = __ldg(p.w_ch + Z * D + r * d + (m - D));
+        const int inv = cmeta >> 13, off = Z * (m - D) + r, rr = (off * inv) >> 16, k = off - rr * d;
+        tile_addr[m * 32 + lane] = (unsigned short)((D + k) * kNqPitch + lbase + rr);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -98,20 +112,20 @@ __global__ void __launch_bounds__(kNqThreads, 1) neural_qc_kernel(const NeuralQc
     int xc_off = 0, xo_off = NX * 32;                   // the same for the degree-1 ring in shared memory
     const float wres0 = p.L >= 1 ? __ldg(p.w_res) : 0.0f, wres1 = p.L >= 2 ? __ldg(p.w_res + 1) : 0.0f;
 
-    for (long long cw0 = (long long)blockIdx.x * kNqGroups; cw0 < p.B; cw0 += (long long)gridDim.x * kNqGroups) {
+    for (long long cw0 = (long long)blockIdx.x * kNqGroups * G; cw0 < p.B; cw0 += (long long)gridDim.x * kNqGroups * G) {
         // groups past the end of the batch keep walking (on the last codeword, without storing): every barrier is reached
-        const bool live = cw0 + grp < p.B;
-        const long long cw = live ? cw0 + grp : p.B - 1;
+        const bool live = cw0 + grp * G + sub < p.B;
+        const long long cw = live ? cw0 + grp * G + sub : p.B - 1;
         // the NEXT codeword of this group: pull its rows (llr_e, ground truth) into L2 while this one is decoded
         {
-            const long long nxt = cw0 + (long long)gridDim.x * kNqGroups + grp;
+            const long long nxt = cw0 + ((long long)gridDim.x * kNqGroups + grp) * G;     // first of the group's next G codewords
             if (nxt < p.B) {
                 const int t = mem * 32 + lane;                      // 128 threads, one 128-byte line each per step
-                const int lines = p.per_var ? BG::kCols : EB;
-                const long long rowlen = p.per_var ? BG::kCols * 32 : E;
-                for (int i = t; i < lines; i += nq::kMembers * 32) {
-                    asm volatile("prefetch.global.L2 [%0];" :: "l"(p.llr + nxt * rowlen + 32 * i));
-                    if (p.gt) asm volatile("prefetch.global.L2 [%0];" :: "l"(p.gt + nxt * rowlen + 32 * i));
+                const long long rowlen = p.per_var ? NV : E;
+                const long long have = (p.B - nxt < G ? p.B - nxt : G) * rowlen;       // the G rows are adjacent in memory
+                for (long long i = 32 * t; i < have; i += 32 * nq::kMembers * 32) {
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(p.llr + nxt * rowlen + i));
+                    if (p.gt) asm volatile("prefetch.global.L2 [%0];" :: "l"(p.gt + nxt * rowlen + i));
                 }
             }
         }
@@ -119,12 +133,12 @@ __global__ void __launch_bounds__(kNqThreads, 1) neural_qc_kernel(const NeuralQc
         if (p.per_var) {
             // one line per base column, copied to each of the column's cells (the value llr[:, edge_to_var] gives its edges);
             // a member's 13 lines are requested together
-            const float* src = p.llr + cw * (BG::kCols * 32) + lane;
+            const float* src = p.llr + cw * NV + r;
             constexpr int kPer = BG::kCols / nq::kMembers;
             static_assert(kPer * nq::kMembers == BG::kCols, "columns split evenly over the members");
             float v[kPer];
 #pragma unroll
-            for (int i = 0; i < kPer; ++i) v[i] = __ldg(src + 32 * (mem + i * nq::kMembers));
+            for (int i = 0; i < kPer; ++i) v[i] = __ldg(src + Z * (mem + i * nq::kMembers));
 #pragma unroll
             for (int i = 0; i < kPer; ++i) {
                 const int j = mem + i * nq::kMembers;
@@ -134,9 +148,9 @@ __global__ void __launch_bounds__(kNqThreads, 1) neural_qc_kernel(const NeuralQc
                 for (int k = 0; k < d; ++k) lls[(D + k) * kNqPitch + lane] = v[i];
             }
         } else {
-            const float* src = p.llr + cw * E + lane;
+            const float* src = p.llr + cw * E + r;
 #pragma unroll 8
-            for (int m = mem; m < EB; m += nq::kMembers) lls[tile_addr[m * 32 + lane]] = __ldg(src + 32 * m);
+            for (int m = mem; m < EB; m += nq::kMembers) lls[tile_addr[m * 32 + lane]] = __ldg(src + Z * m);
         }
         nq_group_sync(grp);
         // x_0 = llr_e in the current ring slot, zeros in the older one (its residual weight is zero until it is written)
@@ -160,23 +174,23 @@ __global__ void __launch_bounds__(kNqThreads, 1) neural_qc_kernel(const NeuralQc
                 constexpr int k = decltype(kc)::value;
                 const unsigned meta = nq::row_meta[row][k];
                 cell[k] = meta & 0xff;
-                sft[k] = meta >> 8;
+                sft[k] = Z == 32 ? (meta >> 8) : ((meta >> 8) & (Z - 1));
                 nq_ld1_issue(tXc + cell[k], v[k]);
             });
             nq_wait_ld();
             static_for<0, NC>([&](auto kc) { nq_tie(v[decltype(kc)::value]); });
             // training forward: this CheckLayer's input as [cell][lane] (one coalesced 128-byte line per cell; every cell
             // belongs to exactly one row) -- the layout the backward kernel reads back without a transposing tile
-            if (save) static_for<0, NC>([&](auto kc) { save[32 * cell[decltype(kc)::value]] = v[decltype(kc)::value]; });
+            if (save) static_for<0, NC>([&](auto kc) { save[Z * cell[decltype(kc)::value]] = v[decltype(kc)::value]; });
             static_for<0, NC>([&](auto kc) {
                 constexpr int k = decltype(kc)::value;
-                v[k] = __shfl_sync(kFull, v[k], lane + sft[k]);           // variable (r + s) mod 32 -> check row r
+                v[k] = rot(v[k], sft[k]);                                  // variable (r + s) mod Z -> check row r
             });
             int xs = 0;
             if constexpr (NE) {
                 xs = nq::row_ext[row];
                 v[NC] = xe0[xc_off + xs * 32 + lane];
-                if (save) save[32 * (EC + xs)] = v[NC];
+                if (save) save[Z * (EC + xs)] = v[NC];
             }
             unsigned nb = 0;
             int zc = 0;
@@ -208,7 +222,7 @@ __global__ void __launch_bounds__(kNqThreads, 1) neural_qc_kernel(const NeuralQc
                     const unsigned sgn = (nb ^ sb[k]) & 0x80000000u;               // their sign product
                     float o = u2f(sgn | f2u(m));
                     if (special) o = __fmul_rn(u2f(sgn | ((zc - zi[k]) > 0 ? 0u : 0x3f800000u)), m);
-                    if constexpr (k < NC) nq_st1(tC + cell[k], __shfl_sync(kFull, o, lane - sft[k]));
+                    if constexpr (k < NC) nq_st1(tC + cell[k], rot_back(o, sft[k]));
                     else ces[xs * 32 + lane] = o;
                 }
             });
@@ -298,7 +312,7 @@ __global__ void __launch_bounds__(kNqThreads, 1) neural_qc_kernel(const NeuralQc
         };
 
         for (int l = 0; l < p.iters; ++l) {
-            float* save = (p.save_x && live) ? p.save_x + ((long long)l * p.B + cw) * E + lane : nullptr;
+            float* save = (p.save_x && live) ? p.save_x + ((long long)l * p.B + cw) * E + r : nullptr;      // [iteration][codeword][cell][Z]
             const bool last = l == p.iters - 1;
             phase_a(last, save);
             nq_group_sync(grp);
@@ -318,8 +332,8 @@ __global__ void __launch_bounds__(kNqThreads, 1) neural_qc_kernel(const NeuralQc
             // cell by cell as below, in the tile's own [cell][lane] order: the output of a column's FIRST cell is the variables'
             // output line; every cell's loss is taken against the column's target line (L1 hits after the first cell);
             // edge (cell m of the column starting at D with degree d, variable `lane`) = 32 D + lane d + (m - D)
-            float* dst = p.soft + cw * (BG::kCols * 32) + lane;
-            const float* gts = p.gt ? p.gt + cw * (BG::kCols * 32) + lane : nullptr;
+            float* dst = p.soft + cw * NV + r;
+            const float* gts = p.gt ? p.gt + cw * NV + r : nullptr;
 #pragma unroll 1
             for (int m0 = mem; m0 < EB; m0 += 4 * nq::kMembers) {
                 float sv[4], yv[4];
@@ -329,7 +343,7 @@ __global__ void __launch_bounds__(kNqThreads, 1) neural_qc_kernel(const NeuralQc
                     const int m = m0 + i * nq::kMembers;
                     col[i] = m < EB ? (int)nq::cell_col[m] : 0;
                     sv[i] = m < EB ? lls[m * kNqPitch + lane] : 0.5f;
-                    yv[i] = (gts && m < EB) ? __ldg(gts + 32 * col[i]) : 0.0f;
+                    yv[i] = (gts && m < EB) ? __ldg(gts + Z * col[i]) : 0.0f;
                 });
                 static_for<0, 4>([&](auto ic) {
                     constexpr int i = decltype(ic)::value;
@@ -338,19 +352,19 @@ __global__ void __launch_bounds__(kNqThreads, 1) neural_qc_kernel(const NeuralQc
                         const unsigned cmeta = nq::chunk_meta[m];
                         const int D = cmeta & 0xff, d = (cmeta >> 8) & 0x1f;
                         const float s = sv[i];
-                        if (live && m == D) dst[32 * col[i]] = s;
+                        if (live && m == D) dst[Z * col[i]] = s;
                         if (gts) {
                             const float y = yv[i];
                             const float l1 = fmaxf(logf(s), -100.0f), l0 = fmaxf(logf(1.0f - s), -100.0f);
                             const float loss = -(y * l1 + (1.0f - y) * l0);
-                            if (loss > best) { best = loss; besti = 32 * D + lane * d + (m - D); best_s = s; best_y = y; }   // ascending per thread
+                            if (loss > best) { best = loss; besti = Z * D + r * d + (m - D); best_s = s; best_y = y; }   // ascending per thread
                         }
                     }
                 });
             }
         } else {
-            float* dst = p.soft + cw * E + lane;
-            const float* gts = p.gt ? p.gt + cw * E + lane : nullptr;
+            float* dst = p.soft + cw * E + r;
+            const float* gts = p.gt ? p.gt + cw * E + r : nullptr;
             // four chunks at a time: their staged values and ground-truth lines are requested before the first logarithm
             // (training step 9.4 -> 8.5 ms per 32 768 codewords; a separate plain store loop for the no-ground-truth case
             // measured slower for both cases -- the kernel is sensitive to the code layout of its hot loops)
@@ -361,21 +375,21 @@ __global__ void __launch_bounds__(kNqThreads, 1) neural_qc_kernel(const NeuralQc
                     constexpr int i = decltype(ic)::value;
                     const int m = m0 + i * nq::kMembers;
                     sv[i] = m < EB ? lls[tile_addr[m * 32 + lane]] : 0.5f;
-                    yv[i] = (gts && m < EB) ? __ldg(gts + 32 * m) : 0.0f;
+                    yv[i] = (gts && m < EB) ? __ldg(gts + Z * m) : 0.0f;
                 });
                 static_for<0, 4>([&](auto ic) {
                     constexpr int i = decltype(ic)::value;
                     const int m = m0 + i * nq::kMembers;
                     if (m < EB) {
                         const float s = sv[i];
-                        if (live) dst[32 * m] = s;
+                        if (live) dst[Z * m] = s;
                         if (gts) {
                             // (a one-logarithm form for binary targets was measured SLOWER: 108 instead of 95 registers, inference
                             // 2.91 vs 2.60 ms per 32 768 codewords even though that path does not run without ground truth)
                             const float y = yv[i];
                             const float l1 = fmaxf(logf(s), -100.0f), l0 = fmaxf(logf(1.0f - s), -100.0f);
                             const float loss = -(y * l1 + (1.0f - y) * l0);
-                            if (loss > best) { best = loss; besti = 32 * m + lane; best_s = s; best_y = y; }   // first (lowest) edge among equal maxima
+                            if (loss > best) { best = loss; besti = Z * m + r; best_s = s; best_y = y; }   // first (lowest) edge among equal maxima
                         }
                     }
                 });
@@ -383,26 +397,27 @@ __global__ void __launch_bounds__(kNqThreads, 1) neural_qc_kernel(const NeuralQc
         }
         if (p.gt) {
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
+            for (int o = Z / 2; o > 0; o >>= 1) {                    // within the codeword's Z lanes
                 const float ob = __shfl_xor_sync(kFull, best, o);
                 const int oi = __shfl_xor_sync(kFull, besti, o);
                 const float os = __shfl_xor_sync(kFull, best_s, o), oy = __shfl_xor_sync(kFull, best_y, o);
                 if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; best_s = os; best_y = oy; }
             }
-            if (lane == 0) { red[mem] = best; red[4 + mem] = __int_as_float(besti); red[8 + mem] = best_s; red[12 + mem] = best_y; }
+            if (r == 0) { float* rd = red + 16 * sub; rd[mem] = best; rd[4 + mem] = __int_as_float(besti); rd[8 + mem] = best_s; rd[12 + mem] = best_y; }
         }
         nq_group_sync(grp);                                  // tile and `red` are complete; the next codeword may overwrite the tile
-        if (p.gt && live && mem == 0 && lane == 0) {
+        if (p.gt && live && mem == 0 && r == 0) {
+            const float* rd = red + 16 * sub;
             int q = 0;
 #pragma unroll
             for (int t = 1; t < nq::kMembers; ++t) {
-                const float ob = red[t], cb = red[q];
-                const int oi = __float_as_int(red[4 + t]), ci = __float_as_int(red[4 + q]);
+                const float ob = rd[t], cb = rd[q];
+                const int oi = __float_as_int(rd[4 + t]), ci = __float_as_int(rd[4 + q]);
                 if (ob > cb || (ob == cb && oi < ci)) q = t;
             }
-            p.max_loss[cw] = red[q];
-            if (p.argmax) p.argmax[cw] = __float_as_int(red[4 + q]);
-            if (p.star) { p.star[2 * cw] = red[8 + q]; p.star[2 * cw + 1] = red[12 + q]; }
+            p.max_loss[cw] = rd[q];
+            if (p.argmax) p.argmax[cw] = __float_as_int(rd[4 + q]);
+            if (p.star) { p.star[2 * cw] = rd[8 + q]; p.star[2 * cw + 1] = rd[12 + q]; }
         }
         nq_group_sync(grp);
     }

@@ -102,21 +102,26 @@ class _NeuralVariableFn(torch.autograd.Function):
 # ---- QC-structured path (csrc/neural_qc.cuh) -------------------------------------------------------------------------
 # The kernel implies the neighbour tables from the base graph, so it may only run when the caller's tables ARE the ones
 # create_LLR_mapping produces for that code.  Checked once per (tensor, version); canonical tables built once per device.
-_QC_CANON = {}      # device index -> (QCCode, check table, var table)
+_QC_CANON = {}      # (device index, Z) -> (QCCode, check table, var table, edge -> variable)
 _QC_SEEN = []       # [(check tensor, its version, var tensor, its version, ok)], most recent first; the tensors are held so that
                     # their addresses cannot be reused by other data while the verdict is cached
 
 
+_QC_LIFTS = (32, 16)     # lifting sizes the QC-structured kernels are compiled for (16: forward only)
+
+
 def _qc_code_for(check_index_tensor, var_index_tensor, num_nodes):
     from ..utils.ldpc_utils import QCCode, create_LLR_mapping
-    if num_nodes != 197 * 32 or tuple(check_index_tensor.shape) != (num_nodes, 9) or tuple(var_index_tensor.shape) != (num_nodes, 22):
+    Z = num_nodes // 197
+    if Z not in _QC_LIFTS or num_nodes != 197 * Z or tuple(check_index_tensor.shape) != (num_nodes, 9) \
+            or tuple(var_index_tensor.shape) != (num_nodes, 22):
         return None
     dev = check_index_tensor.device
-    canon = _QC_CANON.get(dev.index)
+    canon = _QC_CANON.get((dev.index, Z))
     if canon is None:
-        code = QCCode.nr_2_0(32)
+        code = QCCode.nr_2_0(Z)
         _, c, v, o = create_LLR_mapping(code.dense().T)
-        canon = _QC_CANON[dev.index] = (code, c.to(dev), v.to(dev), torch.as_tensor(o).reshape(-1).to(torch.int64).to(dev))
+        canon = _QC_CANON[(dev.index, Z)] = (code, c.to(dev), v.to(dev), torch.as_tensor(o).reshape(-1).to(torch.int64).to(dev))
     for i, (ct, cv, vt, vv, ok) in enumerate(_QC_SEEN):
         if ct is check_index_tensor and vt is var_index_tensor and cv == ct._version and vv == vt._version:
             if i:
@@ -330,7 +335,7 @@ class LDPCNeuralDecoder(nn.Module):
         """(B, N) LLRs (and targets) straight into the QC-structured kernels; None when this call cannot take that path (tables
         that are not the 5G BG2 Z=32 ones, targets in edge space, gradients w.r.t. the LLRs, no targets while training)."""
         n_var = self.var_first_edge.numel()
-        if llr_v.dim() != 2 or llr_v.shape[1] != n_var or n_var != 52 * 32:
+        if llr_v.dim() != 2 or llr_v.shape[1] != n_var or n_var * 197 != 52 * self.num_nodes:
             return None
         if gt_v is not None and tuple(gt_v.shape) != tuple(llr_v.shape):
             return None
@@ -340,11 +345,11 @@ class LDPCNeuralDecoder(nn.Module):
         if needs_grad and (gt_v is None or llr_v.requires_grad):
             return None
         code = _qc_code_for(check_index_tensor, var_index_tensor, self.num_nodes)
-        if code is None:
+        if code is None or (needs_grad and code.Z != 32):          # the one-kernel backward is compiled for Z = 32
             return None
         if self._etv_canonical is None:
             dev = check_index_tensor.device
-            self._etv_canonical = bool(torch.equal(self.edge_to_var.to(dev), _QC_CANON[dev.index][3]))
+            self._etv_canonical = bool(torch.equal(self.edge_to_var.to(dev), _QC_CANON[(dev.index, code.Z)][3]))
         if not self._etv_canonical:
             return None
         w_ch_t, w_res_t = self._weights()
@@ -381,6 +386,8 @@ class LDPCNeuralDecoder(nn.Module):
         if (self.fused and self.qc and needs_grad and gt_e is not None and self.depth_L <= 2 and not llr_e.requires_grad
                 and check_index_tensor.shape[0] == self.num_nodes and var_index_tensor.shape[0] == self.num_nodes):
             code = _qc_code_for(check_index_tensor, var_index_tensor, self.num_nodes)
+            if code is not None and code.Z != 32:
+                code = None                                          # the one-kernel backward is compiled for Z = 32
         if code is not None:
             # training on the QC structure: one forward kernel that saves the CheckLayer inputs + one backward kernel
             w_ch_t, w_res_t = self._weights()

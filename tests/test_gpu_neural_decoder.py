@@ -421,3 +421,51 @@ def test_per_variable_qc_path_is_bit_identical_to_the_expanded_edge_space_path(d
     with torch.no_grad():
         s_m, m_m = dv(llr, cidx, vidx, gt_e)
     assert torch.equal(s_m, s_v.detach()) and torch.equal(m_m, m_v.detach())
+
+
+@pytest.mark.parametrize("depth_L,iters,B", [(2, 5, 2 * 4 * 148 + 3), (1, 3, 1), (0, 2, 2), (2, 8, 45)])
+def test_qc_structured_kernel_at_the_default_lifting_factor_16(depth_L, iters, B):
+    """Z = 16 is the reference's default --lifting_factor (main.py:38).  The QC-structured forward kernel then holds TWO codewords
+    per warp (lane = 16 * sub + r; rotations inside the 16 lanes of a codeword).  Same bits as the table-driven kernel for every
+    soft output and max loss -- edge-space and per-variable I/O, odd batch sizes (a warp with one live codeword), zeros."""
+    code = QCCode.nr_2_0(16)
+    _, cidx, vidx, oidx = create_LLR_mapping(code.dense().T)
+    cidx, vidx = cidx.to(DEV), vidx.to(DEV)
+    etv = torch.as_tensor(oidx).reshape(-1).to(torch.int64).to(DEV)
+    rng = np.random.default_rng(7 * depth_L + iters)
+    llr_e = (rng.normal(size=(B, code.E)) * 0.8 + 0.4).astype(np.float32)
+    llr_e[0, ::7] = 0.0
+    llr_e[B // 2, 5:900:3] = -1e-10
+    w_ch = (rng.random(code.E) * 0.5 + 0.75).astype(np.float32)
+    w_res = np.array([0.2, -0.1][:depth_L], np.float32)
+    gt_e = (rng.random((B, code.E)) < 0.5).astype(np.float32)
+
+    def make(qc, out=None):
+        d = LDPCNeuralDecoder(code.E, iters, depth_L, output_index_tensor=out, qc=qc).to(DEV)
+        with torch.no_grad():
+            d.residual_layer.w_ch.copy_(torch.from_numpy(w_ch))
+            d.residual_layer.w_res.copy_(torch.from_numpy(w_res))
+        return d
+    x, y = torch.from_numpy(llr_e).to(DEV), torch.from_numpy(gt_e).to(DEV)
+    lib = ldpc_b200._native.lib()
+    with torch.no_grad():
+        n0 = lib.ldpc_launch_count()
+        s_qc, m_qc = make(True)(x, cidx, vidx, y)
+        assert lib.ldpc_launch_count() == n0 + 1
+        s_tb, m_tb = make(False)(x, cidx, vidx, y)
+        assert torch.equal(s_qc, s_tb) and torch.equal(m_qc, m_tb)
+        assert torch.equal(make(True)(x, cidx, vidx)[0], s_qc)
+        # per-variable I/O
+        llr_v = torch.from_numpy((rng.normal(size=(B, code.N)) * 0.8 + 0.4).astype(np.float32)).to(DEV)
+        gt_v = torch.from_numpy((rng.random((B, code.N)) < 0.5).astype(np.float32)).to(DEV)
+        dv = make(True, oidx)
+        n0 = lib.ldpc_launch_count()
+        s_v, m_v = dv(llr_v, cidx, vidx, gt_v)
+        assert lib.ldpc_launch_count() == n0 + 1 and s_v.shape == llr_v.shape
+        s_e, m_e = make(False)(llr_v[:, etv].contiguous(), cidx, vidx, gt_v[:, etv].contiguous())
+        assert torch.equal(s_v, s_e[:, dv.var_first_edge.to(DEV)]) and torch.equal(m_v, m_e)
+    # training at Z = 16 takes the per-layer path (the one-kernel backward is compiled for Z = 32): gradients exist
+    d = make(True)
+    _, ml = d(x[:8], cidx, vidx, y[:8])
+    ml.mean().backward()
+    assert d.residual_layer.w_ch.grad is not None and float(d.residual_layer.w_ch.grad.abs().max()) > 0
