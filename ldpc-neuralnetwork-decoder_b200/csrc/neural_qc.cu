@@ -21,23 +21,28 @@ static int launch_neural_qc_bg(const NeuralQcParams& p, cudaStream_t st) {
 
 int launch_neural_qc(const ldpc_code_t* c, const NeuralQcParams& p, cudaStream_t st) {
     if (c->fast_kind == 1) return launch_neural_qc_bg<BG2Z32>(p, st);
-    // Z = 16 (the reference's default --lifting_factor): two codewords per warp; forward only -- the one-kernel backward is Z = 32
-    if (c->fast_kind == 3 && !p.save_x) return launch_neural_qc_bg<BG2Z16>(p, st);
-    return fail(LDPC_ERR_UNSUPPORTED, "neural_decode_qc: the QC-structured kernel is compiled for the 5G BG2 tables at Z = 32 (and Z = 16 without saved activations)");
+    if (c->fast_kind == 3) return launch_neural_qc_bg<BG2Z16>(p, st);      // the reference's default --lifting_factor: two codewords per warp
+    return fail(LDPC_ERR_UNSUPPORTED, "neural_decode_qc: the QC-structured kernel is compiled for the 5G BG2 tables at Z = 32 and Z = 16");
 }
 
-int launch_neural_qc_bwd(const ldpc_code_t* c, const NeuralQcBwdParams& p, cudaStream_t st) {
-    if (c->fast_kind != 1)
-        return fail(LDPC_ERR_UNSUPPORTED, "neural_backward_qc: the QC-structured kernel is compiled for the 5G BG2 Z=32 table only");
-    auto kern = neural_qc_bwd_kernel<BG2Z32>;
-    constexpr size_t smem = neural_qc_bwd_smem_bytes<BG2Z32>();
+template <class BG>
+static int launch_neural_qc_bwd_bg(const NeuralQcBwdParams& p, cudaStream_t st) {
+    auto kern = neural_qc_bwd_kernel<BG>;
+    constexpr size_t smem = neural_qc_bwd_smem_bytes<BG>();
     static_assert(smem <= (size_t)kMaxSmemPerBlock, "neural_qc_bwd shared memory");
     LDPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    long long blocks = (p.B + kNqGroups - 1) / kNqGroups;
+    constexpr int per_cta = kNqGroups * (32 / BG::kZ);
+    long long blocks = (p.B + per_cta - 1) / per_cta;
     if (blocks > kNumSMs) blocks = kNumSMs;
     kern<<<(int)blocks, kNqThreads, smem, st>>>(p);
     LDPC_CHECK_LAUNCH("neural_qc_bwd_kernel");
     return LDPC_OK;
+}
+
+int launch_neural_qc_bwd(const ldpc_code_t* c, const NeuralQcBwdParams& p, cudaStream_t st) {
+    if (c->fast_kind == 1) return launch_neural_qc_bwd_bg<BG2Z32>(p, st);
+    if (c->fast_kind == 3) return launch_neural_qc_bwd_bg<BG2Z16>(p, st);
+    return fail(LDPC_ERR_UNSUPPORTED, "neural_backward_qc: the QC-structured kernel is compiled for the 5G BG2 tables at Z = 32 and Z = 16");
 }
 
 }  // namespace ldpc

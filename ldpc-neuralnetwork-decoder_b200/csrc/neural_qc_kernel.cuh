@@ -451,13 +451,23 @@ constexpr size_t neural_qc_bwd_smem_bytes() {
 
 template <class BG>
 __global__ void __launch_bounds__(kNqThreads, 1) neural_qc_bwd_kernel(const NeuralQcBwdParams p) {
-    static_assert(BG::kZ == 32, "one codeword per warp-wide lane set");
+    constexpr int Z = BG::kZ, G = 32 / Z;                                  // G codewords per warp, as in the forward kernel
+    static_assert(Z == 32 || Z == 16 || Z == 8 || Z == 4, "lifting sizes with a whole number of codewords per warp");
     constexpr int EB = BG::kEdges, EC = BG::kCoreEdges, NX = BG::kExtCols;
     constexpr int ECP = (EC + 3) / 4 * 4;
-    constexpr int E = EB * 32;
+    constexpr int E = EB * Z;
     extern __shared__ float nq_smem[];
     const int lane = threadIdx.x & 31, warp = __shfl_sync(kFull, (int)(threadIdx.x >> 5), 0);
     const int grp = warp & (kNqGroups - 1), mem = warp / kNqGroups;
+    const int r = lane & (Z - 1), sub = lane / Z, lbase = lane & ~(Z - 1);
+    auto rot = [&](float v, int s) {
+        if constexpr (Z == 32) return __shfl_sync(kFull, v, lane + s);
+        else return __shfl_sync(kFull, v, lbase | ((lane + s) & (Z - 1)));
+    };
+    auto rot_back = [&](float v, int s) {
+        if constexpr (Z == 32) return __shfl_sync(kFull, v, lane - s);
+        else return __shfl_sync(kFull, v, lbase | ((lane - s) & (Z - 1)));
+    };
     float* gw = nq_smem;                                                   // [EB][32]  g_w_ch per (cell, lane), all codewords
     float* gc = nq_smem + EB * 32 + grp * nqb_group_floats<BG>();         // [EC][32]  d/d c2v of the core cells (variable-aligned)
     float* ae = gc + EC * 32;                                              // [3][NX][32] gradient ring of the degree-1 cells
@@ -479,18 +489,19 @@ __global__ void __launch_bounds__(kNqThreads, 1) neural_qc_bwd_kernel(const Neur
     const float wres0 = p.L >= 1 ? __ldg(p.w_res) : 0.0f, wres1 = p.L >= 2 ? __ldg(p.w_res + 1) : 0.0f;
     float acc_wr0 = 0.0f, acc_wr1 = 0.0f;
 
-    for (long long cw0 = (long long)blockIdx.x * kNqGroups; cw0 < p.B; cw0 += (long long)gridDim.x * kNqGroups) {
-        const bool live = cw0 + grp < p.B;
-        const long long cw = live ? cw0 + grp : p.B - 1;
+    for (long long cw0 = (long long)blockIdx.x * kNqGroups * G; cw0 < p.B; cw0 += (long long)gridDim.x * kNqGroups * G) {
+        const bool live = cw0 + grp * G + sub < p.B;
+        const long long cw = live ? cw0 + grp * G + sub : p.B - 1;
         // the NEXT codeword of this group: pull its saved activations (all levels) into L2 -- they stream from HBM otherwise
         // and every row / column step would wait a full DRAM latency (first build: long_scoreboard 10 stalls per issue)
         {
-            const long long nxt = cw0 + (long long)gridDim.x * kNqGroups + grp;
+            const long long nxt = cw0 + ((long long)gridDim.x * kNqGroups + grp) * G;
             if (nxt < p.B) {
                 const int t = mem * 32 + lane;
+                const long long have = (p.B - nxt < G ? p.B - nxt : G) * (long long)E;     // the G codewords are adjacent
                 for (int l = 0; l < p.iters; ++l) {
                     const float* base = p.save_x + ((long long)l * p.B + nxt) * E;
-                    for (int i = t; i < EB; i += nq::kMembers * 32) asm volatile("prefetch.global.L2 [%0];" :: "l"(base + 32 * i));
+                    for (long long i = 32 * t; i < have; i += 32 * nq::kMembers * 32) asm volatile("prefetch.global.L2 [%0];" :: "l"(base + i));
                 }
             }
         }
@@ -503,16 +514,16 @@ __global__ void __launch_bounds__(kNqThreads, 1) neural_qc_bwd_kernel(const Neur
             gz = __ldg(p.g_ml + cw) * (s - y) / fmaxf((1.0f - s) * s, 1e-12f) * (s * (1.0f - s));
             if (!live) gz = 0.0f;                                          // a group past the end of the batch contributes nothing
         }
-        const unsigned smeta = nq::chunk_meta[es >> 5];
+        const unsigned smeta = nq::chunk_meta[es / Z];
         const int sD = smeta & 0xff, sd = (smeta >> 8) & 0x1f;
-        const int soff = 32 * ((es >> 5) - sD) + (es & 31), srow = (soff * (int)(smeta >> 13)) >> 16;      // circulant row of e*
+        const int soff = Z * ((es / Z) - sD) + (es & (Z - 1)), srow = (soff * (int)(smeta >> 13)) >> 16;      // circulant row of e*
         for (int m = mem; m < EC; m += nq::kMembers) {
-            gc[m * 32 + lane] = (m >= sD && m < sD + sd && lane == srow) ? gz : 0.0f;
+            gc[m * 32 + lane] = (m >= sD && m < sD + sd && r == srow) ? gz : 0.0f;
             nq_st1(tA0 + m, 0.0f);
             nq_st1(tA1 + m, 0.0f);
         }
         for (int x = mem; x < NX; x += nq::kMembers) {
-            gce[x * 32 + lane] = (EC + x == sD && lane == srow) ? gz : 0.0f;
+            gce[x * 32 + lane] = (EC + x == sD && r == srow) ? gz : 0.0f;
             ae[a0 + x * 32 + lane] = 0.0f;
             ae[a1 + x * 32 + lane] = 0.0f;
         }
@@ -525,10 +536,10 @@ __global__ void __launch_bounds__(kNqThreads, 1) neural_qc_bwd_kernel(const Neur
         auto row_prefetch = [&](int row, const float* xl) {
             static_for<0, 10>([&](auto kc) {
                 constexpr int k = decltype(kc)::value;
-                pre[k] = __ldg(xl + 32 * (int)(nq::row_meta[row][k] & 0xff));
+                pre[k] = __ldg(xl + Z * (int)(nq::row_meta[row][k] & 0xff));
             });
             const int xr = nq::row_ext[row];
-            pre[10] = __ldg(xl + 32 * (EC + (xr < NX ? xr : 0)));                  // rows without a degree-1 edge re-read slot 0
+            pre[10] = __ldg(xl + Z * (EC + (xr < NX ? xr : 0)));                   // rows without a degree-1 edge re-read slot 0
         };
         auto row_bwd = [&](auto ncc, auto nec, int row, int next_row, const float* xl, bool last) {
             constexpr int NC = decltype(ncc)::value, NE = decltype(nec)::value, d = NC + NE;
@@ -542,7 +553,7 @@ __global__ void __launch_bounds__(kNqThreads, 1) neural_qc_bwd_kernel(const Neur
                 constexpr int k = decltype(kc)::value;
                 const unsigned meta = nq::row_meta[row][k];
                 cell[k] = meta & 0xff;
-                sft[k] = meta >> 8;
+                sft[k] = Z == 32 ? (meta >> 8) : ((meta >> 8) & (Z - 1));
                 g[k] = gc[cell[k] * 32 + lane];
                 nq_ld1_issue(tA0 + cell[k], old[k]);
             });
@@ -553,8 +564,8 @@ __global__ void __launch_bounds__(kNqThreads, 1) neural_qc_bwd_kernel(const Neur
             }
             static_for<0, NC>([&](auto kc) {
                 constexpr int k = decltype(kc)::value;
-                v[k] = __shfl_sync(kFull, v[k], lane + sft[k]);
-                g[k] = __shfl_sync(kFull, g[k], lane + sft[k]);
+                v[k] = rot(v[k], sft[k]);
+                g[k] = rot(g[k], sft[k]);
             });
             // forward quantities again: sign bits of (v + 1e-10), first arg-min k1 and runner-up k2 of |v| (zeros -> 1e10)
             unsigned nb = 0;
@@ -588,7 +599,7 @@ __global__ void __launch_bounds__(kNqThreads, 1) neural_qc_bwd_kernel(const Neur
                 c = u2f(f2u(c) ^ (f2u(v[k]) & 0x80000000u));                       // d|x|/dx = sign(x)
                 if constexpr (k < NC) {
                     nq_tie(old[k]);
-                    nq_st1(tA0 + cell[k], __fadd_rn(old[k], __shfl_sync(kFull, c, lane - sft[k])));
+                    nq_st1(tA0 + cell[k], __fadd_rn(old[k], rot_back(c, sft[k])));
                 } else {
                     ae[a0 + xs * 32 + lane] += c;
                 }
@@ -596,7 +607,7 @@ __global__ void __launch_bounds__(kNqThreads, 1) neural_qc_bwd_kernel(const Neur
         };
 
         for (int l = p.iters - 1; l >= 1; --l) {
-            const float* xl = p.save_x + ((long long)l * p.B + cw) * E + lane;
+            const float* xl = p.save_x + ((long long)l * p.B + cw) * E + r;
             const bool last = l == p.iters - 1;
             row_prefetch((int)nq::sched_rows[mem][0], xl);
             static_for<0, nq::kRowClasses>([&](auto cc) {
@@ -609,9 +620,9 @@ __global__ void __launch_bounds__(kNqThreads, 1) neural_qc_bwd_kernel(const Neur
             });
             nq_group_sync(grp);
             // ---- Variable + Residual backward ----
-            const float* x0 = p.save_x + cw * E + lane;                                   // llr_e
-            const float* xm1 = p.save_x + ((long long)(l - 1) * p.B + cw) * E + lane;      // x_{l-1}: queue entry iff l-1 >= 1
-            const float* xm2 = p.save_x + ((long long)(l >= 2 ? l - 2 : 0) * p.B + cw) * E + lane;
+            const float* x0 = p.save_x + cw * E + r;                                      // llr_e
+            const float* xm1 = p.save_x + ((long long)(l - 1) * p.B + cw) * E + r;         // x_{l-1}: queue entry iff l-1 >= 1
+            const float* xm2 = p.save_x + ((long long)(l >= 2 ? l - 2 : 0) * p.B + cw) * E + r;
             const float w0 = l >= 2 ? wres0 : 0.0f, w1 = l >= 3 ? wres1 : 0.0f;
             const float u0 = l >= 2 ? 1.0f : 0.0f, u1 = l >= 3 ? 1.0f : 0.0f;            // which w_res entries this level feeds
             // column sums of gx (the member owns at most kColsMax columns; their sums stay in registers)
@@ -645,9 +656,9 @@ __global__ void __launch_bounds__(kNqThreads, 1) neural_qc_bwd_kernel(const Neur
                     constexpr int i = decltype(ic)::value;
                     const int m = nq::sched_cells[mem][c0 + i];
                     cm[i] = m < 255 ? m : 0;                                        // padding: reads cell 0, stores nothing
-                    ll[i] = __ldg(x0 + 32 * cm[i]);
-                    y1[i] = __ldg(xm1 + 32 * cm[i]);
-                    y2[i] = __ldg(xm2 + 32 * cm[i]);
+                    ll[i] = __ldg(x0 + Z * cm[i]);
+                    y1[i] = __ldg(xm1 + Z * cm[i]);
+                    y2[i] = __ldg(xm2 + Z * cm[i]);
                     nq_ld1_issue(tA0 + cm[i], gx[i]);
                     nq_ld1_issue(tA1 + cm[i], pa[i]);
                 });
@@ -675,9 +686,9 @@ __global__ void __launch_bounds__(kNqThreads, 1) neural_qc_bwd_kernel(const Neur
                 static_for<0, 4>([&](auto ic) {
                     constexpr int i = decltype(ic)::value;
                     xs[i] = nq::sched_ext[mem][t + i < nx ? t + i : t];
-                    ll[i] = __ldg(x0 + 32 * (EC + xs[i]));
-                    y1[i] = __ldg(xm1 + 32 * (EC + xs[i]));
-                    y2[i] = __ldg(xm2 + 32 * (EC + xs[i]));
+                    ll[i] = __ldg(x0 + Z * (EC + xs[i]));
+                    y1[i] = __ldg(xm1 + Z * (EC + xs[i]));
+                    y2[i] = __ldg(xm2 + Z * (EC + xs[i]));
                 });
                 static_for<0, 4>([&](auto ic) {
                     constexpr int i = decltype(ic)::value;
@@ -712,7 +723,7 @@ __global__ void __launch_bounds__(kNqThreads, 1) neural_qc_bwd_kernel(const Neur
     for (int m = warp; m < EB; m += kNqThreads / 32) {
         const unsigned cmeta = nq::chunk_meta[m];
         const int D = cmeta & 0xff, d = (cmeta >> 8) & 0x1f;
-        atomicAdd(p.g_wch + 32 * D + lane * d + (m - D), gw[m * 32 + lane]);
+        atomicAdd(p.g_wch + Z * D + r * d + (m - D), gw[m * 32 + lane]);     // Z < 32: the G codeword slots of a warp add to the same weight
     }
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem_base_s) : "memory");
 }

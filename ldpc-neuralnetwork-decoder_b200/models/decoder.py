@@ -107,7 +107,7 @@ _QC_SEEN = []       # [(check tensor, its version, var tensor, its version, ok)]
                     # their addresses cannot be reused by other data while the verdict is cached
 
 
-_QC_LIFTS = (32, 16)     # lifting sizes the QC-structured kernels are compiled for (16: forward only)
+_QC_LIFTS = (32, 16)     # lifting sizes the QC-structured kernels are compiled for (16 = the reference's default --lifting_factor)
 
 
 def _qc_code_for(check_index_tensor, var_index_tensor, num_nodes):
@@ -345,7 +345,7 @@ class LDPCNeuralDecoder(nn.Module):
         if needs_grad and (gt_v is None or llr_v.requires_grad):
             return None
         code = _qc_code_for(check_index_tensor, var_index_tensor, self.num_nodes)
-        if code is None or (needs_grad and code.Z != 32):          # the one-kernel backward is compiled for Z = 32
+        if code is None:
             return None
         if self._etv_canonical is None:
             dev = check_index_tensor.device
@@ -386,8 +386,6 @@ class LDPCNeuralDecoder(nn.Module):
         if (self.fused and self.qc and needs_grad and gt_e is not None and self.depth_L <= 2 and not llr_e.requires_grad
                 and check_index_tensor.shape[0] == self.num_nodes and var_index_tensor.shape[0] == self.num_nodes):
             code = _qc_code_for(check_index_tensor, var_index_tensor, self.num_nodes)
-            if code is not None and code.Z != 32:
-                code = None                                          # the one-kernel backward is compiled for Z = 32
         if code is not None:
             # training on the QC structure: one forward kernel that saves the CheckLayer inputs + one backward kernel
             w_ch_t, w_res_t = self._weights()

@@ -464,8 +464,29 @@ def test_qc_structured_kernel_at_the_default_lifting_factor_16(depth_L, iters, B
         assert lib.ldpc_launch_count() == n0 + 1 and s_v.shape == llr_v.shape
         s_e, m_e = make(False)(llr_v[:, etv].contiguous(), cidx, vidx, gt_v[:, etv].contiguous())
         assert torch.equal(s_v, s_e[:, dv.var_first_edge.to(DEV)]) and torch.equal(m_v, m_e)
-    # training at Z = 16 takes the per-layer path (the one-kernel backward is compiled for Z = 32): gradients exist
-    d = make(True)
-    _, ml = d(x[:8], cidx, vidx, y[:8])
-    ml.mean().backward()
-    assert d.residual_layer.w_ch.grad is not None and float(d.residual_layer.w_ch.grad.abs().max()) > 0
+    # training at Z = 16: one forward + one backward kernel, against the per-layer kernels under autograd
+    up = torch.linspace(0.5, 1.5, B, device=DEV)
+    xs, ys = x * 0.25, y                                     # keeps sigmoid / BCE out of saturation
+    dq, dt = make(True), make(False)
+    n0 = lib.ldpc_launch_count()
+    _, m_q = dq(xs, cidx, vidx, ys)
+    (m_q * up).mean().backward()
+    assert lib.ldpc_launch_count() == n0 + 2
+    _, m_t = dt(xs, cidx, vidx, ys)
+    (m_t * up).mean().backward()
+    assert torch.equal(m_q.detach(), m_t.detach())
+    gq, gt_ = dq.residual_layer.w_ch.grad, dt.residual_layer.w_ch.grad
+    assert float(gt_.abs().max()) > 0 and float((gq - gt_).abs().max()) <= 1e-4 * float(gt_.abs().max())
+    if depth_L:
+        rq, rt = dq.residual_layer.w_res.grad, dt.residual_layer.w_res.grad
+        assert float((rq - rt).abs().max()) <= 1e-4 * max(float(rt.abs().max()), 1e-12)
+    # per-variable training step: same gradients as the edge-space step on the expanded arrays
+    dvq = make(True, oidx)
+    _, m_v = dvq(llr_v * 0.25, cidx, vidx, gt_v)
+    (m_v * up).mean().backward()
+    dte = make(False)
+    _, m_e2 = dte((llr_v * 0.25)[:, etv].contiguous(), cidx, vidx, gt_v[:, etv].contiguous())
+    (m_e2 * up).mean().backward()
+    assert torch.equal(m_v.detach(), m_e2.detach())
+    gv, ge = dvq.residual_layer.w_ch.grad, dte.residual_layer.w_ch.grad
+    assert float((gv - ge).abs().max()) <= 1e-4 * max(float(ge.abs().max()), 1e-12)
