@@ -244,10 +244,11 @@ int ldpc_neural_decode(const float* llr_e, const uint16_t* cidx, int Kc, const u
                        float* max_loss, void* stream);
 /* The same decoder on the quasi-cyclic structure of the code (csrc/neural_qc.cuh): no index tables -- the neighbour
  * lists of create_LLR_mapping (utils/ldpc_utils.py:62-95) are implied by the base graph, check neighbours are lane
- * rotations, variable neighbours are lane-local, the edge state lives in Tensor Memory.  Compiled for the 5G BG2 Z=32
- * table (LDPC_ERR_UNSUPPORTED otherwise) and residual depth L <= 2.  llr_e / gt_e / soft: [B, E] in the variable-major
+ * rotations, variable neighbours are lane-local, the edge state lives in Tensor Memory.  Compiled for the 5G BG2 tables
+ * at Z = 32 and Z = 16 (the reference's default --lifting_factor; two codewords per warp) -- LDPC_ERR_UNSUPPORTED
+ * otherwise -- and residual depth L <= 2.  llr_e / gt_e / soft: [B, E] in the variable-major
  * edge order of create_LLR_mapping(H.T); bit-identical to ldpc_neural_decode with that code's tables.
- * Training (the loop of training/trainer.py:95-110, `loss.mean().backward()`): pass save_x [iters, B, 197, 32] (the input of
+ * Training (the loop of training/trainer.py:95-110, `loss.mean().backward()`): pass save_x [iters, B, 197, Z] (the input of
  * every CheckLayer, stored lane-major) and argmax [B] (edge whose BCE is the frame's max_loss); ldpc_neural_backward_qc then
  * accumulates d(sum_b g_ml[b] * max_loss[b]) / d w_ch into g_wch [E] and / d w_res into g_wres [L] (+=) -- the autograd of
  * the four reference layers in that composition, one forward and one backward kernel per step.                        */
@@ -258,7 +259,7 @@ int ldpc_neural_backward_qc(const ldpc_code_t* code, const float* save_x, const 
                             void* stream);
 /* The same two kernels with PER-VARIABLE input and output -- the trainer's own call shape (training/trainer.py:95-110,180-187:
  * LLRs and targets per code bit, expanded with llr[:, edge_to_var] before the layers run): llr_v / gt_v / soft_v are [B, N]
- * (N = 1664); every edge of a variable takes its variable's LLR and target, soft_v holds the output at each variable's
+ * (N = 52 Z); every edge of a variable takes its variable's LLR and target, soft_v holds the output at each variable's
  * first edge, max_loss / argmax range over all E edges exactly as in ldpc_neural_decode_qc (bit-identical to it on the
  * expanded arrays).  star [B, 2] receives (soft, target) at the arg-max edge, which is all ldpc_neural_backward_qc_var
  * needs of the two arrays: no [B, E] tensor exists anywhere on this path.                                             */

@@ -41,7 +41,7 @@ struct NeuralQcParams {
     float* soft;           // [B, E]
     float* max_loss;       // [B] (with gt)
     // training forward: activations the backward pass reads, or null
-    float* save_x;         // [iters, B, 197 cells, 32 lanes] input of every CheckLayer (x_0 = llr_e, x_1, ...), lane-major
+    float* save_x;         // [iters, B, 197 cells, Z rows] input of every CheckLayer (x_0 = llr_e, x_1, ...), row-major per cell
     int32_t* argmax;       // [B] edge (caller's numbering) whose loss is the frame's maximum, or null
     // per-variable I/O (the trainer's call shape, training/trainer.py:95-110: LLRs and targets per code bit): llr and gt are
     // [B, N], every edge of a variable takes its variable's value (what llr[:, edge_to_var] would hold), soft is [B, N] and
@@ -52,7 +52,7 @@ struct NeuralQcParams {
 
 // backward of (max_loss) w.r.t. w_ch and w_res from the activations a save_x forward left behind
 struct NeuralQcBwdParams {
-    const float* save_x;   // [iters, B, 197, 32]
+    const float* save_x;   // [iters, B, 197, Z]
     const float* soft;     // [B, E]  (ignored when star is given)
     const float* gt;       // [B, E]
     const float* star;     // [B, 2] (soft, target) at the arg-max edge from a forward with `star`, or null
