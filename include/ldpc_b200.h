@@ -245,7 +245,7 @@ int ldpc_neural_decode(const float* llr_e, const uint16_t* cidx, int Kc, const u
 /* The same decoder on the quasi-cyclic structure of the code (csrc/neural_qc.cuh): no index tables -- the neighbour
  * lists of create_LLR_mapping (utils/ldpc_utils.py:62-95) are implied by the base graph, check neighbours are lane
  * rotations, variable neighbours are lane-local, the edge state lives in Tensor Memory.  Compiled for the 5G BG2 tables
- * at Z = 32 and Z = 16 (the reference's default --lifting_factor; two codewords per warp) -- LDPC_ERR_UNSUPPORTED
+ * at Z = 32, 16 (the reference's default --lifting_factor), 8 and 4 (32 / Z codewords per warp) -- LDPC_ERR_UNSUPPORTED
  * otherwise -- and residual depth L <= 2.  llr_e / gt_e / soft: [B, E] in the variable-major
  * edge order of create_LLR_mapping(H.T); bit-identical to ldpc_neural_decode with that code's tables.
  * Training (the loop of training/trainer.py:95-110, `loss.mean().backward()`): pass save_x [iters, B, 197, Z] (the input of

@@ -22,7 +22,9 @@ static int launch_neural_qc_bg(const NeuralQcParams& p, cudaStream_t st) {
 int launch_neural_qc(const ldpc_code_t* c, const NeuralQcParams& p, cudaStream_t st) {
     if (c->fast_kind == 1) return launch_neural_qc_bg<BG2Z32>(p, st);
     if (c->fast_kind == 3) return launch_neural_qc_bg<BG2Z16>(p, st);      // the reference's default --lifting_factor: two codewords per warp
-    return fail(LDPC_ERR_UNSUPPORTED, "neural_decode_qc: the QC-structured kernel is compiled for the 5G BG2 tables at Z = 32 and Z = 16");
+    if (c->fast_kind == 4) return launch_neural_qc_bg<BG2Z8>(p, st);
+    if (c->fast_kind == 2) return launch_neural_qc_bg<BG2Z4>(p, st);       // the shipped NR_2_0_4.txt: eight codewords per warp
+    return fail(LDPC_ERR_UNSUPPORTED, "neural_decode_qc: the QC-structured kernel is compiled for the 5G BG2 tables at Z = 32, 16, 8, 4");
 }
 
 template <class BG>
@@ -42,7 +44,9 @@ static int launch_neural_qc_bwd_bg(const NeuralQcBwdParams& p, cudaStream_t st) 
 int launch_neural_qc_bwd(const ldpc_code_t* c, const NeuralQcBwdParams& p, cudaStream_t st) {
     if (c->fast_kind == 1) return launch_neural_qc_bwd_bg<BG2Z32>(p, st);
     if (c->fast_kind == 3) return launch_neural_qc_bwd_bg<BG2Z16>(p, st);
-    return fail(LDPC_ERR_UNSUPPORTED, "neural_backward_qc: the QC-structured kernel is compiled for the 5G BG2 tables at Z = 32 and Z = 16");
+    if (c->fast_kind == 4) return launch_neural_qc_bwd_bg<BG2Z8>(p, st);
+    if (c->fast_kind == 2) return launch_neural_qc_bwd_bg<BG2Z4>(p, st);
+    return fail(LDPC_ERR_UNSUPPORTED, "neural_backward_qc: the QC-structured kernel is compiled for the 5G BG2 tables at Z = 32, 16, 8, 4");
 }
 
 }  // namespace ldpc

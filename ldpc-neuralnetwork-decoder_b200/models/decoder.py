@@ -107,7 +107,7 @@ _QC_SEEN = []       # [(check tensor, its version, var tensor, its version, ok)]
                     # their addresses cannot be reused by other data while the verdict is cached
 
 
-_QC_LIFTS = (32, 16)     # lifting sizes the QC-structured kernels are compiled for (16 = the reference's default --lifting_factor)
+_QC_LIFTS = (32, 16, 8, 4)     # lifting sizes the QC-structured kernels are compiled for (16 = the reference's default --lifting_factor)
 
 
 def _qc_code_for(check_index_tensor, var_index_tensor, num_nodes):

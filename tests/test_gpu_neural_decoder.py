@@ -423,12 +423,14 @@ def test_per_variable_qc_path_is_bit_identical_to_the_expanded_edge_space_path(d
     assert torch.equal(s_m, s_v.detach()) and torch.equal(m_m, m_v.detach())
 
 
-@pytest.mark.parametrize("depth_L,iters,B", [(2, 5, 2 * 4 * 148 + 3), (1, 3, 1), (0, 2, 2), (2, 8, 45)])
-def test_qc_structured_kernel_at_the_default_lifting_factor_16(depth_L, iters, B):
+@pytest.mark.parametrize("Z,depth_L,iters,B", [(16, 2, 5, 2 * 4 * 148 + 3), (16, 1, 3, 1), (16, 0, 2, 2), (16, 2, 8, 45),
+                                                (8, 2, 5, 4 * 4 * 148 + 5), (8, 1, 2, 3), (4, 2, 5, 8 * 4 * 148 + 9), (4, 0, 3, 7)])
+def test_qc_structured_kernel_at_the_default_lifting_factor_16(Z, depth_L, iters, B):
     """Z = 16 is the reference's default --lifting_factor (main.py:38).  The QC-structured forward kernel then holds TWO codewords
     per warp (lane = 16 * sub + r; rotations inside the 16 lanes of a codeword).  Same bits as the table-driven kernel for every
-    soft output and max loss -- edge-space and per-variable I/O, odd batch sizes (a warp with one live codeword), zeros."""
-    code = QCCode.nr_2_0(16)
+    soft output and max loss -- edge-space and per-variable I/O, odd batch sizes (a warp with one live codeword), zeros.
+    Z = 8 and Z = 4 (the shipped NR_2_0_4.txt): four and eight codewords per warp, same kernels."""
+    code = QCCode.nr_2_0(Z)
     _, cidx, vidx, oidx = create_LLR_mapping(code.dense().T)
     cidx, vidx = cidx.to(DEV), vidx.to(DEV)
     etv = torch.as_tensor(oidx).reshape(-1).to(torch.int64).to(DEV)

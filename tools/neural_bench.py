@@ -54,7 +54,7 @@ def main():
     # through index_select expansions to (B, E) (what that shape cost before the per-variable kernels existed)
     for tag, fused, qc in (("qc", True, True), ("qc_var", True, True), ("qc_var_expand", True, True), ("fused", True, False),
                            ("composed", False, False)):
-        if tag.startswith("qc") and args.z not in (16, 32):
+        if tag.startswith("qc") and args.z not in (4, 8, 16, 32):
             continue
         var_shape = tag.startswith("qc_var")
         dec = LDPCNeuralDecoder(code.E, args.iters, 2, output_index_tensor=oidx if var_shape else None, fused=fused, qc=qc).to(dev)
